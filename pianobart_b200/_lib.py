@@ -1,0 +1,63 @@
+"""ctypes binding of libpianobart_b200.so (include/pianobart_b200.h).
+
+The library is the product path: if it is missing or fails to load this module raises -
+there is no CPU or PyTorch fallback anywhere in the package.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpianobart_b200.so")
+
+PB_GEMM_OUT_F32 = 1
+PB_GEMM_GELU = 2
+PB_GEMM_ATOMIC_ACC = 4
+PB_GEMM_RES_F32 = 8
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p),
+        ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("a_mn_major", C.c_int), ("b_mn_major", C.c_int),
+        ("lda", C.c_longlong), ("ldb", C.c_longlong), ("ldc", C.c_longlong), ("ldr", C.c_longlong),
+        ("batch_h", C.c_int), ("batch_b", C.c_int),
+        ("a_stride_h", C.c_longlong), ("a_stride_b", C.c_longlong),
+        ("b_stride_h", C.c_longlong), ("b_stride_b", C.c_longlong),
+        ("c_stride_h", C.c_longlong), ("c_stride_b", C.c_longlong),
+        ("r_stride_h", C.c_longlong), ("r_stride_b", C.c_longlong),
+        ("alpha", C.c_float), ("flags", C.c_int), ("split_k", C.c_int), ("causal", C.c_int),
+        ("block_n", C.c_int),
+    ]
+
+
+class PBError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PBError(
+                "libpianobart_b200.so not built (run `python -m pianobart_b200.build`); "
+                "there is no fallback path")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.pb_last_error.restype = C.c_char_p
+        _lib.pb_launch_count.restype = C.c_longlong
+        _lib.pb_reset_launch_count.restype = None
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise PBError("%s failed (%d): %s" % (what, rc, lib().pb_last_error().decode()))
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

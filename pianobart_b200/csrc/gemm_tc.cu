@@ -1,0 +1,489 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+//   C[b,h][m,n] = epi( alpha * sum_k A[b,h][m,k] * B[b,h][n,k] )        bf16 x bf16 -> fp32 (TMEM)
+//
+// Every dense contraction of the PianoBART hot path goes through this kernel:
+// the in_linear of the Octuple front end (reference PianoBart.py:68,71), the q/k/v/out
+// projections and fc1/fc2 of every BART layer (HF modeling_bart.py BartAttention / Bart*Layer),
+// the eight LM heads concatenated to N=1280 (reference model.py:119-126), the batched
+// QK^T / PV attention products, and all of their backward products (dX, dW).
+//
+// Design (B200-first, not a translation of anything in the reference, which has no kernels):
+//   * persistent grid, one CTA per SM, 192 threads = 6 warps with fixed roles:
+//       warp 0   TMA producer   (cp.async.bulk.tensor 4D, 128B swizzle, mbarrier complete_tx)
+//       warp 1   MMA issuer     (one elected thread issues tcgen05.mma, commits to mbarriers)
+//       warp 2-5 epilogue       (tcgen05.ld TMEM->registers, bias/GELU/residual, global stores)
+//   * CTA tile 128 x BLOCK_N (128 or 256), BLOCK_K = 64 bf16 = one 128-byte swizzle row,
+//     multi-stage smem ring (full/empty mbarriers), two TMEM accumulators (2 x BLOCK_N columns)
+//     so the epilogue of tile i overlaps the main loop of tile i+1.
+//   * both operands may be K-major (row = m or n, k contiguous) or MN-major (row = k, m/n
+//     contiguous) so that forward (X W^T), dX (dY W) and dW (dY^T X) all read the tensors in the
+//     layout they already have in HBM - no transposed copies.
+//   * 4-D tensor maps (inner, rows, h, b) give batched / strided operands (per-head attention
+//     slices of the fused QKV activation) without any gather kernel.
+//   * split-K with fp32 red.global.add for the dW products whose output tile count cannot fill
+//     148 SMs.
+#include "ptx.cuh"
+#include "pb_internal.h"
+
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstring>
+
+namespace pb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+struct GemmKParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks, kb_per_split, split_k;
+  int batch_h, batch_b;
+  long long total_units;
+  void* c;
+  long long ldc, c_stride_h, c_stride_b;
+  const float* bias;
+  const void* residual;
+  long long ldr, r_stride_h, r_stride_b;
+  float alpha;
+  int flags;
+  int causal;  // 1: skip tiles entirely above the diagonal (n0 > m0 + BLOCK_M - 1); 2: limit k range to m0+BLOCK_M
+};
+
+template <int BLOCK_N>
+struct SmemCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int DYN_BYTES = STAGES * STAGE_BYTES + 1024;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmKParams p) {
+  using Cfg = SmemCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 256 or 512: power of two >= 32
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // 1024-byte aligned tile ring (required by the 128B swizzle atom = 8 rows x 128 B).
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const long long units_per_batch = (long long)p.num_m_blocks * p.num_n_blocks * p.split_k;
+
+  // unit index -> (m_blk, n_blk, split, h, b); m fastest so concurrently running CTAs share a B tile.
+  auto decode = [&](long long w, int& m_blk, int& n_blk, int& split, int& h, int& b) {
+    long long batch = w / units_per_batch;
+    int r = (int)(w - batch * units_per_batch);
+    m_blk = r % p.num_m_blocks;
+    r /= p.num_m_blocks;
+    n_blk = r % p.num_n_blocks;
+    split = r / p.num_n_blocks;
+    h = (int)(batch % p.batch_h);
+    b = (int)(batch / p.batch_h);
+  };
+  auto k_range = [&](int m_blk, int n_blk, int split, int& kb0, int& kb1) {
+    kb0 = split * p.kb_per_split;
+    kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+    if (p.causal == 2) kb1 = min(kb1, ((m_blk + 1) * BLOCK_M + BLOCK_K - 1) / BLOCK_K);
+    if (p.causal == 1 && n_blk * BLOCK_N > m_blk * BLOCK_M + BLOCK_M - 1) kb1 = kb0;  // fully masked tile
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long w = blockIdx.x; w < p.total_units; w += gridDim.x) {
+        int m_blk, n_blk, split, h, b, kb0, kb1;
+        decode(w, m_blk, n_blk, split, h, b);
+        k_range(m_blk, n_blk, split, kb0, kb1);
+        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem_gen + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], k0, m0, h, b);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_4d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + 64 * j, k0, h, b);
+          }
+          if constexpr (!B_MN) {
+            tma_load_4d(sb, &tmap_b, &full_bar[stage], k0, n0, h, b);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_4d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + 64 * j, k0, h, b);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long w = blockIdx.x; w < p.total_units; w += gridDim.x) {
+        int m_blk, n_blk, split, h, b, kb0, kb1;
+        decode(w, m_blk, n_blk, split, h, b);
+        k_range(m_blk, n_blk, split, kb0, kb1);
+        if (kb1 <= kb0) continue;  // nothing to accumulate; the epilogue skips this unit as well
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            // K-major: 16 k-elements = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
+            // MN-major: 16 k-rows of 128 B = 2048 B; 64-wide mn blocks BLOCK_K*128 B apart.
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + kk * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                        : make_smem_desc_sw128(sa + kk * (UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + kk * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                        : make_smem_desc_sw128(sb + kk * (UMMA_K * 2), 16, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool out_f32 = p.flags & PB_GEMM_OUT_F32;
+    const bool do_gelu = p.flags & PB_GEMM_GELU;
+    const bool atomic_acc = p.flags & PB_GEMM_ATOMIC_ACC;
+    const bool res_f32 = p.flags & PB_GEMM_RES_F32;
+    for (long long w = blockIdx.x; w < p.total_units; w += gridDim.x) {
+      int m_blk, n_blk, split, h, b, kb0, kb1;
+      decode(w, m_blk, n_blk, split, h, b);
+      k_range(m_blk, n_blk, split, kb0, kb1);
+      if (kb1 <= kb0) continue;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const long long c_off = (long long)b * p.c_stride_b + (long long)h * p.c_stride_h + (long long)row * p.ldc;
+      const long long r_off = (long long)b * p.r_stride_b + (long long)h * p.r_stride_h + (long long)row * p.ldr;
+      const bool first_split = (split == 0);
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked body below
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + ch * 32), v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + ch * 32;
+        if (!row_ok || col0 >= p.N) continue;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
+        const bool full = (col0 + 32 <= p.N);
+        if (p.bias != nullptr && first_split) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              x[j] += bv.x; x[j + 1] += bv.y; x[j + 2] += bv.z; x[j + 3] += bv.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) x[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+        if (do_gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+        }
+        if (p.residual != nullptr && first_split) {
+          if (res_f32) {
+            const float* r = reinterpret_cast<const float*>(p.residual) + r_off + col0;
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) x[j] += r[j];
+          } else {
+            const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col0;
+            if (full && ((p.ldr & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(r + j);
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __bfloat1622float2(r2[t]);
+                  x[j + 2 * t] += f.x;
+                  x[j + 2 * t + 1] += f.y;
+                }
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) x[j] += __bfloat162float(r[j]);
+            }
+          }
+        }
+        if (out_f32) {
+          float* c = reinterpret_cast<float*>(p.c) + c_off + col0;
+          if (atomic_acc) {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(c + j, x[j]);
+          } else if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(c + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) c[j] = x[j];
+          }
+        } else {
+          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + col0;
+          if (full && ((p.ldc & 7) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(x[j + 2 * t], x[j + 2 * t + 1]);
+              *reinterpret_cast<uint4*>(c + j) = o;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) c[j] = __float2bfloat16(x[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t d[4];
+  uint64_t s[3];
+  uint32_t b0, b1;
+  bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    size_t hsh = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) hsh = (hsh ^ w[i]) * 1099511628211ull;
+    return hsh;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mutex;
+
+// inner = contiguous dimension (elements); rows = second dimension; ld = row stride (elements)
+static int make_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, long long ld, int nh,
+                     long long stride_h, int nb, long long stride_b, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return pb_set_error("cuTensorMapEncodeTiled entry point not available");
+  TmapKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.d[0] = inner; key.d[1] = rows; key.d[2] = (uint64_t)nh; key.d[3] = (uint64_t)nb;
+  const uint64_t full = (uint64_t)rows * (uint64_t)ld * 2ull;
+  key.s[0] = (uint64_t)ld * 2ull;
+  key.s[1] = nh > 1 ? (uint64_t)stride_h * 2ull : full;
+  key.s[2] = nb > 1 ? (uint64_t)stride_b * 2ull : full * (uint64_t)(nh > 1 ? 1 : 1);
+  key.b0 = box_inner; key.b1 = box_rows;
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mutex);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *out = it->second; return 0; }
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return pb_set_error("gemm operand base not 16-byte aligned");
+  for (int i = 0; i < 3; ++i)
+    if (key.s[i] % 16 != 0 || key.s[i] == 0) return pb_set_error("gemm operand stride not a multiple of 16 bytes");
+  cuuint64_t dims[4] = {key.d[0], key.d[1], key.d[2], key.d[3]};
+  cuuint64_t strides[3] = {key.s[0], key.s[1], key.s[2]};
+  cuuint32_t box[4] = {box_inner, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu ld=%lld", (int)r,
+             (unsigned long long)inner, (unsigned long long)rows, ld);
+    return pb_set_error(msg);
+  }
+  std::lock_guard<std::mutex> lk(g_tmap_mutex);
+  if (g_tmap_cache.size() > 4096) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
+  return 0;
+}
+
+static int g_num_sms = 0;
+int pb_num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, cudaStream_t stream) {
+  using Cfg = SmemCfg<BLOCK_N>;
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::DYN_BYTES);
+    if (e != cudaSuccess) return pb_set_cuda_error("cudaFuncSetAttribute(gemm_tc)", e);
+    attr_set = true;
+  }
+  long long grid = kp.total_units < (long long)pb_num_sms() ? kp.total_units : (long long)pb_num_sms();
+  kern<<<(unsigned)grid, NUM_THREADS, Cfg::DYN_BYTES, stream>>>(ta, tb, kp);
+  return pb_check_launch("gemm_tc_kernel");
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" int pb_gemm_bf16(const pb_gemm_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return pb_set_error("pb_gemm_bf16: empty problem");
+  const int nh = d->batch_h > 0 ? d->batch_h : 1, nb = d->batch_b > 0 ? d->batch_b : 1;
+  const int block_n = (d->block_n == 128 || d->block_n == 256) ? d->block_n : (d->N <= 128 ? 128 : 256);
+  GemmKParams kp;
+  kp.M = d->M; kp.N = d->N; kp.K = d->K;
+  kp.num_m_blocks = (d->M + BLOCK_M - 1) / BLOCK_M;
+  kp.num_n_blocks = (d->N + block_n - 1) / block_n;
+  kp.num_k_blocks = (d->K + BLOCK_K - 1) / BLOCK_K;
+  int split = d->split_k > 1 ? d->split_k : 1;
+  if (split > kp.num_k_blocks) split = kp.num_k_blocks;
+  kp.kb_per_split = (kp.num_k_blocks + split - 1) / split;
+  kp.split_k = (kp.num_k_blocks + kp.kb_per_split - 1) / kp.kb_per_split;
+  if (kp.split_k > 1 && !((d->flags & PB_GEMM_ATOMIC_ACC) && (d->flags & PB_GEMM_OUT_F32)))
+    return pb_set_error("pb_gemm_bf16: split_k > 1 needs OUT_F32|ATOMIC_ACC");
+  if ((d->flags & PB_GEMM_ATOMIC_ACC) && !(d->flags & PB_GEMM_OUT_F32))
+    return pb_set_error("pb_gemm_bf16: ATOMIC_ACC needs OUT_F32");
+  if ((d->flags & PB_GEMM_GELU) && kp.split_k > 1) return pb_set_error("pb_gemm_bf16: GELU with split_k");
+  kp.batch_h = nh; kp.batch_b = nb;
+  kp.total_units = (long long)kp.num_m_blocks * kp.num_n_blocks * kp.split_k * nh * nb;
+  kp.c = d->c; kp.ldc = d->ldc; kp.c_stride_h = d->c_stride_h; kp.c_stride_b = d->c_stride_b;
+  kp.bias = d->bias;
+  kp.residual = d->residual; kp.ldr = d->ldr; kp.r_stride_h = d->r_stride_h; kp.r_stride_b = d->r_stride_b;
+  kp.alpha = d->alpha;
+  kp.flags = d->flags;
+  kp.causal = d->causal;
+  if (kp.causal && kp.split_k > 1) return pb_set_error("pb_gemm_bf16: causal with split_k");
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!d->a_mn_major)
+    rc = make_tmap(&ta, d->a, (uint64_t)d->K, (uint64_t)d->M, d->lda, nh, d->a_stride_h, nb, d->a_stride_b, 64,
+                   BLOCK_M);
+  else
+    rc = make_tmap(&ta, d->a, (uint64_t)d->M, (uint64_t)d->K, d->lda, nh, d->a_stride_h, nb, d->a_stride_b, 64,
+                   BLOCK_K);
+  if (rc) return rc;
+  if (!d->b_mn_major)
+    rc = make_tmap(&tb, d->b, (uint64_t)d->K, (uint64_t)d->N, d->ldb, nh, d->b_stride_h, nb, d->b_stride_b, 64,
+                   (uint32_t)block_n);
+  else
+    rc = make_tmap(&tb, d->b, (uint64_t)d->N, (uint64_t)d->K, d->ldb, nh, d->b_stride_h, nb, d->b_stride_b, 64,
+                   BLOCK_K);
+  if (rc) return rc;
+
+  const int variant = (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
+  if (block_n == 256) {
+    switch (variant) {
+      case 0: return launch<256, false, false>(ta, tb, kp, stream);
+      case 1: return launch<256, false, true>(ta, tb, kp, stream);
+      case 2: return launch<256, true, false>(ta, tb, kp, stream);
+      default: return launch<256, true, true>(ta, tb, kp, stream);
+    }
+  } else {
+    switch (variant) {
+      case 0: return launch<128, false, false>(ta, tb, kp, stream);
+      case 1: return launch<128, false, true>(ta, tb, kp, stream);
+      case 2: return launch<128, true, false>(ta, tb, kp, stream);
+      default: return launch<128, true, true>(ta, tb, kp, stream);
+    }
+  }
+}
