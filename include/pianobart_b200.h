@@ -48,6 +48,8 @@ void pb_reset_launch_count(void);
 #define PB_GEMM_GELU 2       /* exact erf GELU after bias (HF ACT2FN["gelu"])                */
 #define PB_GEMM_ATOMIC_ACC 4 /* C += result with fp32 atomics (grad accumulation, split-K)   */
 #define PB_GEMM_RES_F32 8    /* residual is fp32 (default: same dtype as C)                  */
+#define PB_GEMM_AUX_PREACT 16 /* also store the pre-activation (after bias) to aux (dtype of C) */
+#define PB_GEMM_MUL_DGELU 32  /* multiply the result by gelu'(aux[m,n]) (fc1 backward)          */
 
 typedef struct pb_gemm_desc {
   const void* a;
@@ -66,6 +68,9 @@ typedef struct pb_gemm_desc {
   int split_k; /* >1 requires OUT_F32|ATOMIC_ACC */
   int causal;  /* 0 none; 1 skip output tiles with n > m (scores); 2 limit k to <= m (P.V)      */
   int block_n; /* 0 = auto, else 128 or 256 (tcgen05 path only)                                 */
+  void* aux;   /* see PB_GEMM_AUX_PREACT / PB_GEMM_MUL_DGELU; row stride ldaux, not batched      */
+  long long ldaux;
+  int r_row_mod; /* >0: residual row index = m % r_row_mod (learned position table broadcast over batch) */
 } pb_gemm_desc;
 
 /* bf16 operands, tcgen05/TMEM/TMA kernel */

@@ -13,6 +13,8 @@ PB_GEMM_OUT_F32 = 1
 PB_GEMM_GELU = 2
 PB_GEMM_ATOMIC_ACC = 4
 PB_GEMM_RES_F32 = 8
+PB_GEMM_AUX_PREACT = 16
+PB_GEMM_MUL_DGELU = 32
 
 
 class GemmDesc(C.Structure):
@@ -28,7 +30,7 @@ class GemmDesc(C.Structure):
         ("c_stride_h", C.c_longlong), ("c_stride_b", C.c_longlong),
         ("r_stride_h", C.c_longlong), ("r_stride_b", C.c_longlong),
         ("alpha", C.c_float), ("flags", C.c_int), ("split_k", C.c_int), ("causal", C.c_int),
-        ("block_n", C.c_int),
+        ("block_n", C.c_int), ("aux", C.c_void_p), ("ldaux", C.c_longlong), ("r_row_mod", C.c_int),
     ]
 
 

@@ -26,3 +26,14 @@ extern "C" const char* pb_last_error(void) { return g_err; }
 extern "C" int pb_version(void) { return 100; }
 extern "C" long long pb_launch_count(void) { return g_launches.load(); }
 extern "C" void pb_reset_launch_count(void) { g_launches.store(0); }
+
+static int g_num_sms = 0;
+int pb_num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}

@@ -50,6 +50,9 @@ struct GemmKParams {
   long long ldr, r_stride_h, r_stride_b;
   float alpha;
   int flags;
+  void* aux;
+  long long ldaux;
+  int r_row_mod;
   int causal;  // 1: skip tiles entirely above the diagonal (n0 > m0 + BLOCK_M - 1); 2: limit k range to m0+BLOCK_M
 };
 
@@ -63,6 +66,9 @@ struct SmemCfg {
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float z) {
+  return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+}
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -219,7 +225,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row = m_blk * BLOCK_M + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const long long c_off = (long long)b * p.c_stride_b + (long long)h * p.c_stride_h + (long long)row * p.ldc;
-      const long long r_off = (long long)b * p.r_stride_b + (long long)h * p.r_stride_h + (long long)row * p.ldr;
+      const long long r_off = (long long)b * p.r_stride_b + (long long)h * p.r_stride_h +
+                              (long long)(p.r_row_mod > 0 ? row % p.r_row_mod : row) * p.ldr;
       const bool first_split = (split == 0);
 #pragma unroll 1
       for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
@@ -245,9 +252,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + j < p.N) x[j] += __ldg(p.bias + col0 + j);
           }
         }
+        if (p.flags & PB_GEMM_AUX_PREACT) {
+          const long long a_off = (long long)row * p.ldaux + col0;
+          if (out_f32) {
+            float* ax = reinterpret_cast<float*>(p.aux) + a_off;
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) ax[j] = x[j];
+          } else {
+            __nv_bfloat16* ax = reinterpret_cast<__nv_bfloat16*>(p.aux) + a_off;
+            if (full && ((p.ldaux & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(x[j + 2 * t], x[j + 2 * t + 1]);
+                *reinterpret_cast<uint4*>(ax + j) = o;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) ax[j] = __float2bfloat16(x[j]);
+            }
+            // the activation below must see exactly what backward will re-read
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __bfloat162float(__float2bfloat16(x[j]));
+          }
+        }
         if (do_gelu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+        }
+        if (p.flags & PB_GEMM_MUL_DGELU) {
+          const long long a_off = (long long)row * p.ldaux + col0;
+          if (out_f32) {
+            const float* ax = reinterpret_cast<const float*>(p.aux) + a_off;
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) x[j] *= dgelu_erf(ax[j]);
+          } else {
+            const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(p.aux) + a_off;
+            if (full && ((p.ldaux & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(ax + j);
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __bfloat1622float2(r2[t]);
+                  x[j + 2 * t] *= dgelu_erf(f.x);
+                  x[j + 2 * t + 1] *= dgelu_erf(f.y);
+                }
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) x[j] *= dgelu_erf(__bfloat162float(ax[j]));
+            }
+          }
         }
         if (p.residual != nullptr && first_split) {
           if (res_f32) {
@@ -394,17 +453,6 @@ static int make_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return 0;
 }
 
-static int g_num_sms = 0;
-int pb_num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
 template <int BLOCK_N, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, cudaStream_t stream) {
   using Cfg = SmemCfg<BLOCK_N>;
@@ -451,6 +499,10 @@ extern "C" int pb_gemm_bf16(const pb_gemm_desc* d, void* stream_) {
   kp.alpha = d->alpha;
   kp.flags = d->flags;
   kp.causal = d->causal;
+  kp.aux = d->aux; kp.ldaux = d->ldaux;
+  kp.r_row_mod = d->r_row_mod;
+  if ((d->flags & (PB_GEMM_AUX_PREACT | PB_GEMM_MUL_DGELU)) && (d->aux == nullptr || nh * nb != 1 || kp.split_k > 1))
+    return pb_set_error("pb_gemm_bf16: aux epilogues need aux != NULL, no batching, no split_k");
   if (kp.causal && kp.split_k > 1) return pb_set_error("pb_gemm_bf16: causal with split_k");
 
   CUtensorMap ta, tb;

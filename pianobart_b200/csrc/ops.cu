@@ -1,0 +1,648 @@
+// HBM-bound kernels of the PianoBART path (everything that is not a dense contraction):
+// Octuple front end gather, LayerNorm, masked softmax, bias-gradient column sums, the fused
+// 8-head masked cross-entropy (+argmax accuracy, +dlogits), gradient-norm, HF-semantics AdamW,
+// dtype casts.  All kernels are templated on the activation type T (float = fp32 parity mode,
+// __nv_bfloat16 = production mode), use 16-byte vector accesses and fp32 arithmetic.
+#include "pb_internal.h"
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+template <typename T> struct Pack;
+template <> struct Pack<float> { static constexpr int N = 4; };
+template <> struct Pack<bf16> { static constexpr int N = 8; };
+
+__device__ __forceinline__ void load_pack(const float* p, float (&f)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+__device__ __forceinline__ void load_pack(const bf16* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void store_pack(float* p, const float (&f)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+__device__ __forceinline__ void store_pack(bf16* p, const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16(x); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int grid_for(long long work, int per_block, int max_blocks_per_sm = 16) {
+  long long b = (work + per_block - 1) / per_block;
+  long long cap = (long long)pb_num_sms() * max_blocks_per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------ Octuple front end
+// out[m, 256*i + c] = table[row_off[i] + ids[m,i], c]   (table already scaled by sqrt(256)=16)
+struct EmbedMeta { int row_off[8]; int n_tok[8]; };
+
+template <typename T, typename I>
+__global__ void __launch_bounds__(256) octuple_embed_fwd_kernel(const I* __restrict__ ids, const T* __restrict__ table,
+                                                                T* __restrict__ out, long long M, EmbedMeta meta,
+                                                                int* __restrict__ err) {
+  constexpr int N = Pack<T>::N;
+  constexpr int PACKS = 2048 / N;
+  for (long long m = blockIdx.x; m < M; m += gridDim.x) {
+    for (int pk = threadIdx.x; pk < PACKS; pk += blockDim.x) {
+      const int col = pk * N;
+      const int attr = col >> 8;
+      long long id = (long long)ids[m * 8 + attr];
+      if (id < 0 || id >= meta.n_tok[attr]) { if (err) atomicExch(err, 1); id = 0; }
+      float f[N];
+      load_pack(table + ((long long)(meta.row_off[attr] + id) << 8) + (col & 255), f);
+      store_pack(out + m * 2048 + col, f);
+    }
+  }
+}
+
+// dtable[row_off[i] + ids[m,i], c] += scale * dx[m, 256*i + c]
+template <typename T, typename I>
+__global__ void __launch_bounds__(256) octuple_embed_bwd_kernel(const I* __restrict__ ids, const T* __restrict__ dx,
+                                                                float* __restrict__ dtable, long long M, EmbedMeta meta,
+                                                                float scale) {
+  constexpr int N = Pack<T>::N;
+  constexpr int PACKS = 2048 / N;
+  for (long long m = blockIdx.x; m < M; m += gridDim.x) {
+    for (int pk = threadIdx.x; pk < PACKS; pk += blockDim.x) {
+      const int col = pk * N;
+      const int attr = col >> 8;
+      long long id = (long long)ids[m * 8 + attr];
+      if (id < 0 || id >= meta.n_tok[attr]) continue;
+      float f[N];
+      load_pack(dx + m * 2048 + col, f);
+      float* dst = dtable + ((long long)(meta.row_off[attr] + id) << 8) + (col & 255);
+#pragma unroll
+      for (int j = 0; j < N; ++j) atomicAdd(dst + j, f[j] * scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (one warp per row)
+constexpr int LN_MAXP = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, T* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            long long M, int d, float eps) {
+  constexpr int N = Pack<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = warp_global; row < M; row += nwarps) {
+    const T* xr = x + row * d;
+    float v[LN_MAXP][N];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXP; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < d) {
+        load_pack(xr + c, v[k]);
+#pragma unroll
+        for (int j = 0; j < N; ++j) s += v[k][j];
+      }
+    }
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXP; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < d) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) { const float t = v[k][j] - mean; q += t * t; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    T* yr = y + row * d;
+#pragma unroll
+    for (int k = 0; k < LN_MAXP; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < d) {
+        float o[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[j] = (v[k][j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
+        store_pack(yr + c, o);
+      }
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += dy*xhat, dbeta += dy
+template <typename T>
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in, T* __restrict__ dx,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            long long M, int d) {
+  constexpr int N = Pack<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float ag[LN_MAXP][N], ab[LN_MAXP][N];
+#pragma unroll
+  for (int k = 0; k < LN_MAXP; ++k)
+#pragma unroll
+    for (int j = 0; j < N; ++j) { ag[k][j] = 0.f; ab[k][j] = 0.f; }
+  for (long long row = warp_global; row < M; row += nwarps) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[LN_MAXP][N], g[LN_MAXP][N];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXP; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < d) {
+        float xv[N], dv[N];
+        load_pack(x + row * d + c, xv);
+        load_pack(dy + row * d + c, dv);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          xh[k][j] = (xv[j] - mean) * rstd;
+          g[k][j] = dv[j] * __ldg(gamma + c + j);
+          s1 += g[k][j];
+          s2 += g[k][j] * xh[k][j];
+          ag[k][j] += dv[j] * xh[k][j];
+          ab[k][j] += dv[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int k = 0; k < LN_MAXP; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < d) {
+        float o[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[j] = rstd * (g[k][j] - s1 - xh[k][j] * s2);
+        store_pack(dx + row * d + c, o);
+      }
+    }
+  }
+  // block-level reduction of the per-warp dgamma/dbeta partials, then one atomic per column per block
+  __shared__ float sh[4][32 * 8 + 1];
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int k = 0; k < LN_MAXP; ++k) {
+      const int c = (k * 32 + lane) * N;
+      __syncthreads();
+      if (c < d) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) sh[warp][lane * N + j] = pass == 0 ? ag[k][j] : ab[k][j];
+      }
+      __syncthreads();
+      if (warp == 0 && c < d) {
+        float* dst = (pass == 0 ? dgamma : dbeta) + c;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          float t = 0.f;
+          for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w][lane * N + j];
+          atomicAdd(dst + j, t);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ masked softmax (one warp per row)
+// scores fp32 [B,H,Sq,Sk] (already scaled) -> probs T.  key_keep uint8 [B,Sk] (may be NULL), causal: j <= i.
+constexpr int SM_MAX = 32;  // Sk <= 1024
+
+template <typename T>
+__global__ void __launch_bounds__(128) softmax_fwd_kernel(const float* __restrict__ s, T* __restrict__ p,
+                                                          const uint8_t* __restrict__ key_keep, int B, int H, int Sq,
+                                                          int Sk, int causal) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * H * Sq;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const int i = (int)(row % Sq);
+    const int b = (int)(row / ((long long)H * Sq));
+    const float* sr = s + row * Sk;
+    const uint8_t* kk = key_keep ? key_keep + (long long)b * Sk : nullptr;
+    const int jmax = causal ? min(Sk, i + 1) : Sk;
+    float v[SM_MAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < SM_MAX; ++k) {
+      const int j = k * 32 + lane;
+      float x = -INFINITY;
+      if (j < jmax && (!kk || kk[j])) x = sr[j];
+      v[k] = x;
+      mx = fmaxf(mx, x);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < SM_MAX; ++k) {
+      const float e = (v[k] == -INFINITY) ? 0.f : __expf(v[k] - mx);
+      v[k] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    T* pr = p + row * Sk;
+#pragma unroll
+    for (int k = 0; k < SM_MAX; ++k) {
+      const int j = k * 32 + lane;
+      if (j < Sk) pr[j] = from_f<T>(v[k] * inv);
+    }
+  }
+}
+
+// ds = p * (dp - sum_j p_j dp_j)  (positions outside the mask are forced to 0; dp there may be garbage)
+template <typename T>
+__global__ void __launch_bounds__(128) softmax_bwd_kernel(const T* __restrict__ p, const float* __restrict__ dp,
+                                                          T* __restrict__ ds, const uint8_t* __restrict__ key_keep,
+                                                          int B, int H, int Sq, int Sk, int causal) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * H * Sq;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const int i = (int)(row % Sq);
+    const int b = (int)(row / ((long long)H * Sq));
+    const uint8_t* kk = key_keep ? key_keep + (long long)b * Sk : nullptr;
+    const int jmax = causal ? min(Sk, i + 1) : Sk;
+    float pv[SM_MAX], dv[SM_MAX];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < SM_MAX; ++k) {
+      const int j = k * 32 + lane;
+      float a = 0.f, g = 0.f;
+      if (j < jmax && (!kk || kk[j])) { a = to_f(p[row * Sk + j]); g = dp[row * Sk + j]; }
+      pv[k] = a; dv[k] = g;
+      dot += a * g;
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int k = 0; k < SM_MAX; ++k) {
+      const int j = k * 32 + lane;
+      if (j < Sk) ds[row * Sk + j] = from_f<T>(pv[k] * (dv[k] - dot));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long M, int N,
+                                                     long long ld, int rows_per_block) {
+  constexpr int PN = Pack<T>::N;
+  const int pk = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = pk * PN;
+  if (c >= N) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float acc[PN];
+#pragma unroll
+  for (int j = 0; j < PN; ++j) acc[j] = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    float f[PN];
+    load_pack(x + r * ld + c, f);
+#pragma unroll
+    for (int j = 0; j < PN; ++j) acc[j] += f[j];
+  }
+#pragma unroll
+  for (int j = 0; j < PN; ++j) atomicAdd(out + c + j, acc[j]);
+}
+
+// ------------------------------------------------------------------ fused multi-head masked CE
+struct SegMeta { int nseg; int off[17]; float w[16]; };
+
+// logits fp32 [M, V] (V = off[nseg]); targets int32 [M, nseg]; mask float [M, nseg];
+// coef[s] = w[s] / (sum_w * den[s]) computed on the fly from den (global mask sums).
+// outputs: loss_num[s] += (lse - logit_t) * mask ; correct[s] += (argmax == t) * mask ;
+//          dlogits[m, j] = (softmax_j - [j==t]) * mask * coef[s] * grad_scale      (if dlogits != NULL)
+template <typename T>
+__global__ void __launch_bounds__(128) heads_ce_kernel(const float* __restrict__ logits, const int* __restrict__ targets,
+                                                       const float* __restrict__ mask, const float* __restrict__ den,
+                                                       float* __restrict__ loss_num, float* __restrict__ correct,
+                                                       T* __restrict__ dlogits, int* __restrict__ argmax_out, long long M,
+                                                       SegMeta meta, float sum_w, float grad_scale) {
+  const int lane = threadIdx.x & 31;
+  const int V = meta.off[meta.nseg];
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float acc_loss[16], acc_cor[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) { acc_loss[s] = 0.f; acc_cor[s] = 0.f; }
+  for (long long row = warp_global; row < M; row += nwarps) {
+    const float* lr = logits + row * V;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      if (s < meta.nseg) {
+        const int o = meta.off[s], n = meta.off[s + 1] - meta.off[s];
+        const int t = targets[row * meta.nseg + s];
+        const float mk = mask[row * meta.nseg + s];
+        float mx = -INFINITY;
+        int am = 0x7fffffff;
+        for (int j = lane; j < n; j += 32) {
+          const float x = lr[o + j];
+          if (x > mx) { mx = x; am = j; }
+        }
+        // warp argmax with lowest-index tie break (numpy argmax semantics, pretrain.py:165)
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+          const float omx = __shfl_xor_sync(0xffffffffu, mx, sft);
+          const int oam = __shfl_xor_sync(0xffffffffu, am, sft);
+          if (omx > mx || (omx == mx && oam < am)) { mx = omx; am = oam; }
+        }
+        float se = 0.f;
+        for (int j = lane; j < n; j += 32) se += __expf(lr[o + j] - mx);
+        se = warp_sum(se);
+        const float lse = mx + __logf(se);
+        const bool t_ok = (t >= 0 && t < n);
+        const float lt = t_ok ? lr[o + t] : 0.f;
+        if (lane == 0) {
+          if (mk != 0.f && t_ok) acc_loss[s] += (lse - lt) * mk;
+          if (t_ok && am == t) acc_cor[s] += mk;
+          if (argmax_out) argmax_out[row * meta.nseg + s] = am;
+        }
+        if (dlogits) {
+          const float coef = (mk != 0.f) ? mk * meta.w[s] / (sum_w * den[s]) * grad_scale : 0.f;
+          const float inv = 1.f / se;
+          for (int j = lane; j < n; j += 32) {
+            float g = 0.f;
+            if (coef != 0.f) g = (__expf(lr[o + j] - mx) * inv - ((j == t) ? 1.f : 0.f)) * coef;
+            dlogits[row * V + o + j] = from_f<T>(g);
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      if (s < meta.nseg) {
+        if (acc_loss[s] != 0.f) atomicAdd(loss_num + s, acc_loss[s]);
+        if (acc_cor[s] != 0.f) atomicAdd(correct + s, acc_cor[s]);
+      }
+    }
+  }
+}
+
+// den[s] = sum_m mask[m, s]
+__global__ void __launch_bounds__(256) mask_sums_kernel(const float* __restrict__ mask, float* __restrict__ den,
+                                                        long long M, int nseg) {
+  float acc = 0.f;
+  const long long total = M * nseg;
+  // thread handles a fixed segment: stride by a multiple of nseg
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long stride_al = stride - (stride % nseg);
+  if (tid >= stride_al) return;
+  const int s = (int)(tid % nseg);
+  for (long long i = tid; i < total; i += stride_al) acc += mask[i];
+  atomicAdd(den + s, acc);
+}
+
+// ------------------------------------------------------------------ optimizer
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float acc = 0.f;
+  const long long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = g4[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 << 2; i < n; ++i) acc += g[i] * g[i];
+  acc = warp_sum(acc);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    atomicAdd(out, t);
+  }
+}
+
+// HF transformers AdamW semantics (reference pretrain.py:76 `AdamW(lr, weight_decay=0.01)`, transformers
+// 4.29.2 optimization.py): eps added to sqrt(v) before bias correction, bias correction folded into the
+// step size, decoupled decay applied after the update with plain lr.  Gradient clipping
+// (pretrain.py:195, torch clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))) is folded in:
+// *gnorm_sq holds the squared global norm; max_norm <= 0 disables clipping.
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                    const float* __restrict__ g, bf16* __restrict__ p_bf16, long long n,
+                                                    float lr, float beta1, float beta2, float eps, float wd,
+                                                    float step_size, const float* __restrict__ gnorm_sq, float max_norm,
+                                                    float grad_scale, float bf16_scale) {
+  float coef = grad_scale;
+  if (max_norm > 0.f) {
+    const float norm = sqrtf(*gnorm_sq) * grad_scale;
+    coef *= fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    float pi = p[i] - step_size * mi / (sqrtf(vi) + eps);
+    pi -= lr * wd * pi;
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    if (p_bf16) p_bf16[i] = __float2bfloat16(pi * bf16_scale);
+  }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256) cast_scale_kernel(const float* __restrict__ src, TO* __restrict__ dst, long long n,
+                                                         float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_f<TO>(src[i] * scale);
+}
+template <typename TI>
+__global__ void __launch_bounds__(256) to_f32_kernel(const TI* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = to_f(src[i]);
+}
+
+}  // namespace
+
+#define PB_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+static int fill_embed_meta(EmbedMeta& meta, const int* n_tokens_host) {
+  int off = 0;
+  for (int i = 0; i < 8; ++i) { meta.row_off[i] = off; meta.n_tok[i] = n_tokens_host[i]; off += n_tokens_host[i]; }
+  return off;
+}
+
+extern "C" int pb_octuple_embed_fwd(const void* ids, int ids_int64, const void* table, void* out, long long M,
+                                    const int* n_tokens_host, int dtype, int* err_flag, void* stream) {
+  EmbedMeta meta;
+  fill_embed_meta(meta, n_tokens_host);
+  const int grid = grid_for(M, 1, 16);
+  if (dtype == PB_DTYPE_BF16) {
+    if (ids_int64) octuple_embed_fwd_kernel<bf16, long long><<<grid, 256, 0, PB_STREAM(stream)>>>((const long long*)ids, (const bf16*)table, (bf16*)out, M, meta, err_flag);
+    else octuple_embed_fwd_kernel<bf16, int><<<grid, 256, 0, PB_STREAM(stream)>>>((const int*)ids, (const bf16*)table, (bf16*)out, M, meta, err_flag);
+  } else {
+    if (ids_int64) octuple_embed_fwd_kernel<float, long long><<<grid, 256, 0, PB_STREAM(stream)>>>((const long long*)ids, (const float*)table, (float*)out, M, meta, err_flag);
+    else octuple_embed_fwd_kernel<float, int><<<grid, 256, 0, PB_STREAM(stream)>>>((const int*)ids, (const float*)table, (float*)out, M, meta, err_flag);
+  }
+  return pb_check_launch("octuple_embed_fwd");
+}
+
+extern "C" int pb_octuple_embed_bwd(const void* ids, int ids_int64, const void* dx, float* dtable, long long M,
+                                    const int* n_tokens_host, float scale, int dtype, void* stream) {
+  EmbedMeta meta;
+  fill_embed_meta(meta, n_tokens_host);
+  const int grid = grid_for(M, 1, 16);
+  if (dtype == PB_DTYPE_BF16) {
+    if (ids_int64) octuple_embed_bwd_kernel<bf16, long long><<<grid, 256, 0, PB_STREAM(stream)>>>((const long long*)ids, (const bf16*)dx, dtable, M, meta, scale);
+    else octuple_embed_bwd_kernel<bf16, int><<<grid, 256, 0, PB_STREAM(stream)>>>((const int*)ids, (const bf16*)dx, dtable, M, meta, scale);
+  } else {
+    if (ids_int64) octuple_embed_bwd_kernel<float, long long><<<grid, 256, 0, PB_STREAM(stream)>>>((const long long*)ids, (const float*)dx, dtable, M, meta, scale);
+    else octuple_embed_bwd_kernel<float, int><<<grid, 256, 0, PB_STREAM(stream)>>>((const int*)ids, (const float*)dx, dtable, M, meta, scale);
+  }
+  return pb_check_launch("octuple_embed_bwd");
+}
+
+static int ln_check(int d, int dtype) {
+  const int n = dtype == PB_DTYPE_BF16 ? 8 : 4;
+  if (d % n != 0 || d > LN_MAXP * 32 * n) return pb_set_error("layernorm: unsupported width (needs d % pack == 0 and d <= 1024 fp32 / 2048 bf16)");
+  return 0;
+}
+
+extern "C" int pb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                long long M, int d, float eps, int dtype, void* stream) {
+  if (ln_check(d, dtype)) return -1;
+  const int grid = grid_for(M, 4, 16);
+  if (dtype == PB_DTYPE_BF16)
+    layernorm_fwd_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, d, eps);
+  else
+    layernorm_fwd_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, d, eps);
+  return pb_check_launch("layernorm_fwd");
+}
+
+extern "C" int pb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                void* dx, float* dgamma, float* dbeta, long long M, int d, int dtype, void* stream) {
+  if (ln_check(d, dtype)) return -1;
+  const int grid = grid_for(M, 4 * 8, 4);
+  if (dtype == PB_DTYPE_BF16)
+    layernorm_bwd_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (bf16*)dx, dgamma, dbeta, M, d);
+  else
+    layernorm_bwd_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>((const float*)dy, (const float*)x, gamma, mean, rstd, (float*)dx, dgamma, dbeta, M, d);
+  return pb_check_launch("layernorm_bwd");
+}
+
+extern "C" int pb_softmax_fwd(const float* scores, void* probs, const uint8_t* key_keep, int B, int H, int Sq, int Sk,
+                              int causal, int dtype, void* stream) {
+  if (Sk > SM_MAX * 32) return pb_set_error("softmax: Sk > 1024 not supported");
+  const int grid = grid_for((long long)B * H * Sq, 4, 16);
+  if (dtype == PB_DTYPE_BF16)
+    softmax_fwd_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>(scores, (bf16*)probs, key_keep, B, H, Sq, Sk, causal);
+  else
+    softmax_fwd_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>(scores, (float*)probs, key_keep, B, H, Sq, Sk, causal);
+  return pb_check_launch("softmax_fwd");
+}
+
+extern "C" int pb_softmax_bwd(const void* probs, const float* dprobs, void* dscores, const uint8_t* key_keep, int B, int H,
+                              int Sq, int Sk, int causal, int dtype, void* stream) {
+  if (Sk > SM_MAX * 32) return pb_set_error("softmax: Sk > 1024 not supported");
+  const int grid = grid_for((long long)B * H * Sq, 4, 16);
+  if (dtype == PB_DTYPE_BF16)
+    softmax_bwd_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>((const bf16*)probs, dprobs, (bf16*)dscores, key_keep, B, H, Sq, Sk, causal);
+  else
+    softmax_bwd_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>((const float*)probs, dprobs, (float*)dscores, key_keep, B, H, Sq, Sk, causal);
+  return pb_check_launch("softmax_bwd");
+}
+
+extern "C" int pb_colsum(const void* x, float* out, long long M, int N, long long ld, int dtype, void* stream) {
+  const int pn = dtype == PB_DTYPE_BF16 ? 8 : 4;
+  if (N % pn != 0 || ld % pn != 0) return pb_set_error("colsum: N and ld must be multiples of the pack width");
+  const int packs = N / pn;
+  const int threads = 256;
+  const int gx = (packs + threads - 1) / threads;
+  int rows_per_block = 64;
+  long long gy = (M + rows_per_block - 1) / rows_per_block;
+  dim3 grid(gx, (unsigned)gy);
+  if (dtype == PB_DTYPE_BF16) colsum_kernel<bf16><<<grid, threads, 0, PB_STREAM(stream)>>>((const bf16*)x, out, M, N, ld, rows_per_block);
+  else colsum_kernel<float><<<grid, threads, 0, PB_STREAM(stream)>>>((const float*)x, out, M, N, ld, rows_per_block);
+  return pb_check_launch("colsum");
+}
+
+extern "C" int pb_heads_ce(const float* logits, const int* targets, const float* mask, const float* den, float* loss_num,
+                           float* correct, void* dlogits, int* argmax_out, long long M, int nseg,
+                           const int* seg_sizes_host, const float* weights_host, float grad_scale, int dtype,
+                           void* stream) {
+  if (nseg < 1 || nseg > 16) return pb_set_error("heads_ce: nseg must be in [1,16]");
+  SegMeta meta;
+  meta.nseg = nseg;
+  int off = 0;
+  float sw = 0.f;
+  for (int s = 0; s < nseg; ++s) { meta.off[s] = off; off += seg_sizes_host[s]; meta.w[s] = weights_host[s]; sw += weights_host[s]; }
+  meta.off[nseg] = off;
+  const int grid = grid_for(M, 4 * 4, 8);
+  if (dtype == PB_DTYPE_BF16)
+    heads_ce_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>(logits, targets, mask, den, loss_num, correct, (bf16*)dlogits, argmax_out, M, meta, sw, grad_scale);
+  else
+    heads_ce_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>(logits, targets, mask, den, loss_num, correct, (float*)dlogits, argmax_out, M, meta, sw, grad_scale);
+  return pb_check_launch("heads_ce");
+}
+
+extern "C" int pb_mask_sums(const float* mask, float* den, long long M, int nseg, void* stream) {
+  mask_sums_kernel<<<grid_for(M * nseg, 256 * 8, 4), 256, 0, PB_STREAM(stream)>>>(mask, den, M, nseg);
+  return pb_check_launch("mask_sums");
+}
+
+extern "C" int pb_sumsq(const float* g, long long n, float* out, void* stream) {
+  if ((reinterpret_cast<uintptr_t>(g) & 15) != 0) return pb_set_error("sumsq: pointer not 16-byte aligned");
+  sumsq_kernel<<<grid_for(n, 256 * 16, 8), 256, 0, PB_STREAM(stream)>>>(g, n, out);
+  return pb_check_launch("sumsq");
+}
+
+extern "C" int pb_adamw(float* p, float* m, float* v, const float* g, void* p_bf16, long long n, float lr, float beta1,
+                        float beta2, float eps, float wd, int step, const float* gnorm_sq, float max_norm,
+                        float grad_scale, float bf16_scale, void* stream) {
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  adamw_kernel<<<grid_for(n, 256 * 8, 8), 256, 0, PB_STREAM(stream)>>>(p, m, v, g, (bf16*)p_bf16, n, lr, beta1, beta2, eps, wd, step_size, gnorm_sq, max_norm, grad_scale, bf16_scale);
+  return pb_check_launch("adamw");
+}
+
+extern "C" int pb_cast_from_f32(const float* src, void* dst, long long n, float scale, int dtype, void* stream) {
+  const int grid = grid_for(n, 256 * 8, 8);
+  if (dtype == PB_DTYPE_BF16) cast_scale_kernel<bf16><<<grid, 256, 0, PB_STREAM(stream)>>>(src, (bf16*)dst, n, scale);
+  else cast_scale_kernel<float><<<grid, 256, 0, PB_STREAM(stream)>>>(src, (float*)dst, n, scale);
+  return pb_check_launch("cast_from_f32");
+}
+
+extern "C" int pb_cast_to_f32(const void* src, float* dst, long long n, int dtype, void* stream) {
+  const int grid = grid_for(n, 256 * 8, 8);
+  if (dtype == PB_DTYPE_BF16) to_f32_kernel<bf16><<<grid, 256, 0, PB_STREAM(stream)>>>((const bf16*)src, dst, n);
+  else to_f32_kernel<float><<<grid, 256, 0, PB_STREAM(stream)>>>((const float*)src, dst, n);
+  return pb_check_launch("cast_to_f32");
+}

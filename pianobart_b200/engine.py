@@ -1,0 +1,549 @@
+"""Execution engine: builds, for one (batch, seq) shape, the exact sequence of C-ABI kernel
+launches that computes the PianoBART backbone forward and backward, and replays it.
+
+Host side of the hot path: the arithmetic of
+PianoBart.forward (reference PianoBart.py:56-80) + HF BartModel (modeling_bart.py) + MLM heads
+(model.py:119-126) + masked CE (pretrain.py:112-118,179-189), expressed as a flat "plan" of
+ctypes calls into libpianobart_b200.so.  PyTorch is used for device memory and streams only;
+no torch operator computes anything on this path, and there is no fallback: the plan consists
+solely of library launches.
+
+Two dtype modes share the same plan:
+    fp32  - SIMT fp32 GEMM (pb_gemm_f32); parity mode (loss <= 1e-4 rel. vs the reference)
+    bf16  - tcgen05/TMEM/TMA GEMM (pb_gemm_bf16); production mode
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+PB_F32, PB_BF16 = 0, 1
+N_TOKENS = [262, 134, 135, 262, 134, 38, 260, 55]
+VOCAB = sum(N_TOKENS)  # 1280
+
+
+def _ptr(t, off_elems=0):
+    return t.data_ptr() + off_elems * t.element_size()
+
+
+class ParamLayout:
+    """Flat fp32 parameter layout.  Reference state_dict tensors are views
+    into one flat buffer arranged so that fused operands are contiguous:
+    q_proj|k_proj|v_proj weights of a block form one [3d, d] matrix (cross-attention: k|v form [2d, d]),
+    the eight word_emb tables form one [1280, 256] table, the eight LM heads one [1280, d] matrix."""
+
+    def __init__(self, d, enc_layers, dec_layers, ffn, max_pos, with_heads):
+        self.d, self.enc_layers, self.dec_layers, self.ffn, self.max_pos = d, enc_layers, dec_layers, ffn, max_pos
+        self.entries = {}   # name -> (offset, shape)
+        self.fused = {}     # fused name -> (offset, shape)
+        self.size = 0
+        self._build(with_heads)
+
+    def _add(self, name, shape, pad=True):
+        n = 1
+        for s in shape:
+            n *= s
+        off = self.size
+        self.entries[name] = (off, tuple(shape))
+        self.size += n
+        if pad:  # keep every (fused) tensor 32-byte aligned in fp32 / 16-byte aligned in bf16
+            self.size += (-self.size) % 8
+        return off
+
+    def _fuse(self, fname, names_shapes):
+        """Members are laid out back to back (no padding) so the group is one contiguous matrix/vector."""
+        off0 = self.size
+        rows = 0
+        for name, shape in names_shapes:
+            self._add(name, shape, pad=False)
+            rows += shape[0]
+        self.size += (-self.size) % 8
+        rest = names_shapes[0][1][1:]
+        self.fused[fname] = (off0, (rows,) + tuple(rest))
+
+    def _attn(self, pre, cross):
+        d = self.d
+        if not cross:
+            self._fuse(pre + '.wqkv', [(pre + '.q_proj.weight', (d, d)), (pre + '.k_proj.weight', (d, d)),
+                                       (pre + '.v_proj.weight', (d, d))])
+            self._fuse(pre + '.bqkv', [(pre + '.q_proj.bias', (d,)), (pre + '.k_proj.bias', (d,)),
+                                       (pre + '.v_proj.bias', (d,))])
+        else:
+            self._add(pre + '.q_proj.weight', (d, d))
+            self._add(pre + '.q_proj.bias', (d,))
+            self._fuse(pre + '.wkv', [(pre + '.k_proj.weight', (d, d)), (pre + '.v_proj.weight', (d, d))])
+            self._fuse(pre + '.bkv', [(pre + '.k_proj.bias', (d,)), (pre + '.v_proj.bias', (d,))])
+        self._add(pre + '.out_proj.weight', (d, d))
+        self._add(pre + '.out_proj.bias', (d,))
+
+    def _build(self, with_heads):
+        d, F = self.d, self.ffn
+        assert d % 8 == 0 and F % 8 == 0
+        self._fuse('emb', [('word_emb.%d.lut.weight' % i, (n, 256)) for i, n in enumerate(N_TOKENS)])
+        self.emb_end = self.size
+        self._add('encoder_linear.weight', (d, 2048))
+        self._add('encoder_linear.bias', (d,))
+        for side, nl in (('encoder', self.enc_layers), ('decoder', self.dec_layers)):
+            self._add('bart.%s.embed_positions.weight' % side, (self.max_pos + 2, d))
+            self._add('bart.%s.layernorm_embedding.weight' % side, (d,))
+            self._add('bart.%s.layernorm_embedding.bias' % side, (d,))
+            for l in range(nl):
+                pre = 'bart.%s.layers.%d' % (side, l)
+                self._attn(pre + '.self_attn', False)
+                self._add(pre + '.self_attn_layer_norm.weight', (d,))
+                self._add(pre + '.self_attn_layer_norm.bias', (d,))
+                if side == 'decoder':
+                    self._attn(pre + '.encoder_attn', True)
+                    self._add(pre + '.encoder_attn_layer_norm.weight', (d,))
+                    self._add(pre + '.encoder_attn_layer_norm.bias', (d,))
+                self._add(pre + '.fc1.weight', (F, d))
+                self._add(pre + '.fc1.bias', (F,))
+                self._add(pre + '.fc2.weight', (d, F))
+                self._add(pre + '.fc2.bias', (d,))
+                self._add(pre + '.final_layer_norm.weight', (d,))
+                self._add(pre + '.final_layer_norm.bias', (d,))
+        self.backbone_size = self.size
+        if with_heads:
+            self._fuse('heads.w', [('mask_lm.proj.%d.weight' % i, (n, d)) for i, n in enumerate(N_TOKENS)])
+            self._fuse('heads.b', [('mask_lm.proj.%d.bias' % i, (n,)) for i, n in enumerate(N_TOKENS)])
+
+    def off(self, name):
+        if name in self.entries:
+            return self.entries[name][0]
+        return self.fused[name][0]
+
+
+class Plan:
+    """A recorded list of (function, args) library calls; run() replays it on a stream."""
+
+    def __init__(self, dtype):
+        self.lib = L.lib()
+        self.dtype = dtype
+        self.ops = []
+        self._keep = []  # keep ctypes structs / arrays alive
+
+    def _add(self, name, fn, *args):
+        self.ops.append((name, fn, args))
+
+    def run(self, stream=None):
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+        for name, fn, args in self.ops:
+            rc = fn(*args, s)
+            if rc != 0:
+                raise L.PBError('%s failed (%d): %s' % (name, rc, self.lib.pb_last_error().decode()))
+        return len(self.ops)
+
+    # ---- op recorders ------------------------------------------------------------------
+    def gemm(self, a, b, c, M, N, K, lda, ldb, ldc, bias=0, residual=0, ldr=0, a_mn=0, b_mn=0, flags=0, alpha=1.0,
+             batch_h=1, batch_b=1, a_sh=0, a_sb=0, b_sh=0, b_sb=0, c_sh=0, c_sb=0, r_sh=0, r_sb=0, split_k=1,
+             causal=0, aux=0, ldaux=0, r_row_mod=0, name='gemm'):
+        d = L.GemmDesc()
+        d.a, d.b, d.c = a, b, c
+        d.bias = bias or None
+        d.residual = residual or None
+        d.M, d.N, d.K = M, N, K
+        d.a_mn_major, d.b_mn_major = a_mn, b_mn
+        d.lda, d.ldb, d.ldc, d.ldr = lda, ldb, ldc, ldr
+        d.batch_h, d.batch_b = batch_h, batch_b
+        d.a_stride_h, d.a_stride_b, d.b_stride_h, d.b_stride_b = a_sh, a_sb, b_sh, b_sb
+        d.c_stride_h, d.c_stride_b, d.r_stride_h, d.r_stride_b = c_sh, c_sb, r_sh, r_sb
+        d.alpha, d.flags, d.split_k, d.causal, d.block_n = alpha, flags, split_k, causal, 0
+        d.aux = aux or None
+        d.ldaux = ldaux
+        d.r_row_mod = r_row_mod
+        self._keep.append(d)
+        fn = self.lib.pb_gemm_bf16 if self.dtype == PB_BF16 else self.lib.pb_gemm_f32
+        self._add(name, fn, C.byref(d))
+
+    def wgrad(self, dy, x, dw, n_out, n_in, M, ld_dy, ld_x, name='wgrad'):
+        """dW[n_out, n_in] += dY[M, n_out]^T X[M, n_in]   (fp32 atomic accumulate, split-K)."""
+        units = ((n_out + 127) // 128) * ((n_in + 255) // 256)
+        kblocks = (M + 63) // 64
+        split = max(1, min((296 + units - 1) // units, max(1, kblocks // 4)))
+        self.gemm(dy, x, dw, n_out, n_in, M, ld_dy, ld_x, n_in, a_mn=1, b_mn=1,
+                  flags=L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC, split_k=split, name=name)
+
+    def embed_fwd(self, ids, table, out, M, ntok_arr, err=0):
+        self._add('embed_fwd', self.lib.pb_octuple_embed_fwd, C.c_void_p(ids), 0, C.c_void_p(table), C.c_void_p(out),
+                  C.c_longlong(M), ntok_arr, self.dtype, C.c_void_p(err or None))
+
+    def embed_bwd(self, ids, dx, dtable, M, ntok_arr, scale):
+        self._add('embed_bwd', self.lib.pb_octuple_embed_bwd, C.c_void_p(ids), 0, C.c_void_p(dx), C.c_void_p(dtable),
+                  C.c_longlong(M), ntok_arr, C.c_float(scale), self.dtype)
+
+    def ln_fwd(self, x, gamma, beta, y, mean, rstd, M, d):
+        self._add('ln_fwd', self.lib.pb_layernorm_fwd, C.c_void_p(x), C.c_void_p(gamma), C.c_void_p(beta),
+                  C.c_void_p(y), C.c_void_p(mean), C.c_void_p(rstd), C.c_longlong(M), d, C.c_float(1e-5), self.dtype)
+
+    def ln_bwd(self, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, d):
+        self._add('ln_bwd', self.lib.pb_layernorm_bwd, C.c_void_p(dy), C.c_void_p(x), C.c_void_p(gamma),
+                  C.c_void_p(mean), C.c_void_p(rstd), C.c_void_p(dx), C.c_void_p(dgamma), C.c_void_p(dbeta),
+                  C.c_longlong(M), d, self.dtype)
+
+    def softmax_fwd(self, s, p, keep, B, H, Sq, Sk, causal):
+        self._add('softmax_fwd', self.lib.pb_softmax_fwd, C.c_void_p(s), C.c_void_p(p), C.c_void_p(keep or None), B, H,
+                  Sq, Sk, causal, self.dtype)
+
+    def softmax_bwd(self, p, dp, ds, keep, B, H, Sq, Sk, causal):
+        self._add('softmax_bwd', self.lib.pb_softmax_bwd, C.c_void_p(p), C.c_void_p(dp), C.c_void_p(ds),
+                  C.c_void_p(keep or None), B, H, Sq, Sk, causal, self.dtype)
+
+    def colsum(self, x, out, M, N, ld):
+        self._add('colsum', self.lib.pb_colsum, C.c_void_p(x), C.c_void_p(out), C.c_longlong(M), N, C.c_longlong(ld),
+                  self.dtype)
+
+
+class Workspace:
+    """Named device buffers for one shape; torch only allocates the memory."""
+
+    def __init__(self, device):
+        self.device = device
+        self.t = {}
+
+    def get(self, name, shape, dtype):
+        key = name
+        t = self.t.get(key)
+        n = 1
+        for s in shape:
+            n *= s
+        if t is None:
+            t = torch.empty(max(n, 1), device=self.device, dtype=dtype)
+            self.t[key] = t
+        elif t.numel() < n or t.dtype != dtype:
+            # recorded plans hold raw pointers: a buffer must never be reallocated
+            raise RuntimeError('workspace buffer %s requested with a larger size/dtype than first allocated' % name)
+        return t
+
+    def bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.t.values())
+
+
+class BackboneGraph:
+    """Forward/backward launch plans of the PianoBART backbone (+ optional fused LM heads / CE)
+    for fixed shapes.  All tensors are addressed by raw device pointers."""
+
+    def __init__(self, layout, heads, dtype, device, B, S_enc, S_dec, w_act, w_f32, g_f32, with_heads,
+                 need_backward=True, dec_embed=None):
+        """w_act: working weights (activation dtype, emb region pre-scaled by 16); w_f32: fp32 master
+        (biases / LayerNorm parameters are read from it); g_f32: flat fp32 gradient buffer."""
+        self.lay, self.H, self.dtype, self.device = layout, heads, dtype, device
+        self.B, self.Se, self.Sd = B, S_enc, S_dec
+        self.d, self.F = layout.d, layout.ffn
+        self.hd = self.d // heads
+        assert self.d % heads == 0
+        if dtype == PB_BF16:
+            assert self.hd % 8 == 0, 'bf16 mode needs head_dim % 8 == 0 (TMA 16-byte strides)'
+        self.tdt = torch.bfloat16 if dtype == PB_BF16 else torch.float32
+        self.es = 2 if dtype == PB_BF16 else 4
+        self.w_act, self.w_f32, self.g_f32 = w_act, w_f32, g_f32
+        self.ws = Workspace(device)
+        self.with_heads = with_heads
+        self.has_dec = S_dec > 0
+        self.ntok_arr = (C.c_int * 8)(*N_TOKENS)
+        self.dec_embed = dec_embed
+        # inputs (filled by the caller before run)
+        self.enc_ids = torch.zeros(B * S_enc * 8, device=device, dtype=torch.int32)
+        self.enc_keep = torch.ones(B * S_enc, device=device, dtype=torch.uint8)
+        if self.has_dec:
+            self.dec_ids = torch.zeros(B * S_dec * 8, device=device, dtype=torch.int32)
+            self.dec_keep = torch.ones(B * S_dec, device=device, dtype=torch.uint8)
+        self.err_flag = torch.zeros(1, device=device, dtype=torch.int32)
+        self.fwd = Plan(dtype)
+        self.bwd = Plan(dtype) if need_backward else None
+        self._bwd_chunks = []
+        self._build()
+
+    # pointer helpers -----------------------------------------------------------------------
+    def W(self, name):   # working-dtype weight pointer
+        return _ptr(self.w_act, self.lay.off(name))
+
+    def Pf(self, name):  # fp32 master pointer (bias / LN params)
+        return _ptr(self.w_f32, self.lay.off(name))
+
+    def G(self, name):   # fp32 gradient pointer
+        return _ptr(self.g_f32, self.lay.off(name))
+
+    def buf(self, name, *shape, dtype=None):
+        return self.ws.get(name, shape, dtype or self.tdt)
+
+    # graph construction ----------------------------------------------------------------------
+    def _build(self):
+        B, d = self.B, self.d
+        f, bw = self.fwd, self.bwd
+        back = []  # list of closures recording backward ops; executed in reverse order at the end
+
+        # ---- encoder stream
+        Me = B * self.Se
+        enc_out, enc_back = self._stream('encoder', self.enc_ids, self.enc_keep, self.Se, None, None, 0)
+        self.enc_out = enc_out
+        if self.has_dec:
+            dec_out, dec_back = self._stream('decoder', self.dec_ids, self.dec_keep, self.Sd, enc_out, self.enc_keep,
+                                             self.Se)
+            self.out = dec_out
+        else:
+            self.out = enc_out
+        Mo = B * (self.Sd if self.has_dec else self.Se)
+        self.Mo = Mo
+        self.d_out = self.buf('d_out', Mo, d)  # gradient wrt last hidden state (input of backward)
+
+        if self.with_heads:
+            self.logits = self.buf('logits', Mo, VOCAB, dtype=torch.float32)
+            f.gemm(_ptr(self.out), self.W('heads.w'), _ptr(self.logits), Mo, VOCAB, d, d, d, VOCAB,
+                   bias=self.Pf('heads.b'), flags=L.PB_GEMM_OUT_F32, name='heads')
+
+        if bw is None:
+            return
+        # ---- backward: heads -> decoder -> encoder
+        if self.with_heads:
+            self.dlogits = self.buf('dlogits', Mo, VOCAB)
+            bw.colsum(_ptr(self.dlogits), self.G('heads.b'), Mo, VOCAB, VOCAB)
+            bw.wgrad(_ptr(self.dlogits), _ptr(self.out), self.G('heads.w'), VOCAB, d, Mo, VOCAB, d, name='dW_heads')
+            bw.gemm(_ptr(self.dlogits), self.W('heads.w'), _ptr(self.d_out), Mo, d, VOCAB, VOCAB, d, d, b_mn=1,
+                    name='dH_heads')
+        if self.has_dec:
+            d_enc_out = self.buf('d_enc_out', Me, d)
+            dec_back(self.d_out, d_enc_out)
+            enc_back(d_enc_out, None)
+        else:
+            enc_back(self.d_out, None)
+
+    def _stream(self, side, ids, keep, S, enc_out, enc_keep, S_enc):
+        """Records forward ops of one stack (front end + layers); returns (output tensor,
+        backward recorder(d_out, d_enc_out))."""
+        B, d, F, H, hd = self.B, self.d, self.F, self.H, self.hd
+        f = self.fwd
+        M = B * S
+        pre = 'bart.%s' % side
+        nl = self.lay.enc_layers if side == 'encoder' else self.lay.dec_layers
+        is_dec = side == 'decoder'
+        scale = hd ** -0.5
+        T = self.tdt
+        OUT32 = L.PB_GEMM_OUT_F32
+        nm = lambda s: '%s.%s' % (side, s)
+
+        custom_dec = is_dec and self.dec_embed is not None
+        # ---- front end (PianoBart.py:60-71) + positions + layernorm_embedding
+        Y0 = self.buf(nm('Y0'), M, d)
+        H0 = self.buf(nm('H0'), M, d)
+        st0 = self.buf(nm('st0'), 2, M, dtype=torch.float32)
+        if not custom_dec:
+            X = self.buf(nm('X'), M, 2048)
+            f.embed_fwd(_ptr(ids), self.W('emb'), _ptr(X), M, self.ntok_arr, _ptr(self.err_flag))
+            f.gemm(_ptr(X), self.W('encoder_linear.weight'), _ptr(Y0), M, d, 2048, 2048, 2048, d,
+                   bias=self.Pf('encoder_linear.bias'), residual=self.W(pre + '.embed_positions.weight') + 2 * d * self.es,
+                   ldr=d, r_row_mod=S, name=nm('in_linear'))
+        else:
+            self.dec_embed.record_forward(self, f, Y0, M, S)
+        f.ln_fwd(_ptr(Y0), self.Pf(pre + '.layernorm_embedding.weight'), self.Pf(pre + '.layernorm_embedding.bias'),
+                 _ptr(H0), _ptr(st0), _ptr(st0, M), M, d)
+
+        Smax = max(self.Se, self.Sd)
+        Mmax = B * Smax
+        scores = self.buf('scores', B * H * Smax * Smax, dtype=torch.float32)  # shared fp32 scratch
+        layers = []
+        h_in = H0
+        for l in range(nl):
+            lp = '%s.layers.%d' % (pre, l)
+            ln = lambda s: '%s.L%d.%s' % (side, l, s)
+            rec = {}
+            # -- self attention
+            QKV = self.buf(ln('QKV'), M, 3 * d)
+            Pm = self.buf(ln('P'), B * H * S * S)
+            O = self.buf(ln('O'), M, d)
+            A = self.buf(ln('A'), M, d)
+            H1 = self.buf(ln('H1'), M, d)
+            st1 = self.buf(ln('st1'), 2, M, dtype=torch.float32)
+            f.gemm(_ptr(h_in), self.W(lp + '.self_attn.wqkv'), _ptr(QKV), M, 3 * d, d, d, d, 3 * d,
+                   bias=self.Pf(lp + '.self_attn.bqkv'), name=ln('qkv'))
+            f.gemm(_ptr(QKV), _ptr(QKV, d), _ptr(scores), S, S, hd, 3 * d, 3 * d, S, flags=OUT32, alpha=scale,
+                   batch_h=H, batch_b=B, a_sh=hd, a_sb=S * 3 * d, b_sh=hd, b_sb=S * 3 * d, c_sh=S * S, c_sb=H * S * S,
+                   causal=1 if is_dec else 0, name=ln('qk'))
+            f.softmax_fwd(_ptr(scores), _ptr(Pm), _ptr(keep), B, H, S, S, 1 if is_dec else 0)
+            f.gemm(_ptr(Pm), _ptr(QKV, 2 * d), _ptr(O), S, hd, S, S, 3 * d, d, b_mn=1, batch_h=H, batch_b=B,
+                   a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd, c_sb=S * d,
+                   causal=2 if is_dec else 0, name=ln('pv'))
+            f.gemm(_ptr(O), self.W(lp + '.self_attn.out_proj.weight'), _ptr(A), M, d, d, d, d, d,
+                   bias=self.Pf(lp + '.self_attn.out_proj.bias'), residual=_ptr(h_in), ldr=d, name=ln('out_proj'))
+            f.ln_fwd(_ptr(A), self.Pf(lp + '.self_attn_layer_norm.weight'), self.Pf(lp + '.self_attn_layer_norm.bias'),
+                     _ptr(H1), _ptr(st1), _ptr(st1, M), M, d)
+            rec.update(h_in=h_in, QKV=QKV, P=Pm, O=O, A=A, H1=H1, st1=st1)
+            h_mid = H1
+            if is_dec:
+                Me = B * S_enc
+                Qc = self.buf(ln('Qc'), M, d)
+                KVc = self.buf(ln('KVc'), Me, 2 * d)
+                Pc = self.buf(ln('Pc'), B * H * S * S_enc)
+                Oc = self.buf(ln('Oc'), M, d)
+                Ac = self.buf(ln('Ac'), M, d)
+                Hc = self.buf(ln('Hc'), M, d)
+                stc = self.buf(ln('stc'), 2, M, dtype=torch.float32)
+                ca = lp + '.encoder_attn'
+                f.gemm(_ptr(H1), self.W(ca + '.q_proj.weight'), _ptr(Qc), M, d, d, d, d, d,
+                       bias=self.Pf(ca + '.q_proj.bias'), name=ln('q_c'))
+                f.gemm(_ptr(enc_out), self.W(ca + '.wkv'), _ptr(KVc), Me, 2 * d, d, d, d, 2 * d,
+                       bias=self.Pf(ca + '.bkv'), name=ln('kv_c'))
+                f.gemm(_ptr(Qc), _ptr(KVc), _ptr(scores), S, S_enc, hd, d, 2 * d, S_enc, flags=OUT32, alpha=scale,
+                       batch_h=H, batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=S * S_enc,
+                       c_sb=H * S * S_enc, name=ln('qk_c'))
+                f.softmax_fwd(_ptr(scores), _ptr(Pc), _ptr(enc_keep), B, H, S, S_enc, 0)
+                f.gemm(_ptr(Pc), _ptr(KVc, d), _ptr(Oc), S, hd, S_enc, S_enc, 2 * d, d, b_mn=1, batch_h=H, batch_b=B,
+                       a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=hd, c_sb=S * d,
+                       name=ln('pv_c'))
+                f.gemm(_ptr(Oc), self.W(ca + '.out_proj.weight'), _ptr(Ac), M, d, d, d, d, d,
+                       bias=self.Pf(ca + '.out_proj.bias'), residual=_ptr(H1), ldr=d, name=ln('out_proj_c'))
+                f.ln_fwd(_ptr(Ac), self.Pf(lp + '.encoder_attn_layer_norm.weight'),
+                         self.Pf(lp + '.encoder_attn_layer_norm.bias'), _ptr(Hc), _ptr(stc), _ptr(stc, M), M, d)
+                rec.update(Qc=Qc, KVc=KVc, Pc=Pc, Oc=Oc, Ac=Ac, Hc=Hc, stc=stc)
+                h_mid = Hc
+            # -- feed forward
+            Z = self.buf(ln('Z'), M, F)
+            Gt = self.buf(ln('G'), M, F)
+            A2 = self.buf(ln('A2'), M, d)
+            Hn = self.buf(ln('Hn'), M, d)
+            st2 = self.buf(ln('st2'), 2, M, dtype=torch.float32)
+            f.gemm(_ptr(h_mid), self.W(lp + '.fc1.weight'), _ptr(Gt), M, F, d, d, d, F, bias=self.Pf(lp + '.fc1.bias'),
+                   flags=L.PB_GEMM_GELU | L.PB_GEMM_AUX_PREACT, aux=_ptr(Z), ldaux=F, name=ln('fc1'))
+            f.gemm(_ptr(Gt), self.W(lp + '.fc2.weight'), _ptr(A2), M, d, F, F, F, d, bias=self.Pf(lp + '.fc2.bias'),
+                   residual=_ptr(h_mid), ldr=d, name=ln('fc2'))
+            f.ln_fwd(_ptr(A2), self.Pf(lp + '.final_layer_norm.weight'), self.Pf(lp + '.final_layer_norm.bias'),
+                     _ptr(Hn), _ptr(st2), _ptr(st2, M), M, d)
+            rec.update(h_mid=h_mid, Z=Z, G=Gt, A2=A2, Hn=Hn, st2=st2, lp=lp)
+            layers.append(rec)
+            h_in = Hn
+        out = h_in
+
+        def record_backward(d_out, d_enc_out):
+            """d_out: gradient wrt `out` (overwritten); d_enc_out: accumulator for the encoder output grad."""
+            bw = self.bwd
+            # scratch gradient buffers shared by all layers of both stacks
+            dA = self.buf('g.dA', Mmax, d)
+            dZ = self.buf('g.dZ', Mmax, F)
+            dH1 = self.buf('g.dH1', Mmax, d)
+            dO = self.buf('g.dO', Mmax, d)
+            dQKV = self.buf('g.dQKV', Mmax, 3 * d)
+            dcur = d_out
+            dnext = self.buf('g.dH_' + side, M, d)
+            first_cross = True
+            for l in reversed(range(nl)):
+                r = layers[l]
+                lp = r['lp']
+                ln = lambda s: '%s.L%d.%s' % (side, l, s)
+                # -- FFN backward
+                bw.ln_bwd(_ptr(dcur), _ptr(r['A2']), self.Pf(lp + '.final_layer_norm.weight'), _ptr(r['st2']),
+                          _ptr(r['st2'], M), _ptr(dA), self.G(lp + '.final_layer_norm.weight'),
+                          self.G(lp + '.final_layer_norm.bias'), M, d)
+                bw.colsum(_ptr(dA), self.G(lp + '.fc2.bias'), M, d, d)
+                bw.wgrad(_ptr(dA), _ptr(r['G']), self.G(lp + '.fc2.weight'), d, F, M, d, F, name=ln('dW_fc2'))
+                bw.gemm(_ptr(dA), self.W(lp + '.fc2.weight'), _ptr(dZ), M, F, d, d, F, F, b_mn=1,
+                        flags=L.PB_GEMM_MUL_DGELU, aux=_ptr(r['Z']), ldaux=F, name=ln('dZ'))
+                bw.colsum(_ptr(dZ), self.G(lp + '.fc1.bias'), M, F, F)
+                bw.wgrad(_ptr(dZ), _ptr(r['h_mid']), self.G(lp + '.fc1.weight'), F, d, M, F, d, name=ln('dW_fc1'))
+                bw.gemm(_ptr(dZ), self.W(lp + '.fc1.weight'), _ptr(dH1), M, d, F, F, d, d, b_mn=1, residual=_ptr(dA),
+                        ldr=d, name=ln('dH_mid'))
+                dmid = dH1
+                if is_dec:
+                    Me = B * S_enc
+                    ca = lp + '.encoder_attn'
+                    dQc = self.buf('g.dQc', Mmax, d)
+                    dKVc = self.buf('g.dKVc', Mmax, 2 * d)
+                    bw.ln_bwd(_ptr(dmid), _ptr(r['Ac']), self.Pf(lp + '.encoder_attn_layer_norm.weight'),
+                              _ptr(r['stc']), _ptr(r['stc'], M), _ptr(dA), self.G(lp + '.encoder_attn_layer_norm.weight'),
+                              self.G(lp + '.encoder_attn_layer_norm.bias'), M, d)
+                    bw.colsum(_ptr(dA), self.G(ca + '.out_proj.bias'), M, d, d)
+                    bw.wgrad(_ptr(dA), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
+                    bw.gemm(_ptr(dA), self.W(ca + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dOc'))
+                    # dP = dO V^T ; dV = P^T dO ; dS = softmax'(P, dP) ; dQ = scale dS K ; dK = scale dS^T Q
+                    bw.gemm(_ptr(dO), _ptr(r['KVc'], d), _ptr(scores), S, S_enc, hd, d, 2 * d, S_enc, flags=OUT32,
+                            batch_h=H, batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=S * S_enc,
+                            c_sb=H * S * S_enc, name=ln('dP_c'))
+                    bw.gemm(_ptr(r['Pc']), _ptr(dO), _ptr(dKVc, d), S_enc, hd, S, S_enc, d, 2 * d, a_mn=1, b_mn=1,
+                            batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S * d, c_sh=hd,
+                            c_sb=S_enc * 2 * d, name=ln('dV_c'))
+                    bw.softmax_bwd(_ptr(r['Pc']), _ptr(scores), _ptr(r['Pc']), _ptr(enc_keep), B, H, S, S_enc, 0)
+                    bw.gemm(_ptr(r['Pc']), _ptr(r['KVc']), _ptr(dQc), S, hd, S_enc, S_enc, 2 * d, d, b_mn=1, alpha=scale,
+                            batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S_enc * 2 * d,
+                            c_sh=hd, c_sb=S * d, name=ln('dQ_c'))
+                    bw.gemm(_ptr(r['Pc']), _ptr(r['Qc']), _ptr(dKVc), S_enc, hd, S, S_enc, d, 2 * d, a_mn=1, b_mn=1,
+                            alpha=scale, batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S * d,
+                            c_sh=hd, c_sb=S_enc * 2 * d, name=ln('dK_c'))
+                    bw.colsum(_ptr(dQc), self.G(ca + '.q_proj.bias'), M, d, d)
+                    bw.wgrad(_ptr(dQc), _ptr(r['H1']), self.G(ca + '.q_proj.weight'), d, d, M, d, d, name=ln('dW_qc'))
+                    bw.colsum(_ptr(dKVc), self.G(ca + '.bkv'), Me, 2 * d, 2 * d)
+                    bw.wgrad(_ptr(dKVc), _ptr(enc_out), self.G(ca + '.wkv'), 2 * d, d, Me, 2 * d, d, name=ln('dW_kvc'))
+                    bw.gemm(_ptr(dKVc), self.W(ca + '.wkv'), _ptr(d_enc_out), Me, d, 2 * d, 2 * d, d, d, b_mn=1,
+                            residual=0 if first_cross else _ptr(d_enc_out), ldr=d, name=ln('dEnc'))
+                    first_cross = False
+                    dmid2 = self.buf('g.dH1b', Mmax, d)
+                    bw.gemm(_ptr(dQc), self.W(ca + '.q_proj.weight'), _ptr(dmid2), M, d, d, d, d, d, b_mn=1,
+                            residual=_ptr(dA), ldr=d, name=ln('dH1_c'))
+                    dmid = dmid2
+                # -- self attention backward
+                sa = lp + '.self_attn'
+                cz = 1 if is_dec else 0
+                bw.ln_bwd(_ptr(dmid), _ptr(r['A']), self.Pf(lp + '.self_attn_layer_norm.weight'), _ptr(r['st1']),
+                          _ptr(r['st1'], M), _ptr(dA), self.G(lp + '.self_attn_layer_norm.weight'),
+                          self.G(lp + '.self_attn_layer_norm.bias'), M, d)
+                bw.colsum(_ptr(dA), self.G(sa + '.out_proj.bias'), M, d, d)
+                bw.wgrad(_ptr(dA), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
+                bw.gemm(_ptr(dA), self.W(sa + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dO'))
+                QKV, Pm = r['QKV'], r['P']
+                bw.gemm(_ptr(dO), _ptr(QKV, 2 * d), _ptr(scores), S, S, hd, d, 3 * d, S, flags=OUT32, batch_h=H,
+                        batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S * 3 * d, c_sh=S * S, c_sb=H * S * S, causal=cz,
+                        name=ln('dP'))
+                bw.gemm(_ptr(Pm), _ptr(dO), _ptr(dQKV, 2 * d), S, hd, S, S, d, 3 * d, a_mn=1, b_mn=1, batch_h=H,
+                        batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * d, c_sh=hd, c_sb=S * 3 * d,
+                        name=ln('dV'))
+                bw.softmax_bwd(_ptr(Pm), _ptr(scores), _ptr(Pm), _ptr(keep), B, H, S, S, cz)
+                bw.gemm(_ptr(Pm), _ptr(QKV, d), _ptr(dQKV), S, hd, S, S, 3 * d, 3 * d, b_mn=1, alpha=scale, batch_h=H,
+                        batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd, c_sb=S * 3 * d,
+                        causal=2 if is_dec else 0, name=ln('dQ'))
+                bw.gemm(_ptr(Pm), _ptr(QKV), _ptr(dQKV, d), S, hd, S, S, 3 * d, 3 * d, a_mn=1, b_mn=1, alpha=scale,
+                        batch_h=H, batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd,
+                        c_sb=S * 3 * d, name=ln('dK'))
+                bw.colsum(_ptr(dQKV), self.G(sa + '.bqkv'), M, 3 * d, 3 * d)
+                bw.wgrad(_ptr(dQKV), _ptr(r['h_in']), self.G(sa + '.wqkv'), 3 * d, d, M, 3 * d, d, name=ln('dW_qkv'))
+                bw.gemm(_ptr(dQKV), self.W(sa + '.wqkv'), _ptr(dnext), M, d, 3 * d, 3 * d, d, d, b_mn=1,
+                        residual=_ptr(dA), ldr=d, name=ln('dH_in'))
+                dcur, dnext = dnext, dcur
+            # -- front end backward
+            dY0 = dA
+            bw.ln_bwd(_ptr(dcur), _ptr(Y0), self.Pf(pre + '.layernorm_embedding.weight'), _ptr(st0), _ptr(st0, M),
+                      _ptr(dY0), self.G(pre + '.layernorm_embedding.weight'), self.G(pre + '.layernorm_embedding.bias'),
+                      M, d)
+            # d pos[s+2] += sum_b dY0[b, s]  == column sums of dY0 viewed as [B, S*d]
+            bw.colsum(_ptr(dY0), self.G(pre + '.embed_positions.weight') + 2 * d * 4, B, S * d, S * d)
+            if not custom_dec:
+                bw.colsum(_ptr(dY0), self.G('encoder_linear.bias'), M, d, d)
+                bw.wgrad(_ptr(dY0), _ptr(X), self.G('encoder_linear.weight'), d, 2048, M, d, 2048, name=nm('dW_in'))
+                dX = self.buf('g.dX', Mmax, 2048)
+                bw.gemm(_ptr(dY0), self.W('encoder_linear.weight'), _ptr(dX), M, 2048, d, d, 2048, 2048, b_mn=1,
+                        name=nm('dX'))
+                bw.embed_bwd(_ptr(ids), _ptr(dX), self.G('emb'), M, self.ntok_arr, 16.0)
+            else:
+                self.dec_embed.record_backward(self, bw, dY0, M, S)
+
+        return out, record_backward
+
+    # ---------------------------------------------------------------------------------------
+    def set_inputs(self, enc_ids, enc_keep, dec_ids=None, dec_keep=None):
+        """Copies (device-to-device, or host-to-device from pinned memory) the step inputs into the
+        graph's static input buffers.  ids: (B,S,8) integer tensor; keep: (B,S) any dtype, non-zero = keep."""
+        self.enc_ids.copy_(enc_ids.reshape(-1), non_blocking=True)
+        if enc_keep is None:
+            self.enc_keep.fill_(1)
+        else:
+            self.enc_keep.copy_((enc_keep.reshape(-1) != 0), non_blocking=True)
+        if self.has_dec:
+            self.dec_ids.copy_(dec_ids.reshape(-1), non_blocking=True)
+            if dec_keep is None:
+                self.dec_keep.fill_(1)
+            else:
+                self.dec_keep.copy_((dec_keep.reshape(-1) != 0), non_blocking=True)
+
+    def forward(self):
+        return self.fwd.run()
+
+    def backward(self):
+        return self.bwd.run()

@@ -1,0 +1,303 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REAL REFERENCE (read-only at /root/reference)
+in the build container.  The reference cannot travel to the GPU box, the fixtures can.
+
+    python tools/make_golden.py            # writes tests/golden/
+
+The reference is imported unmodified; the only harness shims are
+  * transformers.AdamW = torch.optim.AdamW   (removed from transformers >= 5; pretrain.py:3 imports it)
+  * weights are overwritten with oracle.params.make_params(...) so fixtures store (config, seed)
+    instead of weights.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get('PIANOBART_REF', '/root/reference')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+os.chdir(REF)
+
+import transformers  # noqa: E402
+
+transformers.AdamW = torch.optim.AdamW
+import pickle  # noqa: E402
+
+from transformers import BartConfig  # noqa: E402
+
+import PianoBart as ref_pb  # noqa: E402
+import model as ref_model  # noqa: E402
+
+sys.modules['transformers'].AdamW = torch.optim.AdamW  # the lazy module object may have been replaced
+import pretrain as ref_pretrain  # noqa: E402
+
+from oracle import params as P  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+with open(os.path.join(REF, 'Data', 'Octuple.pkl'), 'rb') as f:
+    E2W, W2E = pickle.load(f)
+
+torch.set_num_threads(8)
+
+
+def build_ref(cfg, seed, suppress_specials=False):
+    d, el, dl, heads, ffn, max_pos = cfg
+    bc = BartConfig(max_position_embeddings=max_pos, d_model=d, encoder_layers=el, decoder_layers=dl,
+                    encoder_ffn_dim=ffn, decoder_ffn_dim=ffn, encoder_attention_heads=heads,
+                    decoder_attention_heads=heads)
+    pb = ref_pb.PianoBart(bc, E2W, W2E)
+    lm = ref_model.PianoBartLM(pb)
+    prm = P.make_params(d, el, dl, ffn, max_pos, seed)
+    if suppress_specials:
+        P.suppress_specials(prm)
+    sd = lm.state_dict()
+    for k, v in prm.items():
+        kk = k if k.startswith('mask_lm') else 'pianobart.' + k
+        assert kk in sd and tuple(sd[kk].shape) == v.shape, (kk, v.shape)
+        sd[kk] = torch.from_numpy(v.copy())
+    lm.load_state_dict(sd)
+    lm.eval()
+    return pb, lm
+
+
+def ref_pretrain_loss(pb, y, ori, loss_mask):
+    """pretrain.py:179-189 executed with the reference's own objects/ordering."""
+    loss_func = torch.nn.CrossEntropyLoss(reduction='none')
+    losses, n_tok = [], []
+    for i, etype in enumerate(pb.e2w):
+        n_tok.append(len(pb.e2w[etype]))
+        pred = y[i].permute(0, 2, 1)
+        l = loss_func(pred, ori[..., i]) * loss_mask[:, :, i]
+        losses.append(torch.sum(l) / torch.sum(loss_mask[:, :, i]))
+    total = sum(x * w for x, w in zip(losses, n_tok)) / sum(n_tok)
+    return total, losses
+
+
+def ref_acc(y, ori, loss_mask):
+    accs = []
+    for i in range(8):
+        out = torch.from_numpy(np.argmax(y[i].detach().numpy(), axis=-1))
+        accs.append((torch.sum((ori[:, :, i] == out).float() * loss_mask[:, :, i]) / torch.sum(loss_mask[:, :, i])).item())
+    return accs
+
+
+def golden_forward(name, cfg, seed, B, S, full_outputs, grad_full_names, logit_stride=1):
+    pb, lm = build_ref(cfg, seed)
+    ori = torch.from_numpy(P.synth_ids(B, S, seed + 100, padded=True))
+    random.seed(seed)
+    np.random.seed(seed)
+    tr = ref_pretrain.Pretrainer(pb, None, None, 1e-4, B, S, 0.15, True, [])
+    enc = ori.clone()
+    dec = torch.zeros_like(ori)
+    loss_mask = torch.zeros(B, S, 8)
+    for b in range(B):
+        dec[b, 1:] = ori[b, :-1]
+        dec[b, 0] = torch.tensor(pb.sos_word_np)
+        im, mp = tr.gen_mask(ori[b].clone(), choice=[2, 1, 4, 3, 5][b % 5])
+        if mp.size()[-1] != 8:
+            mp = np.repeat(mp[:, np.newaxis], 8, axis=1)
+        enc[b] = im
+        loss_mask[b] = torch.as_tensor(mp)
+    enc_mask = (enc[:, :, 0] != pb.bar_pad_word).float()
+    dec_mask = (dec[:, :, 0] != pb.bar_pad_word).float()
+    lm.zero_grad()
+    torch.set_grad_enabled(True)
+    hidden = pb(enc, dec, enc_mask, dec_mask)
+    y = lm.mask_lm(hidden)
+    total, losses = ref_pretrain_loss(pb, y, ori, loss_mask)
+    total.backward()
+    accs = ref_acc(y, ori, loss_mask)
+    out = dict(cfg=np.array(cfg), seed=seed, ori=ori.numpy().astype(np.int16), enc=enc.numpy().astype(np.int16),
+               dec=dec.numpy().astype(np.int16), loss_mask=loss_mask.numpy().astype(np.uint8),
+               enc_mask=enc_mask.numpy().astype(np.uint8), dec_mask=dec_mask.numpy().astype(np.uint8),
+               total=np.float64(total.item()), losses=np.array([l.item() for l in losses]), accs=np.array(accs))
+    logits = torch.cat(y, dim=-1).detach().numpy()
+    if full_outputs:
+        out['last_hidden'] = hidden.last_hidden_state.detach().numpy()
+        out['enc_hidden'] = hidden.encoder_last_hidden_state.detach().numpy()
+        out['logits'] = logits
+    else:
+        out['logits_sub'] = logits[:, ::logit_stride, :]
+        out['last_hidden_sub'] = hidden.last_hidden_state.detach().numpy()[:, ::logit_stride, ::8]
+    out['logit_stride'] = logit_stride
+    gn_names, gn_vals = [], []
+    for k, v in lm.named_parameters():
+        if v.grad is not None:
+            kk = k[len('pianobart.'):] if k.startswith('pianobart.') else k
+            gn_names.append(kk)
+            gn_vals.append(v.grad.double().norm().item())
+            if kk in grad_full_names:
+                out['grad:' + kk] = v.grad.numpy().copy()
+    out['grad_norm_names'] = np.array(gn_names)
+    out['grad_norm_vals'] = np.array(gn_vals)
+    out['grad_total_norm'] = np.float64(np.sqrt(np.sum(np.array(gn_vals) ** 2)))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'loss', total.item(), 'accs', accs[:3], 'gnorm', out['grad_total_norm'])
+
+
+def golden_noising():
+    pb, lm = build_ref((64, 1, 1, 2, 64, 1024), 3)
+    out = {}
+    for S, nseeds, B in ((1024, 20, 4), (64, 40, 5)):
+        tr = ref_pretrain.Pretrainer(pb, None, None, 1e-4, B, S, 0.15, True, [])
+        encs, lms, chs, oris = [], [], [], []
+        for seed in range(nseeds):
+            ori = torch.from_numpy(P.synth_ids(B, S, 1000 + seed, padded=(seed % 2 == 1), min_len=S // 4))
+            random.seed(seed)
+            np.random.seed(seed)
+            enc = ori.clone()
+            loss_mask = torch.zeros(B, S, 8)
+            for b in range(B):
+                # capture the choice by peeking the state: re-draw with a saved state
+                st = random.getstate()
+                c = random.randint(1, 5)
+                random.setstate(st)
+                im, mp = tr.gen_mask(ori[b].clone())
+                if mp.size()[-1] != 8:
+                    mp = np.repeat(mp[:, np.newaxis], 8, axis=1)
+                enc[b] = im
+                loss_mask[b] = torch.as_tensor(mp)
+                chs.append(c)
+            encs.append(enc.numpy())
+            lms.append(loss_mask.numpy())
+            oris.append(ori.numpy())
+        out['S%d_ori' % S] = np.stack(oris).astype(np.int16)
+        out['S%d_enc' % S] = np.stack(encs).astype(np.int16)
+        out['S%d_loss_mask' % S] = np.stack(lms).astype(np.uint8)
+        out['S%d_choices' % S] = np.array(chs).reshape(nseeds, B)
+        print('noising S', S, 'choices hist', np.bincount(np.array(chs), minlength=6))
+    # every corruption called directly (choice given), S=1024 and a tiny S=10 like the reference's demo
+    for S in (1024, 10):
+        tr = ref_pretrain.Pretrainer(pb, None, None, 1e-4, 1, S, 0.15 if S > 10 else 0.5, True, [])
+        for choice in (1, 2, 3, 4, 5):
+            for seed in (11, 12, 13):
+                ori = torch.from_numpy(P.synth_ids(1, S, 2000 + seed, padded=(seed == 13 and S > 10), min_len=S // 2))[0]
+                random.seed(seed)
+                np.random.seed(seed)
+                im, mp = tr.gen_mask(ori.clone(), choice=choice)
+                if mp.size()[-1] != 8:
+                    mp = np.repeat(mp[:, np.newaxis], 8, axis=1)
+                key = 'direct_S%d_c%d_s%d' % (S, choice, seed)
+                out[key + '_ori'] = ori.numpy().astype(np.int16)
+                out[key + '_enc'] = np.asarray(im).astype(np.int16)
+                out[key + '_loss_mask'] = np.asarray(mp).astype(np.uint8)
+    # infilling failure branch (pretrain.py:429-430), forced by making every Poisson draw 0
+    S = 32
+    tr = ref_pretrain.Pretrainer(pb, None, None, 1e-4, 1, S, 0.9, True, [])
+    ori = torch.from_numpy(P.synth_ids(1, S, 77))[0]
+    random.seed(5)
+    real_poisson = np.random.poisson
+    np.random.poisson = lambda lam: 0
+    try:
+        im, mp = tr.gen_mask(ori.clone(), choice=4)
+    finally:
+        np.random.poisson = real_poisson
+    out['infill_fail_ori'] = ori.numpy().astype(np.int16)
+    out['infill_fail_enc'] = np.asarray(im).astype(np.int16)
+    out['infill_fail_loss_mask'] = np.asarray(mp).astype(np.uint8)
+    out['infill_fail_state_after'] = np.array([random.random()])
+    np.savez_compressed(os.path.join(OUT, 'noising.npz'), **out)
+
+
+def golden_generate():
+    cfg = (64, 2, 2, 4, 128, 48)
+    S = 48
+    pb, lm = build_ref(cfg, 7, suppress_specials=True)
+    enc = torch.from_numpy(P.synth_ids(1, S, 321, padded=True, min_len=S // 2))
+    enc_mask = (enc[:, :, 0] != pb.bar_pad_word).float()
+    out = dict(cfg=np.array(cfg), seed=7, enc=enc.numpy().astype(np.int16))
+    with torch.no_grad():
+        for npseed in (0, 1, 2):
+            np.random.seed(npseed)
+            res = lm(enc, encoder_attention_mask=enc_mask, generate=True, device_num=-1)
+            out['result_seed%d' % npseed] = res.numpy().astype(np.int16)
+            print('generate seed', npseed, 'len', int((res[0, :, 0] != 256).sum()))
+        # teacher-forced logits for the seed-0 trajectory (causal => position i depends on prefix <= i)
+        res = torch.from_numpy(out['result_seed0'].astype(np.int64))
+        n = int((res[0, :, 0] != 256).sum())
+        dec = torch.from_numpy(np.tile(pb.pad_word_np, (1, S, 1)))
+        dec[0, 0] = torch.tensor(pb.sos_word_np)
+        dec[0, 1:n + 1] = res[0, :n] if n + 1 <= S else res[0, :S - 1]
+        dec_mask = torch.zeros(1, S)
+        dec_mask[0, :min(n + 1, S)] = 1
+        y = lm(enc, dec, enc_mask, dec_mask)
+        out['tf_dec'] = dec.numpy().astype(np.int16)
+        out['tf_logits'] = torch.cat(y, dim=-1).numpy()
+    np.savez_compressed(os.path.join(OUT, 'generate_tiny.npz'), **out)
+
+
+def golden_cls():
+    cfg = (64, 2, 2, 4, 128, 32)
+    d, el, dl, heads, ffn, max_pos = cfg
+    S, B = 32, 3
+    out = dict(cfg=np.array(cfg), seed=9)
+    ids = torch.from_numpy(P.synth_ids(B, S, 55, padded=True))
+    out['ids'] = ids.numpy().astype(np.int16)
+    # sequence classification (model.py:165-218), class_num 4
+    pb, _ = build_ref(cfg, 9)
+    sc = ref_model.SequenceClassification(pb, class_num=4, hs=d)
+    extra = {'attention.ws1.weight': (128, d), 'attention.ws2.weight': (4, 128), 'classifier.1.weight': (256, d * 4),
+             'classifier.1.bias': (256,), 'classifier.3.weight': (4, 256), 'classifier.3.bias': (4,)}
+    sd = sc.state_dict()
+    for k, shp in extra.items():
+        sd[k] = torch.from_numpy(P.gen_tensor('seqcls.' + k, shp, 9))
+    sc.load_state_dict(sd)
+    sc.eval()
+    mask = (ids[:, :, 0] != pb.bar_pad_word).float()
+    with torch.no_grad():
+        out['seqcls_logits'] = sc(ids, mask).numpy()
+    # token classification (model.py:236-272): class_num=4 (< 5: decoder ids = x) and 8 (>= 5: label embedding)
+    for cn in (4, 8):
+        pb, _ = build_ref(cfg, 9)
+        tc = ref_model.TokenClassification(pb, class_num=cn, hs=d)
+        sd = tc.state_dict()
+        extra = {'classifier.1.weight': (256, d), 'classifier.1.bias': (256,), 'classifier.3.weight': (cn, 256),
+                 'classifier.3.bias': (cn,)}
+        if cn >= 5:
+            extra['pianobart.decoder_emb.lut.weight'] = (cn, 64)
+            extra['pianobart.decoder_linear.weight'] = (d, 64)
+            extra['pianobart.decoder_linear.bias'] = (d,)
+        for k, shp in extra.items():
+            assert tuple(sd[k].shape) == shp, (k, sd[k].shape, shp)
+            sd[k] = torch.from_numpy(P.gen_tensor('tokcls%d.' % cn + k, shp, 9))
+        tc.load_state_dict(sd)
+        tc.eval()
+        with torch.no_grad():
+            if cn >= 5:
+                labels = torch.from_numpy(np.random.RandomState(4).randint(0, cn - 1, size=(B, S))).long()
+                y_shift = torch.zeros_like(labels)
+                y_shift[:, 1:] = labels[:, :-1]
+                y_shift[:, 0] = cn - 1
+                out['tokcls%d_dec_in' % cn] = y_shift.numpy().astype(np.int16)
+                res = tc(ids, y_shift, mask, mask)
+            else:
+                res = tc(ids, ids, mask, mask)
+            out['tokcls%d_logits' % cn] = res.numpy()
+    np.savez_compressed(os.path.join(OUT, 'cls_tiny.npz'), **out)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['tiny', 'mid', 'default', 'noising', 'generate', 'cls']
+    if 'tiny' in which:
+        golden_forward('fwd_tiny', (64, 2, 2, 4, 128, 32), 1, 5, 32, True,
+                       ['encoder_linear.bias', 'word_emb.3.lut.weight', 'bart.decoder.layers.1.encoder_attn.k_proj.weight',
+                        'mask_lm.proj.5.weight', 'bart.encoder.embed_positions.weight',
+                        'bart.encoder.layers.0.self_attn.q_proj.weight', 'bart.decoder.layers.0.fc1.bias',
+                        'bart.decoder.layernorm_embedding.weight'])
+    if 'mid' in which:
+        golden_forward('fwd_mid', (256, 2, 2, 2, 512, 128), 2, 3, 128, False,
+                       ['encoder_linear.bias', 'mask_lm.proj.7.weight', 'bart.decoder.layers.1.final_layer_norm.weight',
+                        'bart.encoder.layers.1.fc2.bias'], logit_stride=8)
+    if 'default' in which:
+        golden_forward('fwd_default', (1024, 8, 8, 8, 2048, 1024), 3, 1, 1024, False,
+                       ['encoder_linear.bias', 'bart.decoder.layers.7.final_layer_norm.weight'], logit_stride=64)
+    if 'noising' in which:
+        golden_noising()
+    if 'generate' in which:
+        golden_generate()
+    if 'cls' in which:
+        golden_cls()
