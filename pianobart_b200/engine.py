@@ -38,6 +38,7 @@ class ParamLayout:
         self.d, self.enc_layers, self.dec_layers, self.ffn, self.max_pos = d, enc_layers, dec_layers, ffn, max_pos
         self.entries = {}   # name -> (offset, shape)
         self.fused = {}     # fused name -> (offset, shape)
+        self.ranges = {}    # group -> (lo, hi) flat range whose gradients become final together
         self.size = 0
         self._build(with_heads)
 
@@ -85,12 +86,16 @@ class ParamLayout:
         self.emb_end = self.size
         self._add('encoder_linear.weight', (d, 2048))
         self._add('encoder_linear.bias', (d,))
+        self.ranges['front'] = (0, self.size)
         for side, nl in (('encoder', self.enc_layers), ('decoder', self.dec_layers)):
+            lo = self.size
             self._add('bart.%s.embed_positions.weight' % side, (self.max_pos + 2, d))
             self._add('bart.%s.layernorm_embedding.weight' % side, (d,))
             self._add('bart.%s.layernorm_embedding.bias' % side, (d,))
+            self.ranges['%s.front' % side] = (lo, self.size)
             for l in range(nl):
                 pre = 'bart.%s.layers.%d' % (side, l)
+                lo = self.size
                 self._attn(pre + '.self_attn', False)
                 self._add(pre + '.self_attn_layer_norm.weight', (d,))
                 self._add(pre + '.self_attn_layer_norm.bias', (d,))
@@ -104,10 +109,12 @@ class ParamLayout:
                 self._add(pre + '.fc2.bias', (d,))
                 self._add(pre + '.final_layer_norm.weight', (d,))
                 self._add(pre + '.final_layer_norm.bias', (d,))
+                self.ranges['%s.layers.%d' % (side, l)] = (lo, self.size)
         self.backbone_size = self.size
         if with_heads:
             self._fuse('heads.w', [('mask_lm.proj.%d.weight' % i, (n, d)) for i, n in enumerate(N_TOKENS)])
             self._fuse('heads.b', [('mask_lm.proj.%d.bias' % i, (n,)) for i, n in enumerate(N_TOKENS)])
+            self.ranges['heads'] = (self.backbone_size, self.size)
 
     def off(self, name):
         if name in self.entries:
@@ -127,13 +134,35 @@ class Plan:
     def _add(self, name, fn, *args):
         self.ops.append((name, fn, args))
 
-    def run(self, stream=None):
+    def marker(self, *payload):
+        """Host-side marker (no launch): run() hands the payload to `on_marker` when it reaches it."""
+        self.ops.append(('marker', None, payload))
+
+    def run(self, stream=None, on_marker=None, profile=None):
+        """profile: optional list; every GEMM launch is then bracketed by CUDA events on the launching
+        stream and (name, flops, start_event, end_event) is appended (bench.py roofline)."""
         s = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+        n = 0
+        gemm_fns = (self.lib.pb_gemm_bf16, self.lib.pb_gemm_f32)
         for name, fn, args in self.ops:
-            rc = fn(*args, s)
+            if fn is None:
+                if on_marker is not None:
+                    on_marker(*args)
+                continue
+            if profile is not None and fn in gemm_fns:
+                d = args[0]._obj
+                flops = 2.0 * d.M * d.N * d.K * max(1, d.batch_h) * max(1, d.batch_b) * (0.5 if d.causal else 1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*args, s)
+                e1.record()
+                profile.append((name, flops, e0, e1))
+            else:
+                rc = fn(*args, s)
+            n += 1
             if rc != 0:
                 raise L.PBError('%s failed (%d): %s' % (name, rc, self.lib.pb_last_error().decode()))
-        return len(self.ops)
+        return n
 
     # ---- op recorders ------------------------------------------------------------------
     def gemm(self, a, b, c, M, N, K, lda, ldb, ldc, bias=0, residual=0, ldr=0, a_mn=0, b_mn=0, flags=0, alpha=1.0,
@@ -302,12 +331,14 @@ class BackboneGraph:
             bw.wgrad(_ptr(self.dlogits), _ptr(self.out), self.G('heads.w'), VOCAB, d, Mo, VOCAB, d, name='dW_heads')
             bw.gemm(_ptr(self.dlogits), self.W('heads.w'), _ptr(self.d_out), Mo, d, VOCAB, VOCAB, d, d, b_mn=1,
                     name='dH_heads')
+            bw.marker('grads_final', *self.lay.ranges['heads'])
         if self.has_dec:
             d_enc_out = self.buf('d_enc_out', Me, d)
             dec_back(self.d_out, d_enc_out)
             enc_back(d_enc_out, None)
         else:
             enc_back(self.d_out, None)
+        bw.marker('grads_final', *self.lay.ranges['front'])
 
     def _stream(self, side, ids, keep, S, enc_out, enc_keep, S_enc):
         """Records forward ops of one stack (front end + layers); returns (output tensor,
@@ -507,6 +538,7 @@ class BackboneGraph:
                 bw.gemm(_ptr(dQKV), self.W(sa + '.wqkv'), _ptr(dnext), M, d, 3 * d, 3 * d, d, d, b_mn=1,
                         residual=_ptr(dA), ldr=d, name=ln('dH_in'))
                 dcur, dnext = dnext, dcur
+                bw.marker('grads_final', *self.lay.ranges['%s.layers.%d' % (side, l)])
             # -- front end backward
             dY0 = dA
             bw.ln_bwd(_ptr(dcur), _ptr(Y0), self.Pf(pre + '.layernorm_embedding.weight'), _ptr(st0), _ptr(st0, M),
@@ -523,6 +555,7 @@ class BackboneGraph:
                 bw.embed_bwd(_ptr(ids), _ptr(dX), self.G('emb'), M, self.ntok_arr, 16.0)
             else:
                 self.dec_embed.record_backward(self, bw, dY0, M, S)
+            bw.marker('grads_final', *self.lay.ranges['%s.front' % side])
 
         return out, record_backward
 
@@ -547,3 +580,14 @@ class BackboneGraph:
 
     def backward(self):
         return self.bwd.run()
+
+
+def profile_gemms(step):
+    """Runs one training step of `step` (PretrainStep) with every GEMM launch timed by CUDA events.
+    Returns (total algorithmic GEMM flops, total GEMM milliseconds, number of GEMM launches)."""
+    prof = []
+    step.run(train=True, profile=prof)
+    torch.cuda.synchronize()
+    flops = sum(p[1] for p in prof)
+    ms = sum(p[2].elapsed_time(p[3]) for p in prof)
+    return flops, ms, len(prof)

@@ -1,0 +1,316 @@
+"""Pretraining hot loop, mirroring reference pretrain.py (`Pretrainer`, pretrain.py:51-546).
+
+`Pretrainer` keeps the reference's constructor, train()/valid()/iteration()/gen_mask()/
+compute_loss()/save_checkpoint() interface and printed metrics, but one iteration is a single
+fused device step (no per-sample D2H/H2D, no host argmax):
+
+  host : noise plan for the batch (noising.py, bit-exact RNG)      pretrain.py:131-144
+  H2D  : original ids (int16) + plan, from pinned staging buffers
+  dev  : pb_noise_apply -> enc/dec ids, targets, loss mask, pad masks   pretrain.py:128-153
+         pb_mask_sums  (-> all-reduce of the 8 denominators under data parallelism)
+         forward plan (front end, 8+8 BART layers, heads as one N=1280 GEMM)
+         pb_heads_ce   masked CE x8 + weights + argmax accuracy + dlogits  pretrain.py:163-189
+         backward plan (gradient buckets all-reduced on a side stream as they become final)
+         pb_sumsq + pb_adamw (clip 3.0 + HF AdamW, refreshes the bf16 working weights)  pretrain.py:192-196
+"""
+import ctypes as C
+import os
+import shutil
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import engine as E
+from . import noising
+from .modules import PianoBart, PianoBartLM
+
+# e2w pickle key order -> the n_tok sequence pretrain.py:184-189 multiplies the (classes-ordered) losses with
+LOSS_WEIGHTS = [262, 134, 262, 134, 38, 135, 55, 260]
+
+
+class FusedAdamW:
+    """HF-semantics AdamW (transformers 4.29 `AdamW(lr, weight_decay=0.01)`: betas (0.9, 0.999), eps 1e-6,
+    bias correction folded in the step size, decay after the update) over the flat parameter buffer,
+    with torch `clip_grad_norm_` folded in.  One launch for the norm, two for the update."""
+
+    def __init__(self, pianobart, lr, weight_decay=0.01, betas=(0.9, 0.999), eps=1e-6, max_grad_norm=3.0):
+        self.pb = pianobart
+        self.lr, self.wd, self.betas, self.eps, self.max_grad_norm = lr, weight_decay, betas, eps, max_grad_norm
+        self.step_count = 0
+        self.m = self.v = None
+        self.gnorm_sq = None
+
+    def _ensure(self):
+        pb = self.pb
+        pb._ensure_packed()
+        if self.m is None or self.m.device != pb._flat.device or self.m.numel() != pb._flat.numel():
+            self.m = torch.zeros_like(pb._flat)
+            self.v = torch.zeros_like(pb._flat)
+            self.gnorm_sq = torch.zeros(1, device=pb._flat.device, dtype=torch.float32)
+
+    def step(self, grad_scale=1.0):
+        self._ensure()
+        pb, lib, s = self.pb, L.lib(), L.stream_ptr()
+        lay = pb.layout
+        n = lay.size
+        self.step_count += 1
+        self.gnorm_sq.zero_()
+        L.check(lib.pb_sumsq(C.c_void_p(pb._grad.data_ptr()), C.c_longlong(n), C.c_void_p(self.gnorm_sq.data_ptr()), s), 'sumsq')
+        bf16 = pb.pb_dtype == E.PB_BF16
+        for lo, hi, scale in ((0, lay.emb_end, 16.0), (lay.emb_end, n, 1.0)):
+            wp = C.c_void_p(pb._wact.data_ptr() + lo * 2) if bf16 else C.c_void_p(None)
+            L.check(lib.pb_adamw(C.c_void_p(pb._flat.data_ptr() + lo * 4), C.c_void_p(self.m.data_ptr() + lo * 4),
+                                 C.c_void_p(self.v.data_ptr() + lo * 4), C.c_void_p(pb._grad.data_ptr() + lo * 4), wp,
+                                 C.c_longlong(hi - lo), C.c_float(self.lr), C.c_float(self.betas[0]),
+                                 C.c_float(self.betas[1]), C.c_float(self.eps), C.c_float(self.wd), self.step_count,
+                                 C.c_void_p(self.gnorm_sq.data_ptr()), C.c_float(self.max_grad_norm),
+                                 C.c_float(grad_scale), C.c_float(scale), s), 'adamw')
+        if not bf16:
+            pb.mark_weights_dirty()
+            pb._sync_weights()
+
+    def state_dict(self):
+        self._ensure()
+        return {'step': self.step_count, 'exp_avg': self.m, 'exp_avg_sq': self.v, 'lr': self.lr,
+                'weight_decay': self.wd, 'betas': self.betas, 'eps': self.eps}
+
+    def load_state_dict(self, sd):
+        self._ensure()
+        self.step_count = sd['step']
+        self.m.copy_(sd['exp_avg'])
+        self.v.copy_(sd['exp_avg_sq'])
+
+
+class PretrainStep:
+    """One fused device step for a fixed (batch, seq) shape."""
+
+    def __init__(self, lm, B, S, optimizer=None, mask_percent=0.15, process_group=None):
+        self.lm, self.pb = lm, lm.pianobart
+        pb = self.pb
+        pb._ensure_packed()
+        self.B, self.S = B, S
+        self.mask_percent = mask_percent
+        self.opt = optimizer
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        dev = pb._flat.device
+        self.dev = dev
+        self.lib = L.lib()
+        self.graph = pb._graph(B, S, S, True, True)
+        M = B * S
+        self.M = M
+        # pinned host staging + device inputs
+        self.h_ori = torch.empty(B, S, 8, dtype=torch.int16).pin_memory()
+        self.h_src = torch.empty(B, S, dtype=torch.int32).pin_memory()
+        self.h_loss = torch.empty(B, S, dtype=torch.uint8).pin_memory()
+        self.h_mode = torch.empty(B, dtype=torch.int32).pin_memory()
+        self.h_rand = torch.zeros(max(1, M), 8, dtype=torch.int32).pin_memory()
+        self.d_ori = torch.empty(B, S, 8, dtype=torch.int16, device=dev)
+        self.d_src = torch.empty(B, S, dtype=torch.int32, device=dev)
+        self.d_loss = torch.empty(B, S, dtype=torch.uint8, device=dev)
+        self.d_mode = torch.empty(B, dtype=torch.int32, device=dev)
+        self.d_rand = torch.zeros(max(1, M), 8, dtype=torch.int32, device=dev)
+        self.targets = torch.empty(M * 8, dtype=torch.int32, device=dev)
+        self.loss_mask = torch.empty(M * 8, dtype=torch.float32, device=dev)
+        # stats: [0:8] loss numerators, [8:16] correct counts, [16:24] mask sums (denominators)
+        self.stats = torch.zeros(24, dtype=torch.float32, device=dev)
+        self.h_stats = torch.zeros(24, dtype=torch.float32).pin_memory()
+        self.pad = (C.c_int * 8)(*[int(x) for x in pb.pad_word_np])
+        self.mask = (C.c_int * 8)(*[int(x) for x in pb.mask_word_np])
+        self.sos = (C.c_int * 8)(*[int(x) for x in pb.sos_word_np])
+        self.seg = (C.c_int * 8)(*E.N_TOKENS)
+        self.w = (C.c_float * 8)(*[float(x) for x in LOSS_WEIGHTS])
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.launches = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 24 * 4
+
+    # -- stage 1: host plan + H2D + noising kernel
+    def upload(self, ori_batch, choices=None):
+        """ori_batch: (B,S,8) integer tensor or array on the HOST."""
+        ori = ori_batch.numpy() if isinstance(ori_batch, torch.Tensor) else np.asarray(ori_batch)
+        plan = noising.make_plan(ori, self.S, self.mask_percent, choices)
+        self.h_ori.numpy()[...] = ori
+        self.h_src.numpy()[...] = plan.src
+        self.h_loss.numpy()[...] = plan.loss
+        self.h_mode.numpy()[...] = plan.loss_mode
+        nr = len(plan.rand_tok)
+        if nr:
+            self.h_rand.numpy()[:nr] = np.asarray(plan.rand_tok, dtype=np.int32)
+        self.d_ori.copy_(self.h_ori, non_blocking=True)
+        self.d_src.copy_(self.h_src, non_blocking=True)
+        self.d_loss.copy_(self.h_loss, non_blocking=True)
+        self.d_mode.copy_(self.h_mode, non_blocking=True)
+        if nr:
+            self.d_rand[:nr].copy_(self.h_rand[:nr], non_blocking=True)
+        self.h2d_bytes = (self.h_ori.numel() * 2 + self.h_src.numel() * 4 + self.h_loss.numel() + self.h_mode.numel() * 4
+                          + nr * 32)
+        return plan
+
+    def noise(self):
+        g, s = self.graph, L.stream_ptr()
+        P = C.c_void_p
+        L.check(self.lib.pb_noise_apply(P(self.d_ori.data_ptr()), P(self.d_src.data_ptr()), P(self.d_rand.data_ptr()),
+                                        P(self.d_loss.data_ptr()), P(self.d_mode.data_ptr()), P(g.enc_ids.data_ptr()),
+                                        P(g.dec_ids.data_ptr()), P(self.targets.data_ptr()), P(self.loss_mask.data_ptr()),
+                                        P(g.enc_keep.data_ptr()), P(g.dec_keep.data_ptr()), self.B, self.S, self.pad,
+                                        self.mask, self.sos, s), 'noise_apply')
+        self.launches += 1
+
+    def set_device_batch(self, enc_ids, dec_ids, targets, loss_mask, enc_keep, dec_keep):
+        """Alternative to upload()+noise(): already-noised device tensors (parity tests, generation finetune)."""
+        g = self.graph
+        g.set_inputs(enc_ids, enc_keep, dec_ids, dec_keep)
+        self.targets.copy_(targets.reshape(-1))
+        self.loss_mask.copy_(loss_mask.reshape(-1))
+
+    # -- stage 2: forward + loss (+ backward + optimizer)
+    def _allreduce_bucket(self, tag, lo, hi):
+        import torch.distributed as dist
+        ev = torch.cuda.Event()
+        ev.record()
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.pb._grad[lo:hi], group=self.pg)
+
+    def run(self, train=True, profile=None):
+        g, lib, s = self.graph, self.lib, L.stream_ptr()
+        pb = self.pb
+        P = C.c_void_p
+        pb._sync_weights()
+        pb._live_graph = None  # the fused step owns the graph buffers; autograd must not reuse them
+        self.stats.zero_()
+        M = self.M
+        L.check(lib.pb_mask_sums(P(self.loss_mask.data_ptr()), P(self.stats.data_ptr() + 64), C.c_longlong(M), 8, s), 'mask_sums')
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.stats[16:24], group=self.pg)  # global denominators (pretrain.py:117 on the full batch)
+        n = g.fwd.run(profile=profile)
+        L.check(lib.pb_heads_ce(P(g.logits.data_ptr()), P(self.targets.data_ptr()), P(self.loss_mask.data_ptr()),
+                                P(self.stats.data_ptr() + 64), P(self.stats.data_ptr()), P(self.stats.data_ptr() + 32),
+                                P(g.dlogits.data_ptr()) if train else P(None), P(None), C.c_longlong(M), 8, self.seg,
+                                self.w, C.c_float(1.0), pb.pb_dtype, s), 'heads_ce')
+        n += 2
+        if train:
+            pb._grad.zero_()
+            if self.world > 1:
+                n += g.bwd.run(on_marker=self._allreduce_bucket, profile=profile)
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+            else:
+                n += g.bwd.run(profile=profile)
+            if self.opt is not None:
+                self.opt.step()
+                n += 3
+        self.launches += n
+        return n
+
+    def fetch_stats(self):
+        """D2H of the 24 step scalars; returns (total_loss, losses[8], accs[8]) like pretrain.py:171-189."""
+        st = self.stats
+        if self.world > 1:
+            import torch.distributed as dist
+            st = self.stats.clone()
+            dist.all_reduce(st[0:16], group=self.pg)
+        self.h_stats.copy_(st, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        v = self.h_stats.numpy().astype(np.float64)
+        num, cor, den = v[0:8], v[8:16], v[16:24]
+        with np.errstate(divide='ignore', invalid='ignore'):
+            losses = num / den
+            accs = cor / den
+        total = float(np.sum(losses * np.array(LOSS_WEIGHTS)) / np.sum(LOSS_WEIGHTS))
+        return total, losses, accs
+
+
+class Pretrainer:
+    """Same interface as reference `Pretrainer` (pretrain.py:51-209)."""
+
+    def __init__(self, pianobart: PianoBart, train_dataloader, valid_dataloader, lr, batch, max_seq_len, mask_percent,
+                 cpu, cuda_devices=None, process_group=None, verbose=True):
+        if cpu or not torch.cuda.is_available():
+            raise L.PBError('pianobart_b200.Pretrainer has no CPU path (sm_100a kernels only)')
+        dev = 'cuda'
+        if process_group is None and cuda_devices is not None and len(cuda_devices) >= 1:
+            dev += ':' + str(cuda_devices[0])
+        elif process_group is not None:
+            dev += ':' + str(torch.cuda.current_device())
+        self.device = torch.device(dev)
+        self.pianobart = pianobart.to(self.device)
+        self.model = PianoBartLM(pianobart).to(self.device)
+        self.total_params = sum(p.numel() for p in self.model.parameters() if p.requires_grad)
+        self.verbose = verbose
+        if verbose:
+            print('# total parameters:', self.total_params)
+        if cuda_devices is not None and len(cuda_devices) > 1 and process_group is None and verbose:
+            print('pianobart_b200: multi-GPU data parallelism is one process per GPU (torchrun); '
+                  'this process uses %s only' % dev)
+        self.train_data, self.valid_data = train_dataloader, valid_dataloader
+        self.optim = FusedAdamW(self.pianobart, lr=lr, weight_decay=0.01)
+        self.batch, self.max_seq_len, self.mask_percent = batch, max_seq_len, mask_percent
+        self.pg = process_group
+        self._steps = {}
+        self._train_mode = True
+
+    def _step(self, B, S):
+        k = (B, S)
+        if k not in self._steps:
+            self._steps[k] = PretrainStep(self.model, B, S, self.optim, self.mask_percent, self.pg)
+        return self._steps[k]
+
+    def train(self):
+        self.model.train()
+        return self.iteration(self.train_data, self.max_seq_len)
+
+    def valid(self):
+        self.model.eval()
+        return self.iteration(self.valid_data, self.max_seq_len, train=False)
+
+    def compute_loss(self, predict, target, loss_mask):
+        """pretrain.py:112-118 on torch tensors (kept for API compatibility; the fused step does not call it)."""
+        loss = torch.nn.functional.cross_entropy(predict, target, reduction='none') * loss_mask
+        return torch.sum(loss) / torch.sum(loss_mask)
+
+    def gen_mask(self, input_ids, choice=None):
+        """pretrain.py:211-546 for one (S,8) sample: returns (noised ids, loss mask) as CPU tensors, consuming
+        the RNG streams like the reference.  Data movement runs on the device kernel."""
+        ori = input_ids.cpu().numpy()[None]
+        st = self._step(1, ori.shape[1])
+        st.upload(ori, None if choice is None else [choice])
+        st.noise()
+        enc = st.graph.enc_ids.view(1, -1, 8)[0].cpu().long()
+        lm = st.loss_mask.view(-1, 8).cpu()
+        return enc, lm
+
+    def iteration(self, training_data, max_seq_len, train=True):
+        total_acc, total_losses, nb = np.zeros(8), 0.0, 0
+        for ori_seq_batch in training_data:
+            B, S = ori_seq_batch.shape[0], ori_seq_batch.shape[1]
+            st = self._step(B, S)
+            st.upload(ori_seq_batch)
+            st.noise()
+            st.run(train=train)
+            total, losses, accs = st.fetch_stats()
+            if self.verbose:
+                sys.stdout.write('Loss: {:06f} | loss: {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}\n'.format(total, *losses))
+                sys.stdout.write('Acc: {:06f} | acc: {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}\n'.format(np.average(accs), *accs))
+            total_losses += total
+            total_acc += accs
+            nb += 1
+        nb = max(nb, 1)
+        return round(total_losses / nb, 3), [round(float(x) / nb, 3) for x in total_acc]
+
+    def save_checkpoint(self, epoch, best_acc, valid_acc, valid_loss, train_loss, is_best, filename):
+        """Same dict layout as pretrain.py:96-110 ('state_dict' = PianoBart only, reference key names)."""
+        state = {'epoch': epoch + 1,
+                 'state_dict': {k: v.detach().clone() for k, v in self.pianobart.state_dict().items()},
+                 'best_acc': best_acc, 'valid_acc': valid_acc, 'valid_loss': valid_loss, 'train_loss': train_loss,
+                 'optimizer': self.optim.state_dict()}
+        torch.save(state, filename)
+        best_mdl = filename.split('.')[0] + '_best.ckpt'
+        if is_best:
+            shutil.copyfile(filename, best_mdl)
