@@ -78,6 +78,102 @@ int pb_gemm_bf16(const pb_gemm_desc* d, void* stream);
 /* fp32 operands, SIMT kernel - the fp32 parity mode of the same graph */
 int pb_gemm_f32(const pb_gemm_desc* d, void* stream);
 
+/* ------------------------------------------------------------------ Octuple front end
+ * out[m, 256*i + c] = table[row_off(i) + ids[m,i], c] for the 8 attributes (reference PianoBart.py:9-16,60-67:
+ * eight nn.Embedding gathers * sqrt(256) + torch.cat).  `table` is the [1280,256] concatenation of the eight
+ * tables in the activation dtype, already multiplied by 16.  ids: [M,8] int32 (ids_int64 = 0) or int64 (= 1).
+ * n_tokens_host: 8 ints on the HOST.  err_flag (device int, may be NULL) is set to 1 on an out-of-range id. */
+int pb_octuple_embed_fwd(const void* ids, int ids_int64, const void* table, void* out, long long M,
+                         const int* n_tokens_host, int dtype, int* err_flag, void* stream);
+/* dtable[row, c] += scale * dx[m, 256*i + c]  (fp32 atomics; autograd of the gathers above) */
+int pb_octuple_embed_bwd(const void* ids, int ids_int64, const void* dx, float* dtable, long long M,
+                         const int* n_tokens_host, float scale, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ LayerNorm (HF BartEncoder/DecoderLayer
+ * self_attn_layer_norm / encoder_attn_layer_norm / final_layer_norm / layernorm_embedding, eps 1e-5)
+ * mean/rstd: [M] fp32 saved for backward.  d % 8 == 0 (bf16) / % 4 (fp32), d <= 2048 / 1024. */
+int pb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     long long M, int d, float eps, int dtype, void* stream);
+/* dx written; dgamma/dbeta accumulated (+=) with fp32 atomics; dbias (may be NULL) += column sums of dx, i.e. the
+ * bias gradient of the Linear whose output (+ residual) fed this LayerNorm */
+int pb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                     void* dx, float* dgamma, float* dbeta, float* dbias, long long M, int d, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ masked softmax over attention scores
+ * (HF eager_attention_forward: scores + mask -> softmax; masks of create_bidirectional_mask / create_causal_mask
+ * built from pretrain.py:151-153).  scores fp32 [B,H,Sq,Sk] (already scaled); key_keep uint8 [B,Sk] or NULL
+ * (non-zero = key visible); causal != 0: key j visible to query i only if j <= i.  Masked probabilities are
+ * exactly 0; Sk <= 1024. */
+int pb_softmax_fwd(const float* scores, void* probs, const uint8_t* key_keep, int B, int H, int Sq, int Sk,
+                   int causal, int dtype, void* stream);
+/* dscores = probs * (dprobs - sum_j probs_j dprobs_j); may run in place (dscores == probs) */
+int pb_softmax_bwd(const void* probs, const float* dprobs, void* dscores, const uint8_t* key_keep, int B, int H,
+                   int Sq, int Sk, int causal, int dtype, void* stream);
+
+/* out[n] += sum_m x[m, n]   (bias gradients; also d(position table) with x viewed as [B, S*d]) */
+int pb_colsum(const void* x, float* out, long long M, int N, long long ld, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ fused multi-head masked cross-entropy
+ * Replaces pretrain.py:163-189 (8x permute + CrossEntropyLoss(reduction='none') * mask, host argmax accuracy)
+ * and its autograd.  logits fp32 [M, sum(seg_sizes)], targets int32 [M,nseg], mask fp32 [M,nseg],
+ * den[nseg] = (global) mask sums.  Accumulates loss_num[s] += CE*mask, correct[s] += (argmax==target)*mask and, if
+ * dlogits != NULL, writes dlogits = (softmax - onehot) * mask * w[s] / (sum(w) * den[s]) * grad_scale in `dtype`.
+ * argmax_out (int32 [M,nseg]) optional.  seg_sizes_host / weights_host live on the HOST. */
+int pb_heads_ce(const float* logits, const int* targets, const float* mask, const float* den, float* loss_num,
+                float* correct, void* dlogits, int* argmax_out, long long M, int nseg, const int* seg_sizes_host,
+                const float* weights_host, float grad_scale, int dtype, void* stream);
+/* den[s] += sum_m mask[m, s]   (pretrain.py:117 denominators) */
+int pb_mask_sums(const float* mask, float* den, long long M, int nseg, void* stream);
+
+/* ------------------------------------------------------------------ optimizer (pretrain.py:76,195-196)
+ * out[0] += sum(g^2) */
+int pb_sumsq(const float* g, long long n, float* out, void* stream);
+/* HF transformers 4.29 AdamW semantics + torch clip_grad_norm_ folded in (gnorm_sq = device scalar holding the
+ * squared global gradient norm; max_norm <= 0 disables clipping).  p_bf16 (may be NULL) receives bf16(p*bf16_scale). */
+int pb_adamw(float* p, float* m, float* v, const float* g, void* p_bf16, long long n, float lr, float beta1,
+             float beta2, float eps, float wd, int step, const float* gnorm_sq, float max_norm, float grad_scale,
+             float bf16_scale, void* stream);
+int pb_cast_from_f32(const float* src, void* dst, long long n, float scale, int dtype, void* stream);
+int pb_cast_to_f32(const void* src, float* dst, long long n, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ BART noising (pretrain.py:128-153,211-546)
+ * Applies a host-drawn plan (pianobart_b200/noising.py) to a batch: ori int16 [B,S,8]; src int32 [B,S] row codes
+ * (>=0 source row, -1 PAD row, -2 MASK row, <=-3 row (-3-k) of rand_tok int32 [R,8]); loss_in uint8 [B,S];
+ * loss_mode int32 [B] (0 host flags, 1 row-changed, 2 zero).  Outputs: enc_ids/dec_ids/targets int32 [B,S,8],
+ * loss_mask fp32 [B,S,8], enc_keep/dec_keep uint8 [B,S] (Bar != <PAD>, computed after noising). */
+int pb_noise_apply(const int16_t* ori, const int* src, const int* rand_tok, const uint8_t* loss_in,
+                   const int* loss_mode, int* enc_ids, int* dec_ids, int* targets, float* loss_mask,
+                   uint8_t* enc_keep, uint8_t* dec_keep, int B, int S, const int* pad_host, const int* mask_host,
+                   const int* sos_host, void* stream);
+
+/* ------------------------------------------------------------------ KV-cache decode (model.py:28-107)
+ * The reference re-runs encoder + 1024-position decoder per generated token (model.py:42-45); these kernels
+ * implement the same arithmetic incrementally.  bf16 only.  `t_dev` is the device-resident step index.
+ *
+ * pb_decode_finalize: acc fp32 [B,N] (split-K result of pb_gemm_bf16 with M = batch; zeroed again on exit) ->
+ *   y = acc + bias; GELU if gelu; + residual (bf16 [B,N]); + pos_table[t+2] (bf16 rows of width N); LayerNorm if
+ *   gamma != NULL; written as bf16 to `out` and/or fp32 to `out_f32`. */
+int pb_decode_finalize(float* acc, const float* bias, const void* residual, const void* pos_table, const int* t_dev,
+                       const float* gamma, const float* beta, void* out, float* out_f32, int B, int N, int gelu,
+                       void* stream);
+/* one query token per (batch, head).  q: bf16 [B, q_ld], head h at column h*hd.  Cache row j of batch b, head h at
+ * k_cache + b*kv_batch_stride + j*kv_ld + h*hd (same for v).  append != 0: k_new/v_new (addressed like q) are
+ * written to row t and keys 0..t are attended (HF BartAttention with past_key_values); else n_keys keys gated by
+ * key_keep uint8 [B, n_keys] (cross attention on the encoder output). */
+int pb_decode_attn(const void* q, int q_ld, const void* k_new, const void* v_new, void* k_cache, void* v_cache,
+                   long long kv_batch_stride, int kv_ld, const uint8_t* key_keep, int n_keys, const int* t_dev,
+                   int append, void* out, int out_ld, int B, int H, int hd, float scale, int max_keys, void* stream);
+/* PianoBartLM.sample (model.py:68-78) + sampling/nucleus (model.py:84-107) for step t: logits fp32 [B, 1280];
+ * uniforms double [B,S,8] drawn on the host from numpy's stream (one per attribute per step, as np.random.choice
+ * consumes them); forced int32 [B,S,8] or NULL (teacher forcing).  Writes cur_tok int32 [B,8], sampled [B,S,8]. */
+int pb_decode_sample(const float* logits, const double* uniforms, const int* forced, const int* t_dev, int* cur_tok,
+                     int* sampled, int B, int S, const int* seg_sizes_host, const float* temp_host,
+                     const float* top_p_host, void* stream);
+/* model.py:59-65: stop when any attribute >= its <PAD> id (that step is not written), else result[b,t] = cur_tok;
+ * then t += 1.  done int32 [B] sticky flags, n_written int32 [B]. */
+int pb_decode_advance(const int* cur_tok, int* result, int* done, int* t_dev, int* n_written, int B, int S,
+                      const int* pad_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,9 +106,8 @@ __global__ void __launch_bounds__(256) octuple_embed_bwd_kernel(const I* __restr
 }
 
 // ------------------------------------------------------------------ LayerNorm (one warp per row)
-constexpr int LN_MAXP = 8;
-
-template <typename T>
+// MAXP = 16-byte packs per lane (d <= MAXP * 32 * pack width); the row lives in registers.
+template <typename T, int MAXP>
 __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, T* __restrict__ y,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
@@ -119,10 +118,10 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long row = warp_global; row < M; row += nwarps) {
     const T* xr = x + row * d;
-    float v[LN_MAXP][N];
+    float v[MAXP][N];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXP; ++k) {
+    for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
         load_pack(xr + c, v[k]);
@@ -133,7 +132,7 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
     const float mean = warp_sum(s) / d;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXP; ++k) {
+    for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
 #pragma unroll
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
     }
     T* yr = y + row * d;
 #pragma unroll
-    for (int k = 0; k < LN_MAXP; ++k) {
+    for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
         float o[N];
@@ -159,30 +158,31 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
   }
 }
 
-// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += dy*xhat, dbeta += dy
-template <typename T>
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += dy*xhat, dbeta += dy,
+// dbias (optional) += dx  - the bias gradient of the Linear whose output (+ residual) fed this LayerNorm.
+template <typename T, int MAXP>
 __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, T* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            long long M, int d) {
+                                                            float* __restrict__ dbias, long long M, int d) {
   constexpr int N = Pack<T>::N;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  float ag[LN_MAXP][N], ab[LN_MAXP][N];
+  float ag[MAXP][N], ab[MAXP][N], ax[MAXP][N];
 #pragma unroll
-  for (int k = 0; k < LN_MAXP; ++k)
+  for (int k = 0; k < MAXP; ++k)
 #pragma unroll
-    for (int j = 0; j < N; ++j) { ag[k][j] = 0.f; ab[k][j] = 0.f; }
+    for (int j = 0; j < N; ++j) { ag[k][j] = 0.f; ab[k][j] = 0.f; ax[k][j] = 0.f; }
   for (long long row = warp_global; row < M; row += nwarps) {
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[LN_MAXP][N], g[LN_MAXP][N];
+    float xh[MAXP][N], g[MAXP][N];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXP; ++k) {
+    for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
         float xv[N], dv[N];
@@ -202,35 +202,36 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict_
     s1 = warp_sum(s1) / d;
     s2 = warp_sum(s2) / d;
 #pragma unroll
-    for (int k = 0; k < LN_MAXP; ++k) {
+    for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
         float o[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) o[j] = rstd * (g[k][j] - s1 - xh[k][j] * s2);
+        for (int j = 0; j < N; ++j) { o[j] = rstd * (g[k][j] - s1 - xh[k][j] * s2); ax[k][j] += o[j]; }
         store_pack(dx + row * d + c, o);
       }
     }
   }
-  // block-level reduction of the per-warp dgamma/dbeta partials, then one atomic per column per block
+  // block-level reduction of the per-warp partials, then one atomic per column per block
   __shared__ float sh[4][32 * 8 + 1];
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 3; ++pass) {
+    float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
+    if (out == nullptr) continue;
 #pragma unroll
-    for (int k = 0; k < LN_MAXP; ++k) {
+    for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       __syncthreads();
       if (c < d) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) sh[warp][lane * N + j] = pass == 0 ? ag[k][j] : ab[k][j];
+        for (int j = 0; j < N; ++j) sh[warp][lane * N + j] = pass == 0 ? ag[k][j] : (pass == 1 ? ab[k][j] : ax[k][j]);
       }
       __syncthreads();
       if (warp == 0 && c < d) {
-        float* dst = (pass == 0 ? dgamma : dbeta) + c;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
           float t = 0.f;
           for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w][lane * N + j];
-          atomicAdd(dst + j, t);
+          atomicAdd(out + c + j, t);
         }
       }
     }
@@ -318,26 +319,40 @@ __global__ void __launch_bounds__(128) softmax_bwd_kernel(const T* __restrict__ 
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients)
+// block = 32 column packs x 8 row lanes; every thread streams 16-byte packs down its rows, the 8 row lanes are
+// reduced through shared memory and one atomic per column per block is issued.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long M, int N,
                                                      long long ld, int rows_per_block) {
   constexpr int PN = Pack<T>::N;
-  const int pk = blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = pk * PN;
-  if (c >= N) return;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cx) * PN;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
   float acc[PN];
 #pragma unroll
   for (int j = 0; j < PN; ++j) acc[j] = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    float f[PN];
-    load_pack(x + r * ld + c, f);
+  if (c < N) {
+    for (long long r = r0 + ry; r < r1; r += 8) {
+      float f[PN];
+      load_pack(x + r * ld + c, f);
 #pragma unroll
-    for (int j = 0; j < PN; ++j) acc[j] += f[j];
+      for (int j = 0; j < PN; ++j) acc[j] += f[j];
+    }
   }
+  __shared__ float sh[8][32 * PN + 1];
 #pragma unroll
-  for (int j = 0; j < PN; ++j) atomicAdd(out + c + j, acc[j]);
+  for (int j = 0; j < PN; ++j) sh[ry][cx * PN + j] = acc[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * PN; i += 256) {
+    const int col = blockIdx.x * 32 * PN + i;
+    if (col < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sh[w][i];
+      atomicAdd(out + col, t);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ fused multi-head masked CE
@@ -530,31 +545,53 @@ extern "C" int pb_octuple_embed_bwd(const void* ids, int ids_int64, const void* 
   return pb_check_launch("octuple_embed_bwd");
 }
 
-static int ln_check(int d, int dtype) {
+static int ln_packs(int d, int dtype) {
   const int n = dtype == PB_DTYPE_BF16 ? 8 : 4;
-  if (d % n != 0 || d > LN_MAXP * 32 * n) return pb_set_error("layernorm: unsupported width (needs d % pack == 0 and d <= 1024 fp32 / 2048 bf16)");
-  return 0;
+  if (d % n != 0 || d > 8 * 32 * n) {
+    pb_set_error("layernorm: unsupported width (needs d % pack == 0 and d <= 1024 fp32 / 2048 bf16)");
+    return -1;
+  }
+  const int packs = (d / n + 31) / 32;
+  return packs <= 1 ? 1 : (packs <= 2 ? 2 : (packs <= 4 ? 4 : 8));
 }
+
+template <typename T, int MAXP>
+static void ln_fwd_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                          long long M, int d, float eps, cudaStream_t st) {
+  const int grid = grid_for(M, 4, 16);
+  layernorm_fwd_kernel<T, MAXP><<<grid, 128, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, M, d, eps);
+}
+template <typename T, int MAXP>
+static void ln_bwd_launch(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                          float* dgamma, float* dbeta, float* dbias, long long M, int d, cudaStream_t st) {
+  const int grid = grid_for(M, 4 * 4, 4);
+  layernorm_bwd_kernel<T, MAXP><<<grid, 128, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
+                                                      dbias, M, d);
+}
+
+#define LN_DISPATCH(FN, ...)                                                         \
+  if (dtype == PB_DTYPE_BF16) {                                                      \
+    switch (mp) { case 1: FN<bf16, 1>(__VA_ARGS__); break; case 2: FN<bf16, 2>(__VA_ARGS__); break; \
+                  case 4: FN<bf16, 4>(__VA_ARGS__); break; default: FN<bf16, 8>(__VA_ARGS__); }      \
+  } else {                                                                           \
+    switch (mp) { case 1: FN<float, 1>(__VA_ARGS__); break; case 2: FN<float, 2>(__VA_ARGS__); break; \
+                  case 4: FN<float, 4>(__VA_ARGS__); break; default: FN<float, 8>(__VA_ARGS__); }     \
+  }
 
 extern "C" int pb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                                 long long M, int d, float eps, int dtype, void* stream) {
-  if (ln_check(d, dtype)) return -1;
-  const int grid = grid_for(M, 4, 16);
-  if (dtype == PB_DTYPE_BF16)
-    layernorm_fwd_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, d, eps);
-  else
-    layernorm_fwd_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, d, eps);
+  const int mp = ln_packs(d, dtype);
+  if (mp < 0) return -1;
+  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, y, mean, rstd, M, d, eps, PB_STREAM(stream));
   return pb_check_launch("layernorm_fwd");
 }
 
 extern "C" int pb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                                void* dx, float* dgamma, float* dbeta, long long M, int d, int dtype, void* stream) {
-  if (ln_check(d, dtype)) return -1;
-  const int grid = grid_for(M, 4 * 8, 4);
-  if (dtype == PB_DTYPE_BF16)
-    layernorm_bwd_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (bf16*)dx, dgamma, dbeta, M, d);
-  else
-    layernorm_bwd_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>((const float*)dy, (const float*)x, gamma, mean, rstd, (float*)dx, dgamma, dbeta, M, d);
+                                void* dx, float* dgamma, float* dbeta, float* dbias, long long M, int d, int dtype,
+                                void* stream) {
+  const int mp = ln_packs(d, dtype);
+  if (mp < 0) return -1;
+  LN_DISPATCH(ln_bwd_launch, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dbias, M, d, PB_STREAM(stream));
   return pb_check_launch("layernorm_bwd");
 }
 
@@ -583,14 +620,15 @@ extern "C" int pb_softmax_bwd(const void* probs, const float* dprobs, void* dsco
 extern "C" int pb_colsum(const void* x, float* out, long long M, int N, long long ld, int dtype, void* stream) {
   const int pn = dtype == PB_DTYPE_BF16 ? 8 : 4;
   if (N % pn != 0 || ld % pn != 0) return pb_set_error("colsum: N and ld must be multiples of the pack width");
-  const int packs = N / pn;
-  const int threads = 256;
-  const int gx = (packs + threads - 1) / threads;
-  int rows_per_block = 64;
-  long long gy = (M + rows_per_block - 1) / rows_per_block;
+  const int gx = (N + 32 * pn - 1) / (32 * pn);
+  int rows_per_block = 128;
+  // keep roughly >= 4 waves of blocks without exploding the atomic count
+  while (rows_per_block > 16 && (long long)gx * ((M + rows_per_block - 1) / rows_per_block) < 4LL * pb_num_sms()) rows_per_block >>= 1;
+  const long long gy = (M + rows_per_block - 1) / rows_per_block;
+  if (gy > 65535) return pb_set_error("colsum: too many row blocks");
   dim3 grid(gx, (unsigned)gy);
-  if (dtype == PB_DTYPE_BF16) colsum_kernel<bf16><<<grid, threads, 0, PB_STREAM(stream)>>>((const bf16*)x, out, M, N, ld, rows_per_block);
-  else colsum_kernel<float><<<grid, threads, 0, PB_STREAM(stream)>>>((const float*)x, out, M, N, ld, rows_per_block);
+  if (dtype == PB_DTYPE_BF16) colsum_kernel<bf16><<<grid, 256, 0, PB_STREAM(stream)>>>((const bf16*)x, out, M, N, ld, rows_per_block);
+  else colsum_kernel<float><<<grid, 256, 0, PB_STREAM(stream)>>>((const float*)x, out, M, N, ld, rows_per_block);
   return pb_check_launch("colsum");
 }
 

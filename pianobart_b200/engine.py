@@ -206,10 +206,10 @@ class Plan:
         self._add('ln_fwd', self.lib.pb_layernorm_fwd, C.c_void_p(x), C.c_void_p(gamma), C.c_void_p(beta),
                   C.c_void_p(y), C.c_void_p(mean), C.c_void_p(rstd), C.c_longlong(M), d, C.c_float(1e-5), self.dtype)
 
-    def ln_bwd(self, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, d):
+    def ln_bwd(self, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, d, dbias=0):
         self._add('ln_bwd', self.lib.pb_layernorm_bwd, C.c_void_p(dy), C.c_void_p(x), C.c_void_p(gamma),
                   C.c_void_p(mean), C.c_void_p(rstd), C.c_void_p(dx), C.c_void_p(dgamma), C.c_void_p(dbeta),
-                  C.c_longlong(M), d, self.dtype)
+                  C.c_void_p(dbias or None), C.c_longlong(M), d, self.dtype)
 
     def softmax_fwd(self, s, p, keep, B, H, Sq, Sk, causal):
         self._add('softmax_fwd', self.lib.pb_softmax_fwd, C.c_void_p(s), C.c_void_p(p), C.c_void_p(keep or None), B, H,
@@ -464,8 +464,7 @@ class BackboneGraph:
                 # -- FFN backward
                 bw.ln_bwd(_ptr(dcur), _ptr(r['A2']), self.Pf(lp + '.final_layer_norm.weight'), _ptr(r['st2']),
                           _ptr(r['st2'], M), _ptr(dA), self.G(lp + '.final_layer_norm.weight'),
-                          self.G(lp + '.final_layer_norm.bias'), M, d)
-                bw.colsum(_ptr(dA), self.G(lp + '.fc2.bias'), M, d, d)
+                          self.G(lp + '.final_layer_norm.bias'), M, d, dbias=self.G(lp + '.fc2.bias'))
                 bw.wgrad(_ptr(dA), _ptr(r['G']), self.G(lp + '.fc2.weight'), d, F, M, d, F, name=ln('dW_fc2'))
                 bw.gemm(_ptr(dA), self.W(lp + '.fc2.weight'), _ptr(dZ), M, F, d, d, F, F, b_mn=1,
                         flags=L.PB_GEMM_MUL_DGELU, aux=_ptr(r['Z']), ldaux=F, name=ln('dZ'))
@@ -481,8 +480,7 @@ class BackboneGraph:
                     dKVc = self.buf('g.dKVc', Mmax, 2 * d)
                     bw.ln_bwd(_ptr(dmid), _ptr(r['Ac']), self.Pf(lp + '.encoder_attn_layer_norm.weight'),
                               _ptr(r['stc']), _ptr(r['stc'], M), _ptr(dA), self.G(lp + '.encoder_attn_layer_norm.weight'),
-                              self.G(lp + '.encoder_attn_layer_norm.bias'), M, d)
-                    bw.colsum(_ptr(dA), self.G(ca + '.out_proj.bias'), M, d, d)
+                              self.G(lp + '.encoder_attn_layer_norm.bias'), M, d, dbias=self.G(ca + '.out_proj.bias'))
                     bw.wgrad(_ptr(dA), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
                     bw.gemm(_ptr(dA), self.W(ca + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dOc'))
                     # dP = dO V^T ; dV = P^T dO ; dS = softmax'(P, dP) ; dQ = scale dS K ; dK = scale dS^T Q
@@ -515,8 +513,7 @@ class BackboneGraph:
                 cz = 1 if is_dec else 0
                 bw.ln_bwd(_ptr(dmid), _ptr(r['A']), self.Pf(lp + '.self_attn_layer_norm.weight'), _ptr(r['st1']),
                           _ptr(r['st1'], M), _ptr(dA), self.G(lp + '.self_attn_layer_norm.weight'),
-                          self.G(lp + '.self_attn_layer_norm.bias'), M, d)
-                bw.colsum(_ptr(dA), self.G(sa + '.out_proj.bias'), M, d, d)
+                          self.G(lp + '.self_attn_layer_norm.bias'), M, d, dbias=self.G(sa + '.out_proj.bias'))
                 bw.wgrad(_ptr(dA), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
                 bw.gemm(_ptr(dA), self.W(sa + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dO'))
                 QKV, Pm = r['QKV'], r['P']
@@ -543,11 +540,10 @@ class BackboneGraph:
             dY0 = dA
             bw.ln_bwd(_ptr(dcur), _ptr(Y0), self.Pf(pre + '.layernorm_embedding.weight'), _ptr(st0), _ptr(st0, M),
                       _ptr(dY0), self.G(pre + '.layernorm_embedding.weight'), self.G(pre + '.layernorm_embedding.bias'),
-                      M, d)
+                      M, d, dbias=0 if custom_dec else self.G('encoder_linear.bias'))
             # d pos[s+2] += sum_b dY0[b, s]  == column sums of dY0 viewed as [B, S*d]
             bw.colsum(_ptr(dY0), self.G(pre + '.embed_positions.weight') + 2 * d * 4, B, S * d, S * d)
             if not custom_dec:
-                bw.colsum(_ptr(dY0), self.G('encoder_linear.bias'), M, d, d)
                 bw.wgrad(_ptr(dY0), _ptr(X), self.G('encoder_linear.weight'), d, 2048, M, d, 2048, name=nm('dW_in'))
                 dX = self.buf('g.dX', Mmax, 2048)
                 bw.gemm(_ptr(dY0), self.W('encoder_linear.weight'), _ptr(dX), M, 2048, d, d, 2048, 2048, b_mn=1,

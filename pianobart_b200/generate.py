@@ -1,0 +1,251 @@
+"""KV-cache autoregressive generation, replacing the O(S^2) loop of reference
+`PianoBartLM.forward(generate=True)` (model.py:28-66) and `sample`/`sampling`/`nucleus` (model.py:68-107).
+
+Semantics kept from the reference: decoder starts from the <SOS> row, every step samples the 8 attributes
+with temperatures t=[1.2,1.2,5,1,2,5,5,1.2] and nucleus p=[1,1,1,.9,.9,1,1,.9] (p == 1 degenerates to greedy),
+one numpy uniform is consumed per attribute per step in attribute order (np.random.choice), generation stops at
+the first step where any attribute >= its <PAD> id and that step is not written, the result is PAD-filled
+int64 (B,S,8).  Batch sizes > 1 are a new capability (the reference exits unless batch == 1).
+
+One decode step = one CUDA-graph replay of ~120 launches; the step index, the sampled token hand-over and the
+stop flags live in device memory so the same graph is replayed for every position.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import engine as E
+
+SAMPLE_T = [1.2, 1.2, 5, 1, 2, 5, 5, 1.2]      # model.py:70
+SAMPLE_P = [1, 1, 1, 0.9, 0.9, 1, 1, 0.9]      # model.py:71
+
+
+class Generator:
+    def __init__(self, lm, B, S_enc, S_max=None, use_graph=True):
+        pb = lm.pianobart
+        pb._ensure_packed()
+        if pb.pb_dtype != E.PB_BF16:
+            raise L.PBError('KV-cache decode is implemented for the bf16 production mode only')
+        self.lm, self.pb = lm, pb
+        self.B, self.Se = B, S_enc
+        self.S = S_max or S_enc
+        self.use_graph = use_graph
+        lay = pb.layout
+        d, F, H = lay.d, lay.ffn, pb.heads
+        self.d, self.F, self.H, self.hd = d, F, H, d // H
+        dev = pb._flat.device
+        self.dev = dev
+        self.lib = L.lib()
+        bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+        z = lambda *s, dt=bf: torch.zeros(*s, device=dev, dtype=dt)
+        S = self.S
+        self.t_dev = z(1, dt=i32)
+        self.cur_tok = z(B, 8, dt=i32)
+        self.result = z(B, S, 8, dt=i32)
+        self.sampled = z(B, S, 8, dt=i32)
+        self.done = z(B, dt=i32)
+        self.n_written = z(B, dt=i32)
+        self.uniforms = z(B, S, 8, dt=torch.float64)
+        self.forced = None
+        self.x_emb = z(B, 2048)
+        nmax = max(3 * d, F, E.VOCAB, 2 * d)
+        self.acc = z(B, nmax, dt=f32)
+        self.hA, self.hB, self.h1, self.h2 = z(B, d), z(B, d), z(B, d), z(B, d)
+        self.qkv, self.qc, self.ao, self.f1 = z(B, 3 * d), z(B, d), z(B, d), z(B, F)
+        self.logits = z(B, E.VOCAB, dt=f32)
+        self.self_cache = [z(B, S, 2 * d) for _ in range(lay.dec_layers)]
+        self.cross_kv = [z(B * S_enc, 2 * d) for _ in range(lay.dec_layers)]
+        self.enc_graph = pb._graph(B, S_enc, 0, False, False)
+        self.ntok_arr = (C.c_int * 8)(*E.N_TOKENS)
+        self.pad_arr = (C.c_int * 8)(*[int(x) for x in pb.pad_word_np])
+        self.temp_arr = (C.c_float * 8)(*[float(x) for x in SAMPLE_T])
+        self.p_arr = (C.c_float * 8)(*[float(x) for x in SAMPLE_P])
+        self.sos = torch.tensor(pb.sos_word_np, dtype=i32, device=dev)
+        self.prefill = E.Plan(E.PB_BF16)
+        self.step = E.Plan(E.PB_BF16)
+        self._build()
+        self.graph = None
+
+    # ------------------------------------------------------------------
+    def _W(self, name):
+        return E._ptr(self.pb._wact, self.pb.layout.off(name))
+
+    def _Pf(self, name):
+        return E._ptr(self.pb._flat, self.pb.layout.off(name))
+
+    def _skinny(self, plan, x, w, N, K, name):
+        """acc[B, N] += x[B, K] W[N, K]^T : tcgen05 GEMM with M = batch, split over K so that every SM streams a
+        slice of the weight matrix exactly once."""
+        tiles = (N + 127) // 128
+        kblocks = (K + 63) // 64
+        split = max(1, min(kblocks, (148 + tiles - 1) // tiles))
+        plan.gemm(E._ptr(x), w, E._ptr(self.acc), self.B, N, K, K, K, N, flags=L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC,
+                  split_k=split, name=name)
+        plan.ops[-1][2][0]._obj.block_n = 128
+
+    def _finalize(self, plan, N, bias=0, residual=None, pos=0, ln=None, out=None, out_f32=None, gelu=0):
+        P = C.c_void_p
+        g, b = (self._Pf(ln + '.weight'), self._Pf(ln + '.bias')) if ln else (0, 0)
+        plan._add('decode_finalize', self.lib.pb_decode_finalize, P(E._ptr(self.acc)), P(bias or None),
+                  P(E._ptr(residual) if residual is not None else None), P(pos or None), P(E._ptr(self.t_dev)), P(g or None),
+                  P(b or None), P(E._ptr(out) if out is not None else None),
+                  P(E._ptr(out_f32) if out_f32 is not None else None), self.B, N, gelu)
+
+    def _attn(self, plan, q, q_ld, k_new, v_new, kc, vc, kv_bs, kv_ld, keep, n_keys, append, out, max_keys):
+        P = C.c_void_p
+        plan._add('decode_attn', self.lib.pb_decode_attn, P(q), q_ld, P(k_new or None), P(v_new or None), P(kc), P(vc),
+                  C.c_longlong(kv_bs), kv_ld, P(keep or None), n_keys, P(E._ptr(self.t_dev)), append, P(E._ptr(out)), self.d,
+                  self.B, self.H, self.hd, C.c_float(self.hd ** -0.5), max_keys)
+
+    def _build(self):
+        pb, lay = self.pb, self.pb.layout
+        B, d, F, Se, S = self.B, self.d, self.F, self.Se, self.S
+        eg = self.enc_graph
+        # ---- prefill: cross-attention K/V of every decoder layer from the encoder output
+        for l in range(lay.dec_layers):
+            ca = 'bart.decoder.layers.%d.encoder_attn' % l
+            self.prefill.gemm(E._ptr(eg.enc_out), self._W(ca + '.wkv'), E._ptr(self.cross_kv[l]), B * Se, 2 * d, d, d, d, 2 * d,
+                              bias=self._Pf(ca + '.bkv'), name='kv_c%d' % l)
+        # ---- one decode step
+        st = self.step
+        P = C.c_void_p
+        st._add('embed', self.lib.pb_octuple_embed_fwd, P(E._ptr(self.cur_tok)), 0, P(self._W('emb')), P(E._ptr(self.x_emb)),
+                C.c_longlong(B), self.ntok_arr, E.PB_BF16, P(None))
+        self._skinny(st, self.x_emb, self._W('encoder_linear.weight'), d, 2048, 'in_linear')
+        self._finalize(st, d, bias=self._Pf('encoder_linear.bias'), pos=self._W('bart.decoder.embed_positions.weight'),
+                       ln='bart.decoder.layernorm_embedding', out=self.hA)
+        h = self.hA
+        for l in range(lay.dec_layers):
+            lp = 'bart.decoder.layers.%d' % l
+            sa, ca = lp + '.self_attn', lp + '.encoder_attn'
+            self._skinny(st, h, self._W(sa + '.wqkv'), 3 * d, d, 'qkv%d' % l)
+            self._finalize(st, 3 * d, bias=self._Pf(sa + '.bqkv'), out=self.qkv)
+            cache = self.self_cache[l]
+            self._attn(st, E._ptr(self.qkv), 3 * d, E._ptr(self.qkv, d), E._ptr(self.qkv, 2 * d), E._ptr(cache), E._ptr(cache, d),
+                       S * 2 * d, 2 * d, 0, 0, 1, self.ao, S)
+            self._skinny(st, self.ao, self._W(sa + '.out_proj.weight'), d, d, 'o%d' % l)
+            self._finalize(st, d, bias=self._Pf(sa + '.out_proj.bias'), residual=h, ln=lp + '.self_attn_layer_norm', out=self.h1)
+            self._skinny(st, self.h1, self._W(ca + '.q_proj.weight'), d, d, 'qc%d' % l)
+            self._finalize(st, d, bias=self._Pf(ca + '.q_proj.bias'), out=self.qc)
+            kv = self.cross_kv[l]
+            self._attn(st, E._ptr(self.qc), d, 0, 0, E._ptr(kv), E._ptr(kv, d), Se * 2 * d, 2 * d, E._ptr(eg.enc_keep), Se, 0,
+                       self.ao, Se)
+            self._skinny(st, self.ao, self._W(ca + '.out_proj.weight'), d, d, 'oc%d' % l)
+            self._finalize(st, d, bias=self._Pf(ca + '.out_proj.bias'), residual=self.h1, ln=lp + '.encoder_attn_layer_norm',
+                           out=self.h2)
+            self._skinny(st, self.h2, self._W(lp + '.fc1.weight'), F, d, 'fc1_%d' % l)
+            self._finalize(st, F, bias=self._Pf(lp + '.fc1.bias'), out=self.f1, gelu=1)
+            self._skinny(st, self.f1, self._W(lp + '.fc2.weight'), d, F, 'fc2_%d' % l)
+            nxt = self.hB if h is self.hA else self.hA
+            self._finalize(st, d, bias=self._Pf(lp + '.fc2.bias'), residual=self.h2, ln=lp + '.final_layer_norm', out=nxt)
+            h = nxt
+        self._skinny(st, h, self._W('heads.w'), E.VOCAB, d, 'heads')
+        self._finalize(st, E.VOCAB, bias=self._Pf('heads.b'), out_f32=self.logits)
+        self._sample_idx = len(st.ops)
+        st._add('sample', self.lib.pb_decode_sample, P(E._ptr(self.logits)), P(E._ptr(self.uniforms)), P(None),
+                P(E._ptr(self.t_dev)), P(E._ptr(self.cur_tok)), P(E._ptr(self.sampled)), B, S, self.ntok_arr, self.temp_arr,
+                self.p_arr)
+        st._add('advance', self.lib.pb_decode_advance, P(E._ptr(self.cur_tok)), P(E._ptr(self.result)), P(E._ptr(self.done)),
+                P(E._ptr(self.t_dev)), P(E._ptr(self.n_written)), B, S, self.pad_arr)
+        self.launches_per_step = len(st.ops)
+
+    def _set_forced(self, forced):
+        """Teacher forcing (parity tests): the token fed to step t+1 is forced[b, t] instead of the sampled one."""
+        P = C.c_void_p
+        name, fn, args = self.step.ops[self._sample_idx]
+        args = list(args)
+        if forced is None:
+            self.forced = None
+            args[2] = P(None)
+        else:
+            self.forced = forced.to(device=self.dev, dtype=torch.int32).contiguous()
+            args[2] = P(E._ptr(self.forced))
+        self.step.ops[self._sample_idx] = (name, fn, tuple(args))
+        self.graph = None
+
+    # ------------------------------------------------------------------
+    def start(self, input_ids_encoder, encoder_attention_mask, uniforms=None, forced=None):
+        pb = self.pb
+        pb._sync_weights()
+        pb._live_graph = None
+        if (forced is None) != (self.forced is None) or forced is not None:
+            self._set_forced(forced)
+        eg = self.enc_graph
+        eg.set_inputs(input_ids_encoder, encoder_attention_mask)
+        eg.forward()
+        self.prefill.run()
+        self.t_dev.zero_()
+        self.done.zero_()
+        self.n_written.zero_()
+        self.acc.zero_()
+        self.cur_tok.copy_(self.sos.unsqueeze(0).expand(self.B, 8))
+        pad = torch.tensor(pb.pad_word_np, dtype=torch.int32, device=self.dev)
+        self.result.copy_(pad.view(1, 1, 8).expand_as(self.result))
+        if uniforms is not None:
+            self.uniforms.copy_(torch.as_tensor(uniforms, dtype=torch.float64).reshape(self.B, self.S, 8), non_blocking=True)
+
+    def run_steps(self, n):
+        """Replays n decode steps (CUDA graph).  Returns the number of library launches issued."""
+        if not self.use_graph:
+            for _ in range(n):
+                self.step.run()
+            return n * self.launches_per_step
+        if self.graph is None:
+            # one eager step to warm up (function attributes, tensor-map cache), then rewind its side effects
+            snap = [t.clone() for t in (self.t_dev, self.cur_tok, self.result, self.done, self.n_written, self.sampled)]
+            caches = [c[:, :1].clone() for c in self.self_cache]
+            self.step.run()
+            torch.cuda.synchronize()
+            for t, s in zip((self.t_dev, self.cur_tok, self.result, self.done, self.n_written, self.sampled), snap):
+                t.copy_(s)
+            for c, s in zip(self.self_cache, caches):
+                c[:, :1].copy_(s)
+            self.acc.zero_()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step.run()
+            self.graph = g
+            # capture does not execute: state is unchanged
+        for _ in range(n):
+            self.graph.replay()
+        return n * self.launches_per_step
+
+    def finish(self):
+        torch.cuda.synchronize()
+        return self.result.to(torch.int64), self.n_written.cpu().numpy(), self.done.cpu().numpy()
+
+
+_GEN_CACHE = {}
+
+
+def generate(lm, input_ids_encoder, encoder_attention_mask=None, check_every=32):
+    """Drop-in for `PianoBartLM.forward(..., generate=True)`; consumes numpy's global RNG like the reference
+    (8 uniforms per executed step, attribute order)."""
+    B, S = input_ids_encoder.shape[0], input_ids_encoder.shape[1]
+    key = (id(lm), B, S)
+    gen = _GEN_CACHE.get(key)
+    if gen is None:
+        _GEN_CACHE.clear()
+        gen = Generator(lm, B, S, S)
+        _GEN_CACHE[key] = gen
+    state = np.random.get_state()
+    uniforms = np.random.random_sample((B, S, 8))
+    with torch.no_grad():
+        gen.start(input_ids_encoder, encoder_attention_mask, uniforms)
+        done_steps = 0
+        while done_steps < S:
+            n = min(check_every, S - done_steps)
+            gen.run_steps(n)
+            done_steps += n
+            if bool(gen.done.all().item()):
+                break
+        result, n_written, done = gen.finish()
+    if B == 1:
+        # leave numpy's global stream exactly where the reference would: 8 draws per executed step
+        executed = int(n_written[0]) + (1 if done[0] else 0)
+        np.random.set_state(state)
+        if executed:
+            np.random.random_sample(8 * executed)
+    return result.to(input_ids_encoder.device)

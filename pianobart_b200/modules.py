@@ -269,6 +269,15 @@ class PianoBart(nn.Module):
                     view.copy_(p.grad)
                 p.grad = view
 
+    def flat_grad(self, name):
+        """View of the flat fp32 gradient buffer for one reference-named parameter (fused trainer path, where
+        Parameter.grad is not populated)."""
+        off, shape = self.layout.entries[name]
+        n = 1
+        for x in shape:
+            n *= x
+        return self._grad[off:off + n].view(shape)
+
     def zero_grad_flat(self):
         self._ensure_packed()
         self._grad.zero_()

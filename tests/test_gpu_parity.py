@@ -1,0 +1,331 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI / the module API, against
+(a) the golden fixtures recorded from the real reference, (b) the oracle restatement on the same seeded
+inputs, (c) plain torch fp32 references for single floating-point kernels.
+
+Tolerances (north star): noising ids / masks bit-exact; fp32 mode loss <= 1e-4 relative;
+bf16 mode loss <= 1e-2 relative.
+"""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from util import build_cuda_model, golden_inputs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = {'fp32': 1e-4, 'bf16': 1e-2}
+
+
+def _lib():
+    from pianobart_b200 import _lib as L
+    return L, L.lib()
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+# --------------------------------------------------------------------------- GEMM (tcgen05) vs torch fp32
+@pytest.mark.parametrize('a_mn,b_mn,bn', [(0, 0, 128), (0, 0, 256), (0, 1, 256), (1, 0, 128), (1, 1, 256), (1, 1, 128)])
+def test_gemm_tc_layouts(a_mn, b_mn, bn):
+    L, lib = _lib()
+    dev = 'cuda:0'
+    torch.manual_seed(1)
+    M, N, K = 384, 520, 328          # M, N, K tails (not multiples of the tile)
+    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    Bm = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+    a_st = A.t().contiguous() if a_mn else A
+    b_st = Bm.t().contiguous() if b_mn else Bm
+    out = torch.zeros(M, N, device=dev)
+    d = L.GemmDesc()
+    d.a, d.b, d.c = a_st.data_ptr(), b_st.data_ptr(), out.data_ptr()
+    d.M, d.N, d.K = M, N, K
+    d.a_mn_major, d.b_mn_major = a_mn, b_mn
+    d.lda, d.ldb, d.ldc = (M if a_mn else K), (N if b_mn else K), N
+    d.alpha, d.flags, d.split_k, d.block_n = 1.0, L.PB_GEMM_OUT_F32, 1, bn
+    L.check(lib.pb_gemm_bf16(C.byref(d), L.stream_ptr()), 'gemm')
+    torch.cuda.synchronize()
+    ref = A.float() @ Bm.float().t()
+    assert _rel(out.cpu(), ref.cpu()) < 1e-5      # bf16 products are exact in fp32; only summation order differs
+
+
+def test_gemm_tc_epilogues_and_splitk():
+    L, lib = _lib()
+    dev = 'cuda:0'
+    torch.manual_seed(2)
+    M, N, K = 512, 768, 1024
+    A = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev).bfloat16()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    aux = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    d = L.GemmDesc()
+    d.a, d.b, d.c, d.bias, d.residual, d.aux = A.data_ptr(), W.data_ptr(), out.data_ptr(), bias.data_ptr(), res.data_ptr(), aux.data_ptr()
+    d.M, d.N, d.K, d.lda, d.ldb, d.ldc, d.ldr, d.ldaux = M, N, K, K, K, N, N, N
+    d.alpha, d.flags, d.split_k = 1.0, L.PB_GEMM_GELU | L.PB_GEMM_AUX_PREACT, 1
+    L.check(lib.pb_gemm_bf16(C.byref(d), L.stream_ptr()), 'gemm')
+    torch.cuda.synchronize()
+    z = A.float() @ W.float().t() + bias
+    ref = torch.nn.functional.gelu(z.bfloat16().float()) + res.float()
+    assert _rel(aux.float().cpu(), z.cpu()) < 1e-2
+    assert _rel(out.float().cpu(), ref.cpu()) < 1e-2
+    # split-K, fp32 atomic accumulate on top of existing content (dW accumulation)
+    X = (torch.randn(K, M, device=dev) * 0.3).bfloat16()   # stored [K][M]: MN-major operands
+    Y = (torch.randn(K, N, device=dev) * 0.3).bfloat16()
+    acc = torch.ones(M, N, device=dev)
+    d2 = L.GemmDesc()
+    d2.a, d2.b, d2.c = X.data_ptr(), Y.data_ptr(), acc.data_ptr()
+    d2.M, d2.N, d2.K, d2.lda, d2.ldb, d2.ldc = M, N, K, M, N, N
+    d2.a_mn_major = d2.b_mn_major = 1
+    d2.alpha, d2.flags, d2.split_k = 1.0, L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC, 4
+    L.check(lib.pb_gemm_bf16(C.byref(d2), L.stream_ptr()), 'gemm')
+    torch.cuda.synchronize()
+    ref2 = X.float().t() @ Y.float() + 1.0
+    assert _rel(acc.cpu(), ref2.cpu()) < 1e-5
+
+
+# --------------------------------------------------------------------------- single kernels vs torch fp32
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_layernorm_fwd_bwd(dtype):
+    L, lib = _lib()
+    dev = 'cuda:0'
+    code = 0 if dtype == 'fp32' else 1
+    tdt = torch.float32 if dtype == 'fp32' else torch.bfloat16
+    torch.manual_seed(3)
+    M, d = 777, 1024
+    x = torch.randn(M, d, device=dev).to(tdt)
+    dy = torch.randn(M, d, device=dev).to(tdt)
+    g = torch.randn(d, device=dev) * 0.1 + 1
+    b = torch.randn(d, device=dev) * 0.1
+    y = torch.empty_like(x); dx = torch.empty_like(x)
+    mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
+    dg = torch.zeros(d, device=dev); db = torch.zeros(d, device=dev); dbias = torch.zeros(d, device=dev)
+    P = C.c_void_p
+    L.check(lib.pb_layernorm_fwd(P(x.data_ptr()), P(g.data_ptr()), P(b.data_ptr()), P(y.data_ptr()), P(mean.data_ptr()),
+                                 P(rstd.data_ptr()), C.c_longlong(M), d, C.c_float(1e-5), code, L.stream_ptr()), 'ln')
+    L.check(lib.pb_layernorm_bwd(P(dy.data_ptr()), P(x.data_ptr()), P(g.data_ptr()), P(mean.data_ptr()), P(rstd.data_ptr()),
+                                 P(dx.data_ptr()), P(dg.data_ptr()), P(db.data_ptr()), P(dbias.data_ptr()), C.c_longlong(M), d,
+                                 code, L.stream_ptr()), 'ln_bwd')
+    torch.cuda.synchronize()
+    xr = x.float().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-5)
+    yr.backward(dy.float())
+    tol = 1e-5 if dtype == 'fp32' else 1e-2
+    assert _rel(y.float().cpu(), yr.detach().cpu()) < tol
+    assert _rel(dx.float().cpu(), xr.grad.cpu()) < tol
+    assert _rel(dg.cpu(), gr.grad.cpu()) < 1e-4
+    assert _rel(db.cpu(), br.grad.cpu()) < 1e-4
+    assert _rel(dbias.cpu(), dx.float().sum(0).cpu()) < (1e-3 if dtype == 'fp32' else 3e-2)
+
+
+@pytest.mark.parametrize('causal', [0, 1])
+def test_softmax_fwd_bwd_masked(causal):
+    L, lib = _lib()
+    dev = 'cuda:0'
+    torch.manual_seed(4)
+    B, H, S = 2, 3, 200
+    s = torch.randn(B, H, S, S, device=dev) * 3
+    keep = (torch.rand(B, S, device=dev) > 0.2)
+    keep[:, 0] = True
+    keep_u8 = keep.to(torch.uint8)
+    p = torch.empty(B, H, S, S, device=dev)
+    P = C.c_void_p
+    L.check(lib.pb_softmax_fwd(P(s.data_ptr()), P(p.data_ptr()), P(keep_u8.data_ptr()), B, H, S, S, causal, 0, L.stream_ptr()), 'sm')
+    allow = keep[:, None, None, :].expand(B, H, S, S)
+    if causal:
+        allow = allow & torch.ones(S, S, dtype=torch.bool, device=dev).tril()
+    sr = s.clone().requires_grad_(True)
+    pr = torch.softmax(sr.masked_fill(~allow, float('-inf')), -1)
+    torch.cuda.synchronize()
+    assert _rel(p.cpu(), pr.detach().cpu()) < 1e-6
+    assert (p[~allow] == 0).all()
+    dp = torch.randn(B, H, S, S, device=dev)
+    dp[~allow] = float('nan')            # skipped tiles may hold garbage: the kernel must not read them
+    ds = torch.empty_like(p)
+    L.check(lib.pb_softmax_bwd(P(p.data_ptr()), P(dp.data_ptr()), P(ds.data_ptr()), P(keep_u8.data_ptr()), B, H, S, S, causal,
+                               0, L.stream_ptr()), 'smb')
+    torch.cuda.synchronize()
+    pr.backward(torch.nan_to_num(dp, nan=0.0))
+    assert _rel(ds.cpu(), sr.grad.cpu()) < 1e-5
+
+
+def test_adamw_matches_hf_semantics():
+    """Reference optimizer: transformers 4.29.2 AdamW(lr, weight_decay=0.01) (pretrain.py:76) after
+    clip_grad_norm_(3.0) (pretrain.py:195); restated here in torch double."""
+    L, lib = _lib()
+    dev = 'cuda:0'
+    torch.manual_seed(5)
+    n = 100003
+    p = torch.randn(n, device=dev); g = torch.randn(n, device=dev) * 0.05
+    m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+    pr, mr, vr = p.double().clone(), m.double().clone(), v.double().clone()
+    wb = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    lr, b1, b2, eps, wd, maxn = 2e-5, 0.9, 0.999, 1e-6, 0.01, 3.0
+    P = C.c_void_p
+    for step in (1, 2, 3):
+        gs = torch.zeros(1, device=dev)
+        L.check(lib.pb_sumsq(P(g.data_ptr()), C.c_longlong(n), P(gs.data_ptr()), L.stream_ptr()), 'sumsq')
+        L.check(lib.pb_adamw(P(p.data_ptr()), P(m.data_ptr()), P(v.data_ptr()), P(g.data_ptr()), P(wb.data_ptr()),
+                             C.c_longlong(n), C.c_float(lr), C.c_float(b1), C.c_float(b2), C.c_float(eps), C.c_float(wd),
+                             step, P(gs.data_ptr()), C.c_float(maxn), C.c_float(1.0), C.c_float(1.0), L.stream_ptr()), 'adamw')
+        gd = g.double()
+        norm = gd.norm()
+        gd = gd * min(1.0, maxn / (norm.item() + 1e-6))
+        mr = b1 * mr + (1 - b1) * gd
+        vr = b2 * vr + (1 - b2) * gd * gd
+        step_size = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+        pr = pr - step_size * mr / (vr.sqrt() + eps)
+        pr = pr - lr * wd * pr
+        torch.cuda.synchronize()
+        assert abs(gs.item() - (g.double() ** 2).sum().item()) < 1e-4 * gs.item()
+    assert _rel(p.cpu(), pr.cpu()) < 1e-6
+    assert _rel(wb.float().cpu(), pr.cpu()) < 1e-2
+
+
+# --------------------------------------------------------------------------- whole path vs reference fixtures
+@pytest.mark.parametrize('name', ['fwd_tiny', 'fwd_mid'])
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_forward_loss_grads_vs_reference(name, dtype):
+    from oracle import pianobart_oracle as O
+    g = load_golden(name)
+    pb, lm = build_cuda_model(g['cfg'], int(g['seed']), dtype)
+    lm.eval()
+    enc, dec, ori, lmask, em, dm = golden_inputs(g)
+    y = lm(enc, dec, em, dm)
+    total, losses = O.pretrain_loss(y, ori, lmask)
+    ref = float(g['total'])
+    assert abs(total.item() - ref) / ref < LOSS_TOL[dtype]
+    logits = torch.cat(y, -1).detach().cpu().numpy()
+    want = g['logits'] if 'logits' in g.files else g['logits_sub']
+    got = logits if 'logits' in g.files else logits[:, ::int(g['logit_stride'])]
+    assert _rel(got, want) < (1e-4 if dtype == 'fp32' else 3e-2)
+    lm.zero_grad()
+    total.backward()
+    sd = dict(lm.named_parameters())
+    tol = 1e-4 if dtype == 'fp32' else 5e-2
+    for k in g.files:
+        if k.startswith('grad:'):
+            n = k[5:]
+            kk = n if n.startswith('mask_lm') else 'pianobart.' + n
+            assert _rel(sd[kk].grad.cpu().numpy(), g[k]) < tol, n
+    gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in sd.values() if p.grad is not None)).item()
+    assert abs(gn - float(g['grad_total_norm'])) / float(g['grad_total_norm']) < (1e-4 if dtype == 'fp32' else 2e-2)
+
+
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_default_model_loss_vs_reference(dtype):
+    """BASELINE.json configs[0] scale: default pretrain.py model (d=1024, 8+8 layers, S=1024), batch 1."""
+    from oracle import pianobart_oracle as O
+    g = load_golden('fwd_default')
+    pb, lm = build_cuda_model(g['cfg'], int(g['seed']), dtype)
+    lm.eval()
+    enc, dec, ori, lmask, em, dm = golden_inputs(g)
+    with torch.no_grad():
+        y = lm(enc, dec, em, dm)
+    total, losses = O.pretrain_loss(y, ori, lmask)
+    ref = float(g['total'])
+    assert abs(total.item() - ref) / ref < LOSS_TOL[dtype]
+    st = int(g['logit_stride'])
+    got = torch.cat(y, -1).cpu().numpy()[:, ::st]
+    assert _rel(got, g['logits_sub']) < (2e-4 if dtype == 'fp32' else 5e-2)
+    accs = O.pretrain_accuracy(y, ori, lmask)
+    if dtype == 'fp32':
+        assert np.allclose([a.item() for a in accs], g['accs'], atol=1e-6)
+
+
+def test_fused_step_matches_autograd_path_and_oracle():
+    """pb_heads_ce + backward plan (fused trainer path) == module autograd path == reference fixture."""
+    from pianobart_b200.pretrain import PretrainStep
+    g = load_golden('fwd_tiny')
+    pb, lm = build_cuda_model(g['cfg'], int(g['seed']), 'fp32')
+    enc, dec, ori, lmask, em, dm = golden_inputs(g)
+    B, S = enc.shape[0], enc.shape[1]
+    st = PretrainStep(lm, B, S, None, 0.15)
+    st.set_device_batch(enc, dec, ori, lmask, em, dm)
+    st.run(train=True)
+    total, losses, accs = st.fetch_stats()
+    assert abs(total - float(g['total'])) / float(g['total']) < 1e-5
+    assert np.allclose(losses, g['losses'], rtol=1e-5)
+    assert np.allclose(accs, g['accs'], atol=1e-6)
+    for k in g.files:
+        if k.startswith('grad:'):
+            n = k[5:]
+            assert _rel(pb.flat_grad(n).cpu().numpy(), g[k]) < 1e-4, n
+
+
+# --------------------------------------------------------------------------- noising kernel: bit-exact
+@pytest.mark.parametrize('S', [1024, 64])
+def test_noising_device_bit_exact(S):
+    from pianobart_b200.pretrain import PretrainStep
+    g = load_golden('noising')
+    ori, enc, lmk = g['S%d_ori' % S].astype(np.int64), g['S%d_enc' % S], g['S%d_loss_mask' % S]
+    pb, lm = build_cuda_model((64, 1, 1, 2, 64, 1024), 3, 'fp32')
+    B = ori.shape[1]
+    st = PretrainStep(lm, B, S, None, 0.15)
+    for seed in range(ori.shape[0]):
+        random.seed(seed)
+        np.random.seed(seed)
+        st.upload(ori[seed])
+        st.noise()
+        gph = st.graph
+        got = gph.enc_ids.view(B, S, 8).cpu().numpy()
+        assert np.array_equal(got, enc[seed].astype(np.int64)), seed
+        assert np.array_equal(st.loss_mask.view(B, S, 8).cpu().numpy().astype(np.uint8), lmk[seed]), seed
+        dec = gph.dec_ids.view(B, S, 8).cpu().numpy()
+        assert np.array_equal(dec[:, 1:], ori[seed][:, :-1]) and (dec[:, 0] == pb.sos_word_np).all()
+        assert np.array_equal(gph.enc_keep.view(B, S).cpu().numpy(), (enc[seed][:, :, 0] != 256).astype(np.uint8))
+        assert np.array_equal(gph.dec_keep.view(B, S).cpu().numpy(), (dec[:, :, 0] != 256).astype(np.uint8))
+        assert np.array_equal(st.targets.view(B, S, 8).cpu().numpy(), ori[seed])
+
+
+def test_noising_properties_full_size():
+    """Size-independent properties at BASELINE batch x seq (16 x 1024): every corruption keeps the multiset of
+    rows consistent with its definition."""
+    from oracle import params as P
+    from pianobart_b200.pretrain import PretrainStep
+    pb, lm = build_cuda_model((64, 1, 1, 2, 64, 1024), 3, 'fp32')
+    B, S = 16, 1024
+    st = PretrainStep(lm, B, S, None, 0.15)
+    ori = P.synth_ids(B, S, 99, padded=True)
+    PADROW = np.array([256, 128, 129, 256, 128, 32, 254, 49])
+    for choice in (1, 2, 3, 4, 5):
+        random.seed(choice)
+        np.random.seed(choice)
+        st.upload(ori, [choice] * B)
+        st.noise()
+        enc = st.graph.enc_ids.view(B, S, 8).cpu().numpy()
+        lmk = st.loss_mask.view(B, S, 8).cpu().numpy()
+        for b in range(B):
+            if choice == 1:     # deletion: 153 rows removed, 153 PAD rows appended, order preserved
+                assert (enc[b, S - 153:] == PADROW).all()
+            elif choice == 2:   # mask: exactly 154 loss rows, 123 of them MASK rows
+                assert lmk[b, :, 0].sum() == 154 and (enc[b] == PADROW + 1).all(1).sum() >= 123
+            elif choice == 3:   # permutation: same multiset of rows
+                assert np.array_equal(np.sort(enc[b].view([('', enc.dtype)] * 8), axis=0),
+                                      np.sort(ori[b].astype(enc.dtype).view([('', enc.dtype)] * 8), axis=0))
+            elif choice == 5:   # rotation is a roll
+                r = int(np.flatnonzero((enc[b] == ori[b, 0]).all(1))[0])
+                assert np.array_equal(np.roll(ori[b], r, axis=0), enc[b])
+            assert np.array_equal(lmk[b], np.repeat(lmk[b, :, :1], 8, axis=1))
+
+
+def test_padding_invariance_property():
+    """Keys at <PAD> positions must not influence valid positions (masks derived after noising, pretrain.py:151)."""
+    g = load_golden('fwd_mid')
+    pb, lm = build_cuda_model(g['cfg'], int(g['seed']), 'fp32')
+    lm.eval()
+    enc, dec, ori, lmask, em, dm = golden_inputs(g)
+    with torch.no_grad():
+        y1 = torch.cat(lm(enc, dec, em, dm), -1)
+        enc2 = enc.clone()
+        pad_pos = em == 0
+        enc2[..., 1:][pad_pos] = 0     # change every attribute except Bar at padded encoder positions
+        y2 = torch.cat(lm(enc2, dec, em, dm), -1)
+    valid = dm != 0
+    assert torch.allclose(y1[valid], y2[valid], atol=1e-5)

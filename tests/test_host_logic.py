@@ -1,0 +1,108 @@
+"""CPU tests of the host-side logic: noise-plan generator (bit-exact against the reference fixtures),
+parameter layout / state_dict compatibility, vocabulary structure."""
+import json
+import os
+import random
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN
+from pianobart_b200 import noising as N
+
+PAD = np.array([256, 128, 129, 256, 128, 32, 254, 49])
+MASK = PAD + 1
+
+
+def apply_plan_host(ori, plan):
+    """numpy emulation of csrc/noise.cu (the device half) for CPU-side checking of the plan."""
+    B, S, _ = ori.shape
+    out = np.empty_like(ori)
+    lm = np.zeros((B, S, 8), np.uint8)
+    rt = np.array(plan.rand_tok).reshape(-1, 8)
+    for b in range(B):
+        src = plan.src[b]
+        rows = np.where((src >= 0)[:, None], ori[b][np.maximum(src, 0)], 0)
+        rows = np.where((src == -1)[:, None], PAD, rows)
+        rows = np.where((src == -2)[:, None], MASK, rows)
+        for s in np.flatnonzero(src <= -3):
+            rows[s] = rt[-3 - src[s]]
+        out[b] = rows
+        if plan.loss_mode[b] == 0:
+            lm[b] = plan.loss[b][:, None]
+        elif plan.loss_mode[b] == 1:
+            lm[b] = (out[b] != ori[b]).any(1)[:, None]
+    return out, lm
+
+
+def test_noise_plan_bit_exact_against_reference_fixtures():
+    g = np.load(os.path.join(GOLDEN, 'noising.npz'))
+    for S in (1024, 64):
+        ori, enc, lmk, ch = (g['S%d_ori' % S].astype(np.int64), g['S%d_enc' % S], g['S%d_loss_mask' % S],
+                             g['S%d_choices' % S])
+        for seed in range(ori.shape[0]):
+            random.seed(seed)
+            np.random.seed(seed)
+            plan = N.make_plan(ori[seed], S)
+            out, lm = apply_plan_host(ori[seed], plan)
+            assert np.array_equal(out, enc[seed])
+            assert np.array_equal(lm, lmk[seed])
+            assert np.array_equal(plan.choices, ch[seed])
+
+
+def test_noise_plan_direct_choices():
+    g = np.load(os.path.join(GOLDEN, 'noising.npz'))
+    for S, mp in ((1024, 0.15), (10, 0.5)):
+        for choice in (1, 2, 3, 4, 5):
+            for seed in (11, 12, 13):
+                key = 'direct_S%d_c%d_s%d' % (S, choice, seed)
+                random.seed(seed)
+                np.random.seed(seed)
+                ori = g[key + '_ori'].astype(np.int64)[None]
+                plan = N.make_plan(ori, S, mp, [choice])
+                out, lm = apply_plan_host(ori, plan)
+                assert np.array_equal(out[0], g[key + '_enc']), key
+                assert np.array_equal(lm[0], g[key + '_loss_mask']), key
+
+
+def test_state_dict_keys_match_reference_fixture():
+    from pianobart_b200.modules import BartConfig, PianoBart, PianoBartLM
+    from pianobart_b200.vocab import build_octuple_vocab
+    with open(os.path.join(GOLDEN, 'state_dict_keys.json')) as f:
+        ref = json.load(f)
+    e2w, w2e = build_octuple_vocab()
+    bc = BartConfig(max_position_embeddings=32, d_model=64, encoder_layers=2, decoder_layers=2, encoder_ffn_dim=128,
+                    decoder_ffn_dim=128, encoder_attention_heads=4, decoder_attention_heads=4)
+    pb = PianoBart(bc, e2w, w2e)
+    mine_pb = {k: list(v.shape) for k, v in pb.state_dict().items()}
+    assert mine_pb == ref['PianoBart']
+    lm = PianoBartLM(pb)
+    mine_lm = {k: list(v.shape) for k, v in lm.state_dict().items()}
+    assert mine_lm == ref['PianoBartLM']
+
+
+def test_vocab_structure():
+    from pianobart_b200.vocab import build_octuple_vocab
+    e2w, w2e = build_octuple_vocab()
+    assert list(e2w.keys()) == ['Bar', 'Position', 'Pitch', 'Duration', 'Velocity', 'Instrument', 'Tempo', 'TimeSig']
+    classes = ['Bar', 'Position', 'Instrument', 'Pitch', 'Duration', 'Velocity', 'TimeSig', 'Tempo']
+    assert [len(e2w[k]) for k in classes] == [262, 134, 135, 262, 134, 38, 260, 55]
+    assert [e2w[k]['%s <PAD>' % k] for k in classes] == [256, 128, 129, 256, 128, 32, 254, 49]
+    assert e2w['Bar']['Bar <SOS>'] == 258 and e2w['Tempo']['Tempo <EOS>'] == 52
+
+
+def test_param_layout_fused_groups_are_contiguous():
+    from pianobart_b200.engine import ParamLayout
+    lay = ParamLayout(64, 2, 2, 128, 32, True)
+    for fname, (off, shape) in lay.fused.items():
+        n = int(np.prod(shape))
+        members = sorted((o, s, k) for k, (o, s) in lay.entries.items() if off <= o < off + n)
+        pos = off
+        for o, s, k in members:
+            assert o == pos, (fname, k)
+            pos += int(np.prod(s))
+        assert pos == off + n
+    los = sorted(lay.ranges.values())
+    assert los[0][0] == 0 and los[-1][1] == lay.size
+    for (a, b), (c, d) in zip(los[:-1], los[1:]):
+        assert b == c
