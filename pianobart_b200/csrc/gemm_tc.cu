@@ -412,9 +412,12 @@ struct TmapKeyHash {
 static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
 static std::mutex g_tmap_mutex;
 
+}  // namespace pb
+
 // inner = contiguous dimension (elements); rows = second dimension; ld = row stride (elements)
-static int make_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, long long ld, int nh,
+int pb_make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, long long ld, int nh,
                      long long stride_h, int nb, long long stride_b, uint32_t box_inner, uint32_t box_rows) {
+  using namespace pb;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return pb_set_error("cuTensorMapEncodeTiled entry point not available");
   TmapKey key;
@@ -451,6 +454,12 @@ static int make_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   if (g_tmap_cache.size() > 4096) g_tmap_cache.clear();
   g_tmap_cache.emplace(key, *out);
   return 0;
+}
+
+namespace pb {
+static inline int make_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, long long ld, int nh,
+                            long long stride_h, int nb, long long stride_b, uint32_t box_inner, uint32_t box_rows) {
+  return pb_make_tmap_bf16(out, base, inner, rows, ld, nh, stride_h, nb, stride_b, box_inner, box_rows);
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
