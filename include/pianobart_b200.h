@@ -78,6 +78,26 @@ int pb_gemm_bf16(const pb_gemm_desc* d, void* stream);
 /* fp32 operands, SIMT kernel - the fp32 parity mode of the same graph */
 int pb_gemm_f32(const pb_gemm_desc* d, void* stream);
 
+/* ------------------------------------------------------------------ fused attention (tcgen05, head_dim 128)
+ * Replaces the core of HF BartAttention (eager_attention_forward: softmax(Q K^T * hd^-0.5 + mask) V) and its
+ * autograd without materialising scores: encoder self-attention (key padding), decoder self-attention
+ * (causal and key padding), decoder cross-attention (encoder key padding).  All tensors bf16, laid out
+ * [B, S, H*hd] with row stride ld* (elements) so that slices of the fused QKV activation are used in place.
+ * lse fp32 [B,H,Sq] (log2 domain) is written by forward and read by backward; dvec fp32 [B,H,Sq] is scratch. */
+typedef struct pb_attn_desc {
+  const void* q; const void* k; const void* v;
+  void* o;            /* forward output / backward input */
+  const void* dout;   /* backward: gradient wrt o */
+  void* dq; void* dk; void* dv;
+  long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  float* lse; float* dvec;
+  const uint8_t* key_keep; /* [B, Sk] non-zero = key visible, or NULL */
+  int B, H, Sq, Sk, hd, causal;
+  float scale;
+} pb_attn_desc;
+int pb_attn_fwd(const pb_attn_desc* d, void* stream);
+int pb_attn_bwd(const pb_attn_desc* d, void* stream);
+
 /* ------------------------------------------------------------------ Octuple front end
  * out[m, 256*i + c] = table[row_off(i) + ids[m,i], c] for the 8 attributes (reference PianoBart.py:9-16,60-67:
  * eight nn.Embedding gathers * sqrt(256) + torch.cat).  `table` is the [1280,256] concatenation of the eight

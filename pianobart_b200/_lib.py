@@ -34,6 +34,18 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p), ("dout", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("ldq", C.c_longlong), ("ldk", C.c_longlong), ("ldv", C.c_longlong), ("ldo", C.c_longlong),
+        ("lddo", C.c_longlong), ("lddq", C.c_longlong), ("lddk", C.c_longlong), ("lddv", C.c_longlong),
+        ("lse", C.c_void_p), ("dvec", C.c_void_p), ("key_keep", C.c_void_p),
+        ("B", C.c_int), ("H", C.c_int), ("Sq", C.c_int), ("Sk", C.c_int), ("hd", C.c_int), ("causal", C.c_int),
+        ("scale", C.c_float),
+    ]
+
+
 class PBError(RuntimeError):
     pass
 

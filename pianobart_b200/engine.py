@@ -14,6 +14,7 @@ Two dtype modes share the same plan:
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -219,6 +220,21 @@ class Plan:
         self._add('softmax_bwd', self.lib.pb_softmax_bwd, C.c_void_p(p), C.c_void_p(dp), C.c_void_p(ds),
                   C.c_void_p(keep or None), B, H, Sq, Sk, causal, self.dtype)
 
+    def attn(self, backward, q, k, v, o, ldq, ldk, ldv, ldo, lse, dvec, keep, B, H, Sq, Sk, hd, causal, dout=0, dq=0,
+             dk=0, dv=0, lddq=0, lddk=0, lddv=0):
+        a = L.AttnDesc()
+        a.q, a.k, a.v, a.o, a.dout = q, k, v, o, dout or None
+        a.dq, a.dk, a.dv = dq or None, dk or None, dv or None
+        a.ldq, a.ldk, a.ldv, a.ldo, a.lddo = ldq, ldk, ldv, ldo, ldo
+        a.lddq, a.lddk, a.lddv = lddq, lddk, lddv
+        a.lse, a.dvec, a.key_keep = lse, dvec or None, keep or None
+        a.B, a.H, a.Sq, a.Sk, a.hd, a.causal, a.scale = B, H, Sq, Sk, hd, causal, hd ** -0.5
+        self._keep.append(a)
+        if backward:
+            self._add('attn_bwd', self.lib.pb_attn_bwd, C.byref(a))
+        else:
+            self._add('attn_fwd', self.lib.pb_attn_fwd, C.byref(a))
+
     def colsum(self, x, out, M, N, ld):
         self._add('colsum', self.lib.pb_colsum, C.c_void_p(x), C.c_void_p(out), C.c_longlong(M), N, C.c_longlong(ld),
                   self.dtype)
@@ -264,6 +280,9 @@ class BackboneGraph:
         assert self.d % heads == 0
         if dtype == PB_BF16:
             assert self.hd % 8 == 0, 'bf16 mode needs head_dim % 8 == 0 (TMA 16-byte strides)'
+        # fused tcgen05 attention (no S x S tensor in HBM) for the production configuration; otherwise the
+        # unfused GEMM + softmax path (fp32 parity mode, head_dim != 128)
+        self.flash = (dtype == PB_BF16 and self.hd == 128 and os.environ.get('PIANOBART_B200_UNFUSED_ATTN', '0') != '1')
         self.tdt = torch.bfloat16 if dtype == PB_BF16 else torch.float32
         self.es = 2 if dtype == PB_BF16 else 4
         self.w_act, self.w_f32, self.g_f32 = w_act, w_f32, g_f32
@@ -372,7 +391,7 @@ class BackboneGraph:
 
         Smax = max(self.Se, self.Sd)
         Mmax = B * Smax
-        scores = self.buf('scores', B * H * Smax * Smax, dtype=torch.float32)  # shared fp32 scratch
+        scores = None if self.flash else self.buf('scores', B * H * Smax * Smax, dtype=torch.float32)  # fp32 scratch
         layers = []
         h_in = H0
         for l in range(nl):
@@ -381,31 +400,37 @@ class BackboneGraph:
             rec = {}
             # -- self attention
             QKV = self.buf(ln('QKV'), M, 3 * d)
-            Pm = self.buf(ln('P'), B * H * S * S)
+            Pm = None if self.flash else self.buf(ln('P'), B * H * S * S)
+            lse = self.buf(ln('lse'), B * H * S, dtype=torch.float32) if self.flash else None
             O = self.buf(ln('O'), M, d)
             A = self.buf(ln('A'), M, d)
             H1 = self.buf(ln('H1'), M, d)
             st1 = self.buf(ln('st1'), 2, M, dtype=torch.float32)
             f.gemm(_ptr(h_in), self.W(lp + '.self_attn.wqkv'), _ptr(QKV), M, 3 * d, d, d, d, 3 * d,
                    bias=self.Pf(lp + '.self_attn.bqkv'), name=ln('qkv'))
-            f.gemm(_ptr(QKV), _ptr(QKV, d), _ptr(scores), S, S, hd, 3 * d, 3 * d, S, flags=OUT32, alpha=scale,
-                   batch_h=H, batch_b=B, a_sh=hd, a_sb=S * 3 * d, b_sh=hd, b_sb=S * 3 * d, c_sh=S * S, c_sb=H * S * S,
-                   causal=1 if is_dec else 0, name=ln('qk'))
-            f.softmax_fwd(_ptr(scores), _ptr(Pm), _ptr(keep), B, H, S, S, 1 if is_dec else 0)
-            f.gemm(_ptr(Pm), _ptr(QKV, 2 * d), _ptr(O), S, hd, S, S, 3 * d, d, b_mn=1, batch_h=H, batch_b=B,
-                   a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd, c_sb=S * d,
-                   causal=2 if is_dec else 0, name=ln('pv'))
+            if self.flash:
+                f.attn(False, _ptr(QKV), _ptr(QKV, d), _ptr(QKV, 2 * d), _ptr(O), 3 * d, 3 * d, 3 * d, d, _ptr(lse), 0,
+                       _ptr(keep), B, H, S, S, hd, 1 if is_dec else 0)
+            else:
+                f.gemm(_ptr(QKV), _ptr(QKV, d), _ptr(scores), S, S, hd, 3 * d, 3 * d, S, flags=OUT32, alpha=scale,
+                       batch_h=H, batch_b=B, a_sh=hd, a_sb=S * 3 * d, b_sh=hd, b_sb=S * 3 * d, c_sh=S * S, c_sb=H * S * S,
+                       causal=1 if is_dec else 0, name=ln('qk'))
+                f.softmax_fwd(_ptr(scores), _ptr(Pm), _ptr(keep), B, H, S, S, 1 if is_dec else 0)
+                f.gemm(_ptr(Pm), _ptr(QKV, 2 * d), _ptr(O), S, hd, S, S, 3 * d, d, b_mn=1, batch_h=H, batch_b=B,
+                       a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd, c_sb=S * d,
+                       causal=2 if is_dec else 0, name=ln('pv'))
             f.gemm(_ptr(O), self.W(lp + '.self_attn.out_proj.weight'), _ptr(A), M, d, d, d, d, d,
                    bias=self.Pf(lp + '.self_attn.out_proj.bias'), residual=_ptr(h_in), ldr=d, name=ln('out_proj'))
             f.ln_fwd(_ptr(A), self.Pf(lp + '.self_attn_layer_norm.weight'), self.Pf(lp + '.self_attn_layer_norm.bias'),
                      _ptr(H1), _ptr(st1), _ptr(st1, M), M, d)
-            rec.update(h_in=h_in, QKV=QKV, P=Pm, O=O, A=A, H1=H1, st1=st1)
+            rec.update(h_in=h_in, QKV=QKV, P=Pm, lse=lse, O=O, A=A, H1=H1, st1=st1)
             h_mid = H1
             if is_dec:
                 Me = B * S_enc
                 Qc = self.buf(ln('Qc'), M, d)
                 KVc = self.buf(ln('KVc'), Me, 2 * d)
-                Pc = self.buf(ln('Pc'), B * H * S * S_enc)
+                Pc = None if self.flash else self.buf(ln('Pc'), B * H * S * S_enc)
+                lse_c = self.buf(ln('lse_c'), B * H * S, dtype=torch.float32) if self.flash else None
                 Oc = self.buf(ln('Oc'), M, d)
                 Ac = self.buf(ln('Ac'), M, d)
                 Hc = self.buf(ln('Hc'), M, d)
@@ -415,18 +440,22 @@ class BackboneGraph:
                        bias=self.Pf(ca + '.q_proj.bias'), name=ln('q_c'))
                 f.gemm(_ptr(enc_out), self.W(ca + '.wkv'), _ptr(KVc), Me, 2 * d, d, d, d, 2 * d,
                        bias=self.Pf(ca + '.bkv'), name=ln('kv_c'))
-                f.gemm(_ptr(Qc), _ptr(KVc), _ptr(scores), S, S_enc, hd, d, 2 * d, S_enc, flags=OUT32, alpha=scale,
-                       batch_h=H, batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=S * S_enc,
-                       c_sb=H * S * S_enc, name=ln('qk_c'))
-                f.softmax_fwd(_ptr(scores), _ptr(Pc), _ptr(enc_keep), B, H, S, S_enc, 0)
-                f.gemm(_ptr(Pc), _ptr(KVc, d), _ptr(Oc), S, hd, S_enc, S_enc, 2 * d, d, b_mn=1, batch_h=H, batch_b=B,
-                       a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=hd, c_sb=S * d,
-                       name=ln('pv_c'))
+                if self.flash:
+                    f.attn(False, _ptr(Qc), _ptr(KVc), _ptr(KVc, d), _ptr(Oc), d, 2 * d, 2 * d, d, _ptr(lse_c), 0,
+                           _ptr(enc_keep), B, H, S, S_enc, hd, 0)
+                else:
+                    f.gemm(_ptr(Qc), _ptr(KVc), _ptr(scores), S, S_enc, hd, d, 2 * d, S_enc, flags=OUT32, alpha=scale,
+                           batch_h=H, batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=S * S_enc,
+                           c_sb=H * S * S_enc, name=ln('qk_c'))
+                    f.softmax_fwd(_ptr(scores), _ptr(Pc), _ptr(enc_keep), B, H, S, S_enc, 0)
+                    f.gemm(_ptr(Pc), _ptr(KVc, d), _ptr(Oc), S, hd, S_enc, S_enc, 2 * d, d, b_mn=1, batch_h=H, batch_b=B,
+                           a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=hd, c_sb=S * d,
+                           name=ln('pv_c'))
                 f.gemm(_ptr(Oc), self.W(ca + '.out_proj.weight'), _ptr(Ac), M, d, d, d, d, d,
                        bias=self.Pf(ca + '.out_proj.bias'), residual=_ptr(H1), ldr=d, name=ln('out_proj_c'))
                 f.ln_fwd(_ptr(Ac), self.Pf(lp + '.encoder_attn_layer_norm.weight'),
                          self.Pf(lp + '.encoder_attn_layer_norm.bias'), _ptr(Hc), _ptr(stc), _ptr(stc, M), M, d)
-                rec.update(Qc=Qc, KVc=KVc, Pc=Pc, Oc=Oc, Ac=Ac, Hc=Hc, stc=stc)
+                rec.update(Qc=Qc, KVc=KVc, Pc=Pc, lse_c=lse_c, Oc=Oc, Ac=Ac, Hc=Hc, stc=stc)
                 h_mid = Hc
             # -- feed forward
             Z = self.buf(ln('Z'), M, F)
@@ -484,19 +513,25 @@ class BackboneGraph:
                     bw.wgrad(_ptr(dA), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
                     bw.gemm(_ptr(dA), self.W(ca + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dOc'))
                     # dP = dO V^T ; dV = P^T dO ; dS = softmax'(P, dP) ; dQ = scale dS K ; dK = scale dS^T Q
-                    bw.gemm(_ptr(dO), _ptr(r['KVc'], d), _ptr(scores), S, S_enc, hd, d, 2 * d, S_enc, flags=OUT32,
-                            batch_h=H, batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=S * S_enc,
-                            c_sb=H * S * S_enc, name=ln('dP_c'))
-                    bw.gemm(_ptr(r['Pc']), _ptr(dO), _ptr(dKVc, d), S_enc, hd, S, S_enc, d, 2 * d, a_mn=1, b_mn=1,
-                            batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S * d, c_sh=hd,
-                            c_sb=S_enc * 2 * d, name=ln('dV_c'))
-                    bw.softmax_bwd(_ptr(r['Pc']), _ptr(scores), _ptr(r['Pc']), _ptr(enc_keep), B, H, S, S_enc, 0)
-                    bw.gemm(_ptr(r['Pc']), _ptr(r['KVc']), _ptr(dQc), S, hd, S_enc, S_enc, 2 * d, d, b_mn=1, alpha=scale,
-                            batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S_enc * 2 * d,
-                            c_sh=hd, c_sb=S * d, name=ln('dQ_c'))
-                    bw.gemm(_ptr(r['Pc']), _ptr(r['Qc']), _ptr(dKVc), S_enc, hd, S, S_enc, d, 2 * d, a_mn=1, b_mn=1,
-                            alpha=scale, batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S * d,
-                            c_sh=hd, c_sb=S_enc * 2 * d, name=ln('dK_c'))
+                    if self.flash:
+                        dvec = self.buf('g.dvec', B * H * Smax, dtype=torch.float32)
+                        bw.attn(True, _ptr(r['Qc']), _ptr(r['KVc']), _ptr(r['KVc'], d), _ptr(r['Oc']), d, 2 * d, 2 * d, d,
+                                _ptr(r['lse_c']), _ptr(dvec), _ptr(enc_keep), B, H, S, S_enc, hd, 0, dout=_ptr(dO),
+                                dq=_ptr(dQc), dk=_ptr(dKVc), dv=_ptr(dKVc, d), lddq=d, lddk=2 * d, lddv=2 * d)
+                    else:
+                        bw.gemm(_ptr(dO), _ptr(r['KVc'], d), _ptr(scores), S, S_enc, hd, d, 2 * d, S_enc, flags=OUT32,
+                                batch_h=H, batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=S * S_enc,
+                                c_sb=H * S * S_enc, name=ln('dP_c'))
+                        bw.gemm(_ptr(r['Pc']), _ptr(dO), _ptr(dKVc, d), S_enc, hd, S, S_enc, d, 2 * d, a_mn=1, b_mn=1,
+                                batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S * d, c_sh=hd,
+                                c_sb=S_enc * 2 * d, name=ln('dV_c'))
+                        bw.softmax_bwd(_ptr(r['Pc']), _ptr(scores), _ptr(r['Pc']), _ptr(enc_keep), B, H, S, S_enc, 0)
+                        bw.gemm(_ptr(r['Pc']), _ptr(r['KVc']), _ptr(dQc), S, hd, S_enc, S_enc, 2 * d, d, b_mn=1,
+                                alpha=scale, batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd,
+                                b_sb=S_enc * 2 * d, c_sh=hd, c_sb=S * d, name=ln('dQ_c'))
+                        bw.gemm(_ptr(r['Pc']), _ptr(r['Qc']), _ptr(dKVc), S_enc, hd, S, S_enc, d, 2 * d, a_mn=1, b_mn=1,
+                                alpha=scale, batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd,
+                                b_sb=S * d, c_sh=hd, c_sb=S_enc * 2 * d, name=ln('dK_c'))
                     bw.colsum(_ptr(dQc), self.G(ca + '.q_proj.bias'), M, d, d)
                     bw.wgrad(_ptr(dQc), _ptr(r['H1']), self.G(ca + '.q_proj.weight'), d, d, M, d, d, name=ln('dW_qc'))
                     bw.colsum(_ptr(dKVc), self.G(ca + '.bkv'), Me, 2 * d, 2 * d)
@@ -517,19 +552,25 @@ class BackboneGraph:
                 bw.wgrad(_ptr(dA), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
                 bw.gemm(_ptr(dA), self.W(sa + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dO'))
                 QKV, Pm = r['QKV'], r['P']
-                bw.gemm(_ptr(dO), _ptr(QKV, 2 * d), _ptr(scores), S, S, hd, d, 3 * d, S, flags=OUT32, batch_h=H,
-                        batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S * 3 * d, c_sh=S * S, c_sb=H * S * S, causal=cz,
-                        name=ln('dP'))
-                bw.gemm(_ptr(Pm), _ptr(dO), _ptr(dQKV, 2 * d), S, hd, S, S, d, 3 * d, a_mn=1, b_mn=1, batch_h=H,
-                        batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * d, c_sh=hd, c_sb=S * 3 * d,
-                        name=ln('dV'))
-                bw.softmax_bwd(_ptr(Pm), _ptr(scores), _ptr(Pm), _ptr(keep), B, H, S, S, cz)
-                bw.gemm(_ptr(Pm), _ptr(QKV, d), _ptr(dQKV), S, hd, S, S, 3 * d, 3 * d, b_mn=1, alpha=scale, batch_h=H,
-                        batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd, c_sb=S * 3 * d,
-                        causal=2 if is_dec else 0, name=ln('dQ'))
-                bw.gemm(_ptr(Pm), _ptr(QKV), _ptr(dQKV, d), S, hd, S, S, 3 * d, 3 * d, a_mn=1, b_mn=1, alpha=scale,
-                        batch_h=H, batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd,
-                        c_sb=S * 3 * d, name=ln('dK'))
+                if self.flash:
+                    dvec = self.buf('g.dvec', B * H * Smax, dtype=torch.float32)
+                    bw.attn(True, _ptr(QKV), _ptr(QKV, d), _ptr(QKV, 2 * d), _ptr(r['O']), 3 * d, 3 * d, 3 * d, d,
+                            _ptr(r['lse']), _ptr(dvec), _ptr(keep), B, H, S, S, hd, cz, dout=_ptr(dO), dq=_ptr(dQKV),
+                            dk=_ptr(dQKV, d), dv=_ptr(dQKV, 2 * d), lddq=3 * d, lddk=3 * d, lddv=3 * d)
+                else:
+                    bw.gemm(_ptr(dO), _ptr(QKV, 2 * d), _ptr(scores), S, S, hd, d, 3 * d, S, flags=OUT32, batch_h=H,
+                            batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S * 3 * d, c_sh=S * S, c_sb=H * S * S, causal=cz,
+                            name=ln('dP'))
+                    bw.gemm(_ptr(Pm), _ptr(dO), _ptr(dQKV, 2 * d), S, hd, S, S, d, 3 * d, a_mn=1, b_mn=1, batch_h=H,
+                            batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * d, c_sh=hd, c_sb=S * 3 * d,
+                            name=ln('dV'))
+                    bw.softmax_bwd(_ptr(Pm), _ptr(scores), _ptr(Pm), _ptr(keep), B, H, S, S, cz)
+                    bw.gemm(_ptr(Pm), _ptr(QKV, d), _ptr(dQKV), S, hd, S, S, 3 * d, 3 * d, b_mn=1, alpha=scale, batch_h=H,
+                            batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd, c_sb=S * 3 * d,
+                            causal=2 if is_dec else 0, name=ln('dQ'))
+                    bw.gemm(_ptr(Pm), _ptr(QKV), _ptr(dQKV, d), S, hd, S, S, 3 * d, 3 * d, a_mn=1, b_mn=1, alpha=scale,
+                            batch_h=H, batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd,
+                            c_sb=S * 3 * d, name=ln('dK'))
                 bw.colsum(_ptr(dQKV), self.G(sa + '.bqkv'), M, 3 * d, 3 * d)
                 bw.wgrad(_ptr(dQKV), _ptr(r['h_in']), self.G(sa + '.wqkv'), 3 * d, d, M, 3 * d, d, name=ln('dW_qkv'))
                 bw.gemm(_ptr(dQKV), self.W(sa + '.wqkv'), _ptr(dnext), M, d, 3 * d, 3 * d, d, d, b_mn=1,

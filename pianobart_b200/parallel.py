@@ -1,0 +1,62 @@
+"""Data-parallel gradient exchange: one process per GPU, NCCL all-reduce(sum) of the
+flat fp32 gradient buffer, issued in buckets on a side stream while backward is still running.
+
+The reference uses single-process torch.nn.DataParallel (pretrain.py:63-65: replicate / gather / reduce-add
+to device 0 every step).  Here every rank computes its own loss terms; because the per-attribute
+denominators (mask sums, pretrain.py:117) are all-reduced BEFORE backward, summing the rank gradients gives
+exactly the gradient of the reference's full-batch loss.
+
+`BucketReducer` is device-agnostic (CUDA + NCCL in production, CPU + gloo in the tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+class BucketReducer:
+    def __init__(self, flat_grad, group=None, target_bytes=48 << 20, comm_stream=None):
+        self.g = flat_grad
+        self.group = group
+        self.target = max(1, target_bytes // flat_grad.element_size())
+        self.comm_stream = comm_stream
+        self.pending = None          # (lo, hi) contiguous range whose gradients are final but not yet reduced
+        self.issued = []             # ranges handed to all_reduce, in order
+        self.works = []
+
+    def _issue(self, lo, hi):
+        self.issued.append((lo, hi))
+        view = self.g[lo:hi]
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(view, group=self.group)
+        else:
+            self.works.append(dist.all_reduce(view, group=self.group, async_op=True))
+
+    def on_final(self, tag, lo, hi):
+        """Plan marker callback: gradients of flat[lo:hi] will not be touched again by this backward."""
+        if self.pending is None:
+            self.pending = (lo, hi)
+        elif hi == self.pending[0]:
+            self.pending = (lo, self.pending[1])
+        elif lo == self.pending[1]:
+            self.pending = (self.pending[0], hi)
+        else:
+            self._issue(*self.pending)
+            self.pending = (lo, hi)
+        if self.pending[1] - self.pending[0] >= self.target:
+            self._issue(*self.pending)
+            self.pending = None
+
+    def finish(self):
+        if self.pending is not None:
+            self._issue(*self.pending)
+            self.pending = None
+        for w in self.works:
+            w.wait()
+        self.works = []
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        issued, self.issued = self.issued, []
+        return issued

@@ -170,14 +170,6 @@ class PretrainStep:
         self.loss_mask.copy_(loss_mask.reshape(-1))
 
     # -- stage 2: forward + loss (+ backward + optimizer)
-    def _allreduce_bucket(self, tag, lo, hi):
-        import torch.distributed as dist
-        ev = torch.cuda.Event()
-        ev.record()
-        self.comm_stream.wait_event(ev)
-        with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(self.pb._grad[lo:hi], group=self.pg)
-
     def run(self, train=True, profile=None):
         g, lib, s = self.graph, self.lib, L.stream_ptr()
         pb = self.pb
@@ -199,8 +191,10 @@ class PretrainStep:
         if train:
             pb._grad.zero_()
             if self.world > 1:
-                n += g.bwd.run(on_marker=self._allreduce_bucket, profile=profile)
-                torch.cuda.current_stream().wait_stream(self.comm_stream)
+                from .parallel import BucketReducer
+                red = BucketReducer(pb._grad, self.pg, comm_stream=self.comm_stream)
+                n += g.bwd.run(on_marker=red.on_final, profile=profile)
+                red.finish()
             else:
                 n += g.bwd.run(profile=profile)
             if self.opt is not None:
