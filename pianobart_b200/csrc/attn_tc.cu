@@ -14,8 +14,9 @@
 //   attn_bwd_dkv CTA = (b, h, 128 keys)     loop over query blocks: S, dP -> P, dS -> dV += P^T dO, dK += dS^T Q
 //   attn_bwd_dq  CTA = (b, h, 128 queries)  loop over key blocks:  S, dP -> dS -> dQ += dS K
 //   attn_bwd_prep                           D = rowsum(dO * O)
-// Warp roles per CTA (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue
-// (thread <-> TMEM lane <-> tile row, so row reductions are thread-local).
+// Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax / epilogue:
+// thread <-> (TMEM lane = tile row, 64-column half), two warps per scheduler so that the dependent ALU chains of
+// one warp hide behind the other (a single warp per scheduler left the kernel latency-bound, profiles/).
 #include "ptx.cuh"
 #include "pb_internal.h"
 
@@ -81,7 +82,33 @@ __device__ __forceinline__ void store_chunk(uint8_t* tile, int r, int c0, const 
     *reinterpret_cast<uint4*>(half + (((cbase + g) ^ (r & 7)) << 4)) = v;
   }
 }
-__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+constexpr int NCOMPUTE = 256;             // 8 softmax / epilogue warps: (TMEM lane quadrant) x (column half)
+constexpr int NTHREADS = 64 + NCOMPUTE;
+__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// bit i of the result = column (c0 + i) of this key block may be attended by query qg:
+// key-padding bitmap word AND (causal: kg0 + c0 + i <= qg)
+__device__ __forceinline__ uint32_t chunk_mask(uint32_t keep_word, bool causal, int qg, int kg_c0) {
+  if (!causal) return keep_word;
+  const int lim = qg - kg_c0;            // largest allowed i
+  if (lim < 0) return 0u;
+  if (lim >= 31) return keep_word;
+  return keep_word & ((2u << lim) - 1u);
+}
+// compute threads 0..127 publish the key-padding bitmap of key block kg0 as four 32-bit words
+__device__ __forceinline__ void build_keep_bits(uint32_t* s_bits, const AttnParams& p, int b, int kg0, int tid) {
+  if (tid < AT) {
+    const int kc = kg0 + tid;
+    bool kp = kc < p.Sk;
+    if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc] != 0;
+    const uint32_t w = __ballot_sync(0xffffffffu, kp);
+    if ((tid & 31) == 0) s_bits[tid >> 5] = w;
+  }
+}
 
 struct Smem4 { uint8_t* t[6]; uint32_t a[6]; };
 __device__ __forceinline__ void carve(uint8_t* raw, Smem4& s, int n) {
@@ -91,13 +118,14 @@ __device__ __forceinline__ void carve(uint8_t* raw, Smem4& s, int n) {
 }
 
 // ===================================================================================== forward
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                 const __grid_constant__ CUtensorMap tv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, k_full, v_full, k_empty, v_empty, s_full, p_full, o_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint8_t s_keep[AT];
+  __shared__ uint32_t s_bits[4];
+  __shared__ float s_red[2][AT];
   Smem4 sm;
   carve(smem_raw, sm, 4);  // 0 Q, 1 K, 2 V, 3 P
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,7 +137,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); }
   if (warp == 1 && lane == 0) {
     mbar_init(&q_full, 1); mbar_init(&k_full, 1); mbar_init(&v_full, 1); mbar_init(&k_empty, 1); mbar_init(&v_empty, 1);
-    mbar_init(&s_full, 1); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
+    mbar_init(&s_full, 1); mbar_init(&p_full, NCOMPUTE); mbar_init(&o_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
@@ -150,63 +178,57 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int cw = warp - 2;                 // 0..7
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int hf = cw >> 2;                  // column half: S columns / O columns [64*hf, 64*hf + 64)
     const int r = quad * 32 + lane;          // tile row = TMEM lane
-    const int tid = threadIdx.x - 64;        // 0..127
+    const int tid = threadIdx.x - 64;        // 0..255
     const int qg = q0 + r;                   // global query index
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float sl2 = p.scale * LOG2E;
-    float o[AT];
+    float o[64];
 #pragma unroll
-    for (int i = 0; i < AT; ++i) o[i] = 0.f;
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nkb; ++j) {
       const int kg0 = j * AT;
-      {
-        const int kc = kg0 + tid;
-        uint8_t kp = (kc < p.Sk) ? 1 : 0;
-        if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc];
-        compute_bar_sync();                  // previous iteration finished reading s_keep
-        s_keep[tid] = kp;
-        compute_bar_sync();
-      }
+      build_keep_bits(s_bits, p, b, kg0, tid);
+      compute_bar_sync();
+      uint32_t msk[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) msk[c] = chunk_mask(s_bits[hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32);
       mbar_wait(&s_full, j & 1);
       tc_fence_after();
-      // pass 1: masked row maximum
+      float t[64];
       float bm = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tS + lane_addr + c * 32, v);
+        tmem_ld32(tS + lane_addr + hf * 64 + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int col = c * 32 + i;
-          const bool ok = s_keep[col] && (!p.causal || kg0 + col <= qg);
-          if (ok) bm = fmaxf(bm, __uint_as_float(v[i]) * sl2);
+          const float x = ((msk[c] >> i) & 1u) ? __uint_as_float(v[i]) * sl2 : -INFINITY;
+          t[c * 32 + i] = x;
+          bm = fmaxf(bm, x);
         }
       }
-      const float m_new = fmaxf(m, bm);
+      s_red[hf][r] = bm;
+      compute_bar_sync();
+      const float m_new = fmaxf(m, fmaxf(s_red[0][r], s_red[1][r]));
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m == -INFINITY) ? 0.f : exp2f(m - m_use);
+      const float alpha = (m == -INFINITY) ? 0.f : ex2(m - m_use);
       float rs = 0.f;
-      // pass 2: probabilities -> bf16 -> swizzled smem tile (A operand of the PV product)
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_addr + c * 32, v);
-        tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int col = c * 32 + i;
-          const bool ok = s_keep[col] && (!p.causal || kg0 + col <= qg);
-          const float e = ok ? exp2f(__uint_as_float(v[i]) * sl2 - m_use) : 0.f;
-          // the row sum must match what the tensor core will see: accumulate the bf16-rounded value
-          x[i] = __bfloat162float(__float2bfloat16(e));
+          // masked entries are -inf -> ex2 gives 0; the row sum uses the bf16-rounded value the tensor core sees
+          x[i] = __bfloat162float(__float2bfloat16(ex2(t[c * 32 + i] - m_use)));
           rs += x[i];
         }
-        store_chunk(sm.t[3], r, c * 32, x);
+        store_chunk(sm.t[3], r, hf * 64 + c * 32, x);
       }
       l = l * alpha + rs;
       m = m_new;
@@ -216,27 +238,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       mbar_wait(&o_full, j & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tO + lane_addr + c * 32, v);
+        tmem_ld32(tO + lane_addr + hf * 64 + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(v[i]);
       }
       tc_fence_before();
     }
+    compute_bar_sync();
+    s_red[hf][r] = l;
+    compute_bar_sync();
+    l = s_red[0][r] + s_red[1][r];
     if (qg < p.Sq) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      __nv_bfloat16* orow = p.o + (long long)b * p.o_sb + (long long)qg * p.ldo + h * AT;
+      __nv_bfloat16* orow = p.o + (long long)b * p.o_sb + (long long)qg * p.ldo + h * AT + hf * 64;
 #pragma unroll
-      for (int g = 0; g < 16; ++g) {
+      for (int g = 0; g < 8; ++g) {
         uint4 v;
         __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(o[g * 8 + 2 * t] * inv, o[g * 8 + 2 * t + 1] * inv);
+        for (int tt = 0; tt < 4; ++tt) h2[tt] = __floats2bfloat162_rn(o[g * 8 + 2 * tt] * inv, o[g * 8 + 2 * tt + 1] * inv);
         *reinterpret_cast<uint4*>(orow + g * 8) = v;
       }
-      p.lse[((long long)b * p.H + h) * p.Sq + qg] = (l > 0.f) ? (m + log2f(l)) : INFINITY;
+      if (hf == 0) p.lse[((long long)b * p.H + h) * p.Sq + qg] = (l > 0.f) ? (m + log2f(l)) : INFINITY;
     }
   }
   tc_fence_before();
@@ -245,13 +271,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 }
 
 // ===================================================================================== backward: dK, dV
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                     const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t kv_full, qdo_full, qdo_empty, sdp_full, pds_full, acc_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint8_t s_keep[AT];
+  __shared__ uint32_t s_bits[4];
+  __shared__ float s_red[2][AT];
   Smem4 sm;
   carve(smem_raw, sm, 6);  // 0 K, 1 V, 2 Q, 3 dO, 4 P, 5 dS
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,7 +291,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); }
   if (warp == 1 && lane == 0) {
     mbar_init(&kv_full, 1); mbar_init(&qdo_full, 1); mbar_init(&qdo_empty, 1); mbar_init(&sdp_full, 1);
-    mbar_init(&pds_full, 128); mbar_init(&acc_full, 1);
+    mbar_init(&pds_full, NCOMPUTE); mbar_init(&acc_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -304,18 +331,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       umma_commit(&acc_full);
     }
   } else {
+    const int cw = warp - 2;
     const int quad = warp & 3;
+    const int hf = cw >> 2;
     const int r = quad * 32 + lane;
     const int tid = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float sl2 = p.scale * LOG2E;
-    {
-      const int kc = k0 + tid;
-      uint8_t kp = (kc < p.Sk) ? 1 : 0;
-      if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc];
-      s_keep[tid] = kp;
-      compute_bar_sync();
-    }
+    build_keep_bits(s_bits, p, b, k0, tid);
+    compute_bar_sync();
+    const uint32_t kw0 = s_bits[hf * 2], kw1 = s_bits[hf * 2 + 1];
     const long long rbase = ((long long)b * p.H + h) * p.Sq;
     float L_next = INFINITY, D_next = 0.f;
     if (qb0 * AT + r < p.Sq) { L_next = p.lse[rbase + qb0 * AT + r]; D_next = p.dvec[rbase + qb0 * AT + r]; }
@@ -325,33 +350,34 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       const float L = L_next, Dv = D_next;
       if (it + 1 < niter && qg + AT < p.Sq) { L_next = p.lse[rbase + qg + AT]; D_next = p.dvec[rbase + qg + AT]; }
       else { L_next = INFINITY; D_next = 0.f; }
+      uint32_t msk[2];
+      msk[0] = qok ? chunk_mask(kw0, p.causal != 0, qg, k0 + hf * 64) : 0u;
+      msk[1] = qok ? chunk_mask(kw1, p.causal != 0, qg, k0 + hf * 64 + 32) : 0u;
       mbar_wait(&sdp_full, it & 1);
       tc_fence_after();
-      // P / dS smem of the previous iteration were released by qdo_empty's MMAs; the MMA warp only issues this
-      // iteration's S/dP after them (in-order tensor pipe), so sdp_full implies the buffers are free.
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      // P / dS smem of the previous iteration were consumed by MMAs that precede this iteration's S/dP in the
+      // in-order tensor pipe, so sdp_full implies the buffers are free.
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t sv[32], dv[32];
-        tmem_ld32(tS + lane_addr + c * 32, sv);
-        tmem_ld32(tdP + lane_addr + c * 32, dv);
+        tmem_ld32(tS + lane_addr + hf * 64 + c * 32, sv);
+        tmem_ld32(tdP + lane_addr + hf * 64 + c * 32, dv);
         tmem_ld_wait();
         float pr[32], ds[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int col = c * 32 + i;
-          const bool ok = qok && s_keep[col] && (!p.causal || k0 + col <= qg);
-          const float pv = ok ? exp2f(__uint_as_float(sv[i]) * sl2 - L) : 0.f;
+          const float pv = ((msk[c] >> i) & 1u) ? ex2(__uint_as_float(sv[i]) * sl2 - L) : 0.f;
           pr[i] = pv;
           ds[i] = pv * (__uint_as_float(dv[i]) - Dv) * p.scale;
         }
-        store_chunk(sm.t[4], r, c * 32, pr);
-        store_chunk(sm.t[5], r, c * 32, ds);
+        store_chunk(sm.t[4], r, hf * 64 + c * 32, pr);
+        store_chunk(sm.t[5], r, hf * 64 + c * 32, ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&pds_full);
     }
-    // epilogue: thread = key row
+    // epilogue: thread = (key row, 64-column half of head_dim)
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     const int kg = k0 + r;
@@ -361,9 +387,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       __nv_bfloat16* dst = which == 0 ? (p.dv + (long long)b * p.dv_sb + (long long)kg * p.lddv + h * AT)
                                       : (p.dk + (long long)b * p.dk_sb + (long long)kg * p.lddk + h * AT);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tacc + lane_addr + c * 32, v);
+        tmem_ld32(tacc + lane_addr + hf * 64 + c * 32, v);
         tmem_ld_wait();
         if (kg < p.Sk) {
 #pragma unroll
@@ -371,9 +397,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
             uint4 o;
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              h2[t] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * t]), __uint_as_float(v[g * 8 + 2 * t + 1]));
-            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+            for (int tt = 0; tt < 4; ++tt)
+              h2[tt] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * tt]), __uint_as_float(v[g * 8 + 2 * tt + 1]));
+            *reinterpret_cast<uint4*>(dst + hf * 64 + c * 32 + g * 8) = o;
           }
         }
       }
@@ -386,13 +412,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 }
 
 // ===================================================================================== backward: dQ
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t qdo_full, kv_full, kv_empty, sdp_full, ds_full, acc_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint8_t s_keep[AT];
+  __shared__ uint32_t s_bits[4];
+  __shared__ float s_red[2][AT];
   Smem4 sm;
   carve(smem_raw, sm, 5);  // 0 Q, 1 dO, 2 K, 3 V, 4 dS
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -404,7 +431,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); }
   if (warp == 1 && lane == 0) {
     mbar_init(&qdo_full, 1); mbar_init(&kv_full, 1); mbar_init(&kv_empty, 1); mbar_init(&sdp_full, 1);
-    mbar_init(&ds_full, 128); mbar_init(&acc_full, 1);
+    mbar_init(&ds_full, NCOMPUTE); mbar_init(&acc_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -443,7 +470,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       umma_commit(&acc_full);
     }
   } else {
+    const int cw = warp - 2;
     const int quad = warp & 3;
+    const int hf = cw >> 2;
     const int r = quad * 32 + lane;
     const int tid = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -455,31 +484,28 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const float Dv = qok ? p.dvec[ridx] : 0.f;
     for (int j = 0; j < nkb; ++j) {
       const int kg0 = j * AT;
-      {
-        const int kc = kg0 + tid;
-        uint8_t kp = (kc < p.Sk) ? 1 : 0;
-        if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc];
-        compute_bar_sync();
-        s_keep[tid] = kp;
-        compute_bar_sync();
-      }
+      compute_bar_sync();                    // everyone finished reading the previous block's bitmap
+      build_keep_bits(s_bits, p, b, kg0, tid);
+      compute_bar_sync();
+      uint32_t msk[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        msk[c] = qok ? chunk_mask(s_bits[hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32) : 0u;
       mbar_wait(&sdp_full, j & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t sv[32], dv[32];
-        tmem_ld32(tS + lane_addr + c * 32, sv);
-        tmem_ld32(tdP + lane_addr + c * 32, dv);
+        tmem_ld32(tS + lane_addr + hf * 64 + c * 32, sv);
+        tmem_ld32(tdP + lane_addr + hf * 64 + c * 32, dv);
         tmem_ld_wait();
         float ds[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int col = c * 32 + i;
-          const bool ok = qok && s_keep[col] && (!p.causal || kg0 + col <= qg);
-          const float pv = ok ? exp2f(__uint_as_float(sv[i]) * sl2 - L) : 0.f;
+          const float pv = ((msk[c] >> i) & 1u) ? ex2(__uint_as_float(sv[i]) * sl2 - L) : 0.f;
           ds[i] = pv * (__uint_as_float(dv[i]) - Dv) * p.scale;
         }
-        store_chunk(sm.t[4], r, c * 32, ds);
+        store_chunk(sm.t[4], r, hf * 64 + c * 32, ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -487,11 +513,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     }
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    __nv_bfloat16* dst = p.dq + (long long)b * p.dq_sb + (long long)qg * p.lddq + h * AT;
+    __nv_bfloat16* dst = p.dq + (long long)b * p.dq_sb + (long long)qg * p.lddq + h * AT + hf * 64;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(tdQ + lane_addr + c * 32, v);
+      tmem_ld32(tdQ + lane_addr + hf * 64 + c * 32, v);
       tmem_ld_wait();
       if (qok) {
 #pragma unroll
@@ -499,8 +525,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           uint4 o;
           __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            h2[t] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * t]), __uint_as_float(v[g * 8 + 2 * t + 1]));
+          for (int tt = 0; tt < 4; ++tt)
+            h2[tt] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * tt]), __uint_as_float(v[g * 8 + 2 * tt + 1]));
           *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
         }
       }
@@ -585,7 +611,7 @@ extern "C" int pb_attn_fwd(const pb_attn_desc* d, void* stream_) {
   const int smem = 4 * TILE_BYTES + 1024;
   if (set_smem(attn_fwd_kernel, smem, attr)) return -1;
   dim3 grid((d->Sq + AT - 1) / AT, d->H, d->B);
-  attn_fwd_kernel<<<grid, 192, smem, stream>>>(tq, tk, tv, p);
+  attn_fwd_kernel<<<grid, NTHREADS, smem, stream>>>(tq, tk, tv, p);
   return pb_check_launch("attn_fwd_kernel");
 }
 
@@ -611,9 +637,9 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
   if (set_smem(attn_bwd_dkv_kernel, smem1, attr1)) return -1;
   if (set_smem(attn_bwd_dq_kernel, smem2, attr2)) return -1;
   dim3 g1((d->Sk + AT - 1) / AT, d->H, d->B);
-  attn_bwd_dkv_kernel<<<g1, 192, smem1, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_dkv_kernel<<<g1, NTHREADS, smem1, stream>>>(tq, tk, tv, tdo, p);
   if (pb_check_launch("attn_bwd_dkv_kernel")) return -1;
   dim3 g2((d->Sq + AT - 1) / AT, d->H, d->B);
-  attn_bwd_dq_kernel<<<g2, 192, smem2, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_dq_kernel<<<g2, NTHREADS, smem2, stream>>>(tq, tk, tv, tdo, p);
   return pb_check_launch("attn_bwd_dq_kernel");
 }
