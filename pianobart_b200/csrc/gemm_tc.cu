@@ -336,8 +336,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (out_f32) {
           float* c = reinterpret_cast<float*>(p.c) + c_off + col0;
           if (atomic_acc) {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(c + j, x[j]);
+            if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)   // 16-byte vector reduction (red.global.add.v4.f32, sm_90+)
+                atomicAdd(reinterpret_cast<float4*>(c + j), make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]));
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(c + j, x[j]);
+            }
           } else if (full && ((p.ldc & 3) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)

@@ -160,8 +160,9 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
 
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += dy*xhat, dbeta += dy,
 // dbias (optional) += dx  - the bias gradient of the Linear whose output (+ residual) fed this LayerNorm.
+constexpr int LNB_WARPS = 8;
 template <typename T, int MAXP>
-__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, T* __restrict__ dx,
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict_
     }
   }
   // block-level reduction of the per-warp partials, then one atomic per column per block
-  __shared__ float sh[4][32 * 8 + 1];
+  __shared__ float sh[LNB_WARPS][32 * 8 + 1];
   for (int pass = 0; pass < 3; ++pass) {
     float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
     if (out == nullptr) continue;
@@ -564,8 +565,10 @@ static void ln_fwd_launch(const void* x, const float* gamma, const float* beta, 
 template <typename T, int MAXP>
 static void ln_bwd_launch(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
                           float* dgamma, float* dbeta, float* dbias, long long M, int d, cudaStream_t st) {
-  const int grid = grid_for(M, 4 * 4, 4);
-  layernorm_bwd_kernel<T, MAXP><<<grid, 128, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
+  // one 16-warp block per SM: the per-column partial sums are reduced through shared memory first, so only
+  // #SM atomics per column reach L2 (the 12 KB gradient row is a contention hot spot otherwise)
+  const int grid = grid_for(M, LNB_WARPS * 2, 1);
+  layernorm_bwd_kernel<T, MAXP><<<grid, LNB_WARPS * 32, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
                                                       dbias, M, d);
 }
 

@@ -168,7 +168,7 @@ class Plan:
     # ---- op recorders ------------------------------------------------------------------
     def gemm(self, a, b, c, M, N, K, lda, ldb, ldc, bias=0, residual=0, ldr=0, a_mn=0, b_mn=0, flags=0, alpha=1.0,
              batch_h=1, batch_b=1, a_sh=0, a_sb=0, b_sh=0, b_sb=0, c_sh=0, c_sb=0, r_sh=0, r_sb=0, split_k=1,
-             causal=0, aux=0, ldaux=0, r_row_mod=0, name='gemm'):
+             causal=0, aux=0, ldaux=0, r_row_mod=0, block_n=0, name='gemm'):
         d = L.GemmDesc()
         d.a, d.b, d.c = a, b, c
         d.bias = bias or None
@@ -179,7 +179,7 @@ class Plan:
         d.batch_h, d.batch_b = batch_h, batch_b
         d.a_stride_h, d.a_stride_b, d.b_stride_h, d.b_stride_b = a_sh, a_sb, b_sh, b_sb
         d.c_stride_h, d.c_stride_b, d.r_stride_h, d.r_stride_b = c_sh, c_sb, r_sh, r_sb
-        d.alpha, d.flags, d.split_k, d.causal, d.block_n = alpha, flags, split_k, causal, 0
+        d.alpha, d.flags, d.split_k, d.causal, d.block_n = alpha, flags, split_k, causal, block_n
         d.aux = aux or None
         d.ldaux = ldaux
         d.r_row_mod = r_row_mod
@@ -189,11 +189,13 @@ class Plan:
 
     def wgrad(self, dy, x, dw, n_out, n_in, M, ld_dy, ld_x, name='wgrad'):
         """dW[n_out, n_in] += dY[M, n_out]^T X[M, n_in]   (fp32 atomic accumulate, split-K)."""
-        units = ((n_out + 127) // 128) * ((n_in + 255) // 256)
+        bn = int(os.environ.get('PIANOBART_B200_WGRAD_BN', '256'))
+        units = ((n_out + 127) // 128) * ((n_in + bn - 1) // bn)
         kblocks = (M + 63) // 64
-        split = max(1, min((296 + units - 1) // units, max(1, kblocks // 4)))
+        target = int(os.environ.get('PIANOBART_B200_WGRAD_UNITS', '296'))
+        split = max(1, min((target + units - 1) // units, max(1, kblocks // 4)))
         self.gemm(dy, x, dw, n_out, n_in, M, ld_dy, ld_x, n_in, a_mn=1, b_mn=1,
-                  flags=L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC, split_k=split, name=name)
+                  flags=L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC, split_k=split, block_n=bn, name=name)
 
     def embed_fwd(self, ids, table, out, M, ntok_arr, err=0):
         self._add('embed_fwd', self.lib.pb_octuple_embed_fwd, C.c_void_p(ids), 0, C.c_void_p(table), C.c_void_p(out),
