@@ -124,6 +124,43 @@ def cpu_baseline(batch=1, steps=2, warmup=1):
                       % (batch, S, steps, os.cpu_count()), 's_per_step': per}
 
 
+def decode_bench(lm, pb, dev, peaks, steps=192, warmup=16):
+    """KV-cache decode (BASELINE.json configs[2]): encoder prompt 1024 tokens, batch 1 and 64; timed region = `steps`
+    CUDA-graph replays (one generated Octuple token per sequence per replay), CUDA events on the launching stream."""
+    import numpy as np
+    import torch
+    from oracle import params as P
+    from pianobart_b200.generate import Generator
+    out = {}
+    d, L, F, S = 1024, 8, 2048, 1024
+    w_bytes = 2 * (L * (4 * d * d + 2 * d * d + 2 * d * F) + 2048 * d + d * 1280)
+    for B in (1, 64):
+        gen = Generator(lm, B, S, S)
+        ids = torch.from_numpy(P.synth_ids(B, S, 4321)).to(dev)
+        keep = torch.ones(B, S, device=dev)
+        uni = np.random.RandomState(0).random_sample((B, S, 8))
+        # teacher-force valid tokens so that no sequence stops early and the full decode work is timed
+        forced = torch.from_numpy(P.synth_ids(B, S, 99)).to(dev)
+        gen.start(ids, keep, uni, forced)
+        gen.run_steps(warmup)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launches = gen.run_steps(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        byts = sum(w_bytes + B * (L * 2 * (t + 1) * d * 2 + L * 2 * S * d * 2) for t in range(warmup, warmup + steps))
+        ach = byts / (ms / 1e3) / 1e9
+        out['batch%d' % B] = {'tokens_per_s': B * steps / (ms / 1e3), 'us_per_step': ms / steps * 1e3,
+                              'steps': steps, 'launches_per_step': gen.launches_per_step,
+                              'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                                           'frac': ach / peaks['hbm_gbs']}}
+        del gen
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -149,6 +186,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--dtype', default='bf16')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-decode', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -278,6 +316,11 @@ def main():
                             'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
                             'peak_source': peak_src + ' (sustained: kernel timed inside a long step)',
                             'share_of_step': gemm_ms / (ms / args.steps)}
+    if world == 1 and not args.no_decode:
+        try:
+            line['decode'] = decode_bench(lm, pb, dev, peaks)
+        except Exception as e:  # the headline metric must still be printed
+            line['decode'] = {'error': repr(e)[:200]}
     if not args.no_cpu_baseline:
         cb = cpu_baseline(batch=1, steps=2, warmup=1)
         line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}

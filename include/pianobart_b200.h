@@ -179,10 +179,13 @@ int pb_decode_finalize(float* acc, const float* bias, const void* residual, cons
 /* one query token per (batch, head).  q: bf16 [B, q_ld], head h at column h*hd.  Cache row j of batch b, head h at
  * k_cache + b*kv_batch_stride + j*kv_ld + h*hd (same for v).  append != 0: k_new/v_new (addressed like q) are
  * written to row t and keys 0..t are attended (HF BartAttention with past_key_values); else n_keys keys gated by
- * key_keep uint8 [B, n_keys] (cross attention on the encoder output). */
+ * key_keep uint8 [B, n_keys] (cross attention on the encoder output).  Keys are split over ceil(max_keys/128) CTAs per
+ * (batch, head); partial (max, sum, out) go through `workspace` and the last CTA (ticket) combines them. */
 int pb_decode_attn(const void* q, int q_ld, const void* k_new, const void* v_new, void* k_cache, void* v_cache,
                    long long kv_batch_stride, int kv_ld, const uint8_t* key_keep, int n_keys, const int* t_dev,
-                   int append, void* out, int out_ld, int B, int H, int hd, float scale, int max_keys, void* stream);
+                   int append, void* out, int out_ld, int B, int H, int hd, float scale, int max_keys,
+                   float* workspace /* B*H*ceil(max_keys/128)*(hd+2) floats */, int* tickets /* B*H ints, zeroed once */,
+                   void* stream);
 /* PianoBartLM.sample (model.py:68-78) + sampling/nucleus (model.py:84-107) for step t: logits fp32 [B, 1280];
  * uniforms double [B,S,8] drawn on the host from numpy's stream (one per attribute per step, as np.random.choice
  * consumes them); forced int32 [B,S,8] or NULL (teacher forcing).  Writes cur_tok int32 [B,8], sampled [B,S,8]. */

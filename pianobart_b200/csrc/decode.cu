@@ -81,58 +81,99 @@ __global__ void __launch_bounds__(256) decode_finalize_kernel(float* __restrict_
   }
 }
 
-// grid (H, B), 128 threads.  q: [B, q_ld] (head h at column h*hd).  K/V: row j of batch b at
-// base + b*kv_bs + j*kv_ld + h*hd.  append != 0: first copy k_new/v_new (same addressing as q with their own
-// pointers) into row t = *t_dev and attend to t+1 keys; else attend to n_keys keys gated by key_keep [B, n_keys].
+// Split-key ("flash-decoding") single-query attention.  grid (H, B, NS), 128 threads; CTA z handles keys
+// [z*128, z*128+128).  q: [B, q_ld] (head h at column h*hd).  K/V: row j of batch b at base + b*kv_bs + j*kv_ld + h*hd.
+// append != 0: split 0 first copies k_new/v_new into row t = *t_dev (visible to the split that owns row t because that
+// split re-reads the new row from k_new/v_new directly); keys 0..t are attended.  Otherwise n_keys keys gated by
+// key_keep [B, n_keys].  Each CTA writes (max, sum, unnormalised out[hd]) to the workspace; the last CTA of a (b, h)
+// group (atomic ticket) combines the partials and writes the bf16 output.
+constexpr int DK = 128;  // keys per CTA
 __global__ void __launch_bounds__(128) decode_attn_kernel(const bf16* __restrict__ q, int q_ld, const bf16* __restrict__ k_new,
                                                           const bf16* __restrict__ v_new, bf16* __restrict__ kc,
                                                           bf16* __restrict__ vc, long long kv_bs, int kv_ld,
                                                           const uint8_t* __restrict__ key_keep, int n_keys,
                                                           const int* __restrict__ t_dev, int append, bf16* __restrict__ out,
-                                                          int out_ld, int hd, float scale, int max_keys) {
-  extern __shared__ float sc[];  // max_keys scores
+                                                          int out_ld, int hd, float scale, int max_keys,
+                                                          float* __restrict__ ws, int* __restrict__ tickets) {
   __shared__ float qs[128];
+  __shared__ float pr[DK];
   __shared__ float red[8];
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int is_last;
+  const int h = blockIdx.x, b = blockIdx.y, z = blockIdx.z, NS = gridDim.z, H = gridDim.x;
+  const int tid = threadIdx.x;
   bf16* K = kc + (long long)b * kv_bs + h * hd;
   bf16* V = vc + (long long)b * kv_bs + h * hd;
-  int n = n_keys;
+  int n = n_keys, t = -1;
   if (append) {
-    const int t = *t_dev;
+    t = *t_dev;
     if (t >= max_keys) return;
-    for (int i = threadIdx.x; i < hd; i += blockDim.x) {
-      K[(long long)t * kv_ld + i] = k_new[(long long)b * q_ld + h * hd + i];
-      V[(long long)t * kv_ld + i] = v_new[(long long)b * q_ld + h * hd + i];
-    }
     n = t + 1;
+    if (z == 0)
+      for (int i = tid; i < hd; i += blockDim.x) {
+        K[(long long)t * kv_ld + i] = k_new[(long long)b * q_ld + h * hd + i];
+        V[(long long)t * kv_ld + i] = v_new[(long long)b * q_ld + h * hd + i];
+      }
   }
-  for (int i = threadIdx.x; i < hd; i += blockDim.x) qs[i] = __bfloat162float(q[(long long)b * q_ld + h * hd + i]) * scale;
+  for (int i = tid; i < hd; i += blockDim.x) qs[i] = __bfloat162float(q[(long long)b * q_ld + h * hd + i]) * scale;
   __syncthreads();
+  const int j0 = z * DK;
+  const int j = j0 + tid;
   const uint8_t* keep = (!append && key_keep) ? key_keep + (long long)b * n_keys : nullptr;
-  float mx = -INFINITY;
-  for (int j = warp; j < n; j += 4) {
+  // one key per thread: 2*hd bytes of the key row in 16-byte loads (row t comes from k_new: it may not be visible yet)
+  float sc = -INFINITY;
+  if (j < n && (!keep || keep[j])) {
+    const bf16* krow = (j == t) ? (k_new + (long long)b * q_ld + h * hd) : (K + (long long)j * kv_ld);
     float d = 0.f;
-    for (int i = lane; i < hd; i += 32) d += qs[i] * __bfloat162float(K[(long long)j * kv_ld + i]);
+    for (int i = 0; i < hd; i += 8) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(krow + i);
+      const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (keep && !keep[j]) d = -INFINITY;
-    if (lane == 0) sc[j] = d;
-    mx = fmaxf(mx, d);
+      for (int u = 0; u < 4; ++u) {
+        const float2 f = __bfloat1622float2(k2[u]);
+        d += qs[i + 2 * u] * f.x + qs[i + 2 * u + 1] * f.y;
+      }
+    }
+    sc = d;
   }
-  mx = block_max(mx, red);
-  float sum = 0.f;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const float e = (sc[j] == -INFINITY) ? 0.f : __expf(sc[j] - mx);
-    sc[j] = e;
-    sum += e;
+  const float mx = block_max(sc, red);
+  const float e = (sc == -INFINITY) ? 0.f : __expf(sc - mx);
+  pr[tid] = e;
+  const float sum = block_sum(e, red);   // contains the __syncthreads that publishes pr[]
+  const int cnt = min(DK, n - j0);
+  float o = 0.f;
+  if (tid < hd && cnt > 0) {
+#pragma unroll 4
+    for (int jj = 0; jj < cnt; ++jj) {
+      const int key = j0 + jj;
+      const bf16* vrow = (key == t) ? (v_new + (long long)b * q_ld + h * hd) : (V + (long long)key * kv_ld);
+      o += pr[jj] * __bfloat162float(vrow[tid]);
+    }
   }
-  sum = block_sum(sum, red);
-  const float inv = sum > 0.f ? 1.f / sum : 0.f;
-  for (int i = threadIdx.x; i < hd; i += blockDim.x) {
-    float o = 0.f;
-    for (int j = 0; j < n; ++j) o += sc[j] * __bfloat162float(V[(long long)j * kv_ld + i]);
-    out[(long long)b * out_ld + h * hd + i] = __float2bfloat16(o * inv);
+  float* w = ws + (((long long)b * H + h) * NS + z) * (hd + 2);
+  if (tid < hd) w[2 + tid] = o;
+  if (tid == 0) { w[0] = mx; w[1] = sum; }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int tk = atomicAdd(tickets + b * H + h, 1);
+    is_last = (tk == NS - 1);
+    if (is_last) tickets[b * H + h] = 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float* wb = ws + ((long long)b * H + h) * NS * (hd + 2);
+  float gm = -INFINITY;
+  for (int s2 = 0; s2 < NS; ++s2) gm = fmaxf(gm, wb[s2 * (hd + 2)]);
+  if (tid < hd) {
+    float tot = 0.f, acc = 0.f;
+    for (int s2 = 0; s2 < NS; ++s2) {
+      const float m2 = wb[s2 * (hd + 2)];
+      const float f = (m2 == -INFINITY) ? 0.f : __expf(m2 - gm);
+      tot += wb[s2 * (hd + 2) + 1] * f;
+      acc += wb[s2 * (hd + 2) + 2 + tid] * f;
+    }
+    out[(long long)b * out_ld + h * hd + tid] = __float2bfloat16(tot > 0.f ? acc / tot : 0.f);
   }
 }
 
@@ -239,13 +280,14 @@ extern "C" int pb_decode_finalize(float* acc, const float* bias, const void* res
 
 extern "C" int pb_decode_attn(const void* q, int q_ld, const void* k_new, const void* v_new, void* k_cache, void* v_cache,
                               long long kv_batch_stride, int kv_ld, const uint8_t* key_keep, int n_keys, const int* t_dev,
-                              int append, void* out, int out_ld, int B, int H, int hd, float scale, int max_keys, void* stream) {
-  if (hd > 128) return pb_set_error("decode_attn: head_dim > 128");
-  if (max_keys * 4 > 40 * 1024) return pb_set_error("decode_attn: too many keys");
-  dim3 grid(H, B);
-  decode_attn_kernel<<<grid, 128, max_keys * sizeof(float), PB_STREAM(stream)>>>(
+                              int append, void* out, int out_ld, int B, int H, int hd, float scale, int max_keys,
+                              float* workspace, int* tickets, void* stream) {
+  if (hd > 128 || (hd % 8) != 0) return pb_set_error("decode_attn: head_dim must be a multiple of 8 and <= 128");
+  const int NS = (max_keys + DK - 1) / DK;
+  dim3 grid(H, B, NS);
+  decode_attn_kernel<<<grid, 128, 0, PB_STREAM(stream)>>>(
       (const bf16*)q, q_ld, (const bf16*)k_new, (const bf16*)v_new, (bf16*)k_cache, (bf16*)v_cache, kv_batch_stride, kv_ld, key_keep,
-      n_keys, t_dev, append, (bf16*)out, out_ld, hd, scale, max_keys);
+      n_keys, t_dev, append, (bf16*)out, out_ld, hd, scale, max_keys, workspace, tickets);
   return pb_check_launch("decode_attn");
 }
 

@@ -55,6 +55,9 @@ class Generator:
         self.hA, self.hB, self.h1, self.h2 = z(B, d), z(B, d), z(B, d), z(B, d)
         self.qkv, self.qc, self.ao, self.f1 = z(B, 3 * d), z(B, d), z(B, d), z(B, F)
         self.logits = z(B, E.VOCAB, dt=f32)
+        ns = (max(S, S_enc) + 127) // 128
+        self.attn_ws = z(B * H * ns * (self.hd + 2), dt=f32)
+        self.attn_tickets = z(B * H, dt=i32)
         self.self_cache = [z(B, S, 2 * d) for _ in range(lay.dec_layers)]
         self.cross_kv = [z(B * S_enc, 2 * d) for _ in range(lay.dec_layers)]
         self.enc_graph = pb._graph(B, S_enc, 0, False, False)
@@ -97,7 +100,8 @@ class Generator:
         P = C.c_void_p
         plan._add('decode_attn', self.lib.pb_decode_attn, P(q), q_ld, P(k_new or None), P(v_new or None), P(kc), P(vc),
                   C.c_longlong(kv_bs), kv_ld, P(keep or None), n_keys, P(E._ptr(self.t_dev)), append, P(E._ptr(out)), self.d,
-                  self.B, self.H, self.hd, C.c_float(self.hd ** -0.5), max_keys)
+                  self.B, self.H, self.hd, C.c_float(self.hd ** -0.5), max_keys, P(E._ptr(self.attn_ws)),
+                  P(E._ptr(self.attn_tickets)))
 
     def _build(self):
         pb, lay = self.pb, self.pb.layout
