@@ -222,6 +222,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     pb = PianoBart(bc, e2w, w2e, dtype=args.dtype)
     lm = PianoBartLM(pb).to(dev)
+    lm.train()   # training-mode arithmetic: dropout(0.1) active as in the reference's Pretrainer.train()
     opt = FusedAdamW(pb, lr=2e-5, weight_decay=0.01)
     B, S = args.batch, c['seq']
     step = PretrainStep(lm, B, S, opt, 0.15, pg)
@@ -299,7 +300,7 @@ def main():
                                'default model d=1024 8+8 layers 8 heads ffn 2048, synthetic Octuple ids',
                    'per_gpu_batch': B, 'global_batch': B * world, 'seq_len': S, 'parallelism': 'dp%d' % world,
                    'l2_policy': 'per-step working set (weights 0.35 GB + activations > 10 GB) is far larger than the 126 MB L2',
-                   'dropout': 'not applied (eval-mode arithmetic, see DESIGN.md)'},
+                   'dropout': 'p=%.2f applied (train mode, counter-based masks)' % pb.dropout_p()},
         'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,

@@ -71,6 +71,13 @@ typedef struct pb_gemm_desc {
   void* aux;   /* see PB_GEMM_AUX_PREACT / PB_GEMM_MUL_DGELU; row stride ldaux, not batched      */
   long long ldaux;
   int r_row_mod; /* >0: residual row index = m % r_row_mod (learned position table broadcast over batch) */
+  /* training-mode dropout on (acc + bias [+ activation]) BEFORE the residual is added (HF Bart*Layer.forward):
+   * element (m, n) is kept iff hash(*drop_seed, drop_op, m*N + n) < drop_thresh and scaled by drop_scale.
+   * drop_seed == NULL disables it. */
+  const unsigned long long* drop_seed;
+  unsigned int drop_op;
+  unsigned int drop_thresh;
+  float drop_scale;
 } pb_gemm_desc;
 
 /* bf16 operands, tcgen05/TMEM/TMA kernel */
@@ -114,6 +121,24 @@ int pb_octuple_embed_bwd(const void* ids, int ids_int64, const void* dx, float* 
  * mean/rstd: [M] fp32 saved for backward.  d % 8 == 0 (bf16) / % 4 (fp32), d <= 2048 / 1024. */
 int pb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                      long long M, int d, float eps, int dtype, void* stream);
+/* dropout sites (see pb_gemm_desc): `out` site masks the LayerNorm OUTPUT (layernorm_embedding -> dropout);
+ * for backward, `in` site masks the incoming dy the same way, `out` site produces the second tensor dx_drop =
+ * mask(dx) (gradient of the dropped-out Linear output feeding this LayerNorm) and dbias then sums dx_drop. */
+typedef struct pb_drop_site {
+  const unsigned long long* seed; /* NULL = disabled */
+  unsigned int op, thresh;
+  float scale;
+} pb_drop_site;
+int pb_layernorm_fwd_drop(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                          long long M, int d, float eps, const pb_drop_site* out_site, int dtype, void* stream);
+int pb_layernorm_bwd_drop(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                          void* dx, void* dx_drop, float* dgamma, float* dbeta, float* dbias, long long M, int d,
+                          const pb_drop_site* in_site, const pb_drop_site* out_site, int dtype, void* stream);
+/* test hook: mask[i] = 1 iff element i of site (seed, op) is kept */
+int pb_dropout_mask(const unsigned long long* seed, unsigned int op, unsigned int thresh, unsigned char* mask,
+                    long long n, void* stream);
+/* *ptr += inc  (per-step dropout seed bump, keeps the host out of the loop) */
+int pb_add_u64(unsigned long long* ptr, unsigned long long inc, void* stream);
 /* dx written; dgamma/dbeta accumulated (+=) with fp32 atomics; dbias (may be NULL) += column sums of dx, i.e. the
  * bias gradient of the Linear whose output (+ residual) fed this LayerNorm */
 int pb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,

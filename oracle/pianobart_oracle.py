@@ -88,53 +88,66 @@ def attention(p, pre, x_q, x_kv, heads, key_keep, causal):
     return linear(o, p[pre + '.out_proj.weight'], p[pre + '.out_proj.bias'])
 
 
-def encoder(p, cfg, x, keep):
+def _drop(x, masks, key):
+    """Training-mode dropout with an explicit, already scaled mask (mask = keep / (1 - p)).  HF applies
+    nn.functional.dropout(p=config.dropout) at exactly these sites (Bart{Encoder,Decoder}.forward after
+    layernorm_embedding; Bart*Layer.forward after each attention block and after fc2)."""
+    if masks is None or key not in masks:
+        return x
+    return x * masks[key].to(x.dtype)
+
+
+def encoder(p, cfg, x, keep, masks=None):
     """HF BartEncoder.forward: embeds + positions(offset 2) -> LN -> post-LN layers."""
     S = x.shape[1]
     h = x + p['bart.encoder.embed_positions.weight'][2:2 + S]
     h = layer_norm(h, p['bart.encoder.layernorm_embedding.weight'], p['bart.encoder.layernorm_embedding.bias'])
+    h = _drop(h, masks, ('encoder', -1, 0))
     for l in range(cfg.enc_layers):
         pre = 'bart.encoder.layers.%d' % l
-        a = attention(p, pre + '.self_attn', h, h, cfg.heads, keep, False)
+        a = _drop(attention(p, pre + '.self_attn', h, h, cfg.heads, keep, False), masks, ('encoder', l, 1))
         h = layer_norm(h + a, p[pre + '.self_attn_layer_norm.weight'], p[pre + '.self_attn_layer_norm.bias'])
         f = linear(gelu_erf(linear(h, p[pre + '.fc1.weight'], p[pre + '.fc1.bias'])), p[pre + '.fc2.weight'],
                    p[pre + '.fc2.bias'])
+        f = _drop(f, masks, ('encoder', l, 3))
         h = layer_norm(h + f, p[pre + '.final_layer_norm.weight'], p[pre + '.final_layer_norm.bias'])
     return h
 
 
-def decoder(p, cfg, y, enc_out, enc_keep, dec_keep):
+def decoder(p, cfg, y, enc_out, enc_keep, dec_keep, masks=None):
     """HF BartDecoder.forward: causal self-attention, cross-attention on the encoder output."""
     S = y.shape[1]
     h = y + p['bart.decoder.embed_positions.weight'][2:2 + S]
     h = layer_norm(h, p['bart.decoder.layernorm_embedding.weight'], p['bart.decoder.layernorm_embedding.bias'])
+    h = _drop(h, masks, ('decoder', -1, 0))
     for l in range(cfg.dec_layers):
         pre = 'bart.decoder.layers.%d' % l
-        a = attention(p, pre + '.self_attn', h, h, cfg.heads, dec_keep, True)
+        a = _drop(attention(p, pre + '.self_attn', h, h, cfg.heads, dec_keep, True), masks, ('decoder', l, 1))
         h = layer_norm(h + a, p[pre + '.self_attn_layer_norm.weight'], p[pre + '.self_attn_layer_norm.bias'])
-        c = attention(p, pre + '.encoder_attn', h, enc_out, cfg.heads, enc_keep, False)
+        c = _drop(attention(p, pre + '.encoder_attn', h, enc_out, cfg.heads, enc_keep, False), masks, ('decoder', l, 2))
         h = layer_norm(h + c, p[pre + '.encoder_attn_layer_norm.weight'], p[pre + '.encoder_attn_layer_norm.bias'])
         f = linear(gelu_erf(linear(h, p[pre + '.fc1.weight'], p[pre + '.fc1.bias'])), p[pre + '.fc2.weight'],
                    p[pre + '.fc2.bias'])
+        f = _drop(f, masks, ('decoder', l, 3))
         h = layer_norm(h + f, p[pre + '.final_layer_norm.weight'], p[pre + '.final_layer_norm.bias'])
     return h
 
 
-def pianobart_forward(p, cfg, enc_ids, dec_ids=None, enc_mask=None, dec_mask=None, dec_embeds=None):
+def pianobart_forward(p, cfg, enc_ids, dec_ids=None, enc_mask=None, dec_mask=None, dec_embeds=None, masks=None):
     """PianoBart.forward (PianoBart.py:56-80).  Returns (last_hidden_state, encoder_last_hidden_state).
     Masks are (B,S) with non-zero = keep (pretrain.py:151-153 builds them as float 0/1).
     dec_embeds: pre-computed decoder input embeddings (the change_decoder_embedding path)."""
     enc_keep = None if enc_mask is None else (enc_mask != 0)
     dec_keep = None if dec_mask is None else (dec_mask != 0)
     x = linear(octuple_embed(p, enc_ids), p['encoder_linear.weight'], p['encoder_linear.bias'])
-    enc_out = encoder(p, cfg, x, enc_keep)
+    enc_out = encoder(p, cfg, x, enc_keep, masks)
     if dec_ids is None and dec_embeds is None:
         return enc_out, enc_out
     if dec_embeds is None:
         y = linear(octuple_embed(p, dec_ids), p['decoder_linear.weight'], p['decoder_linear.bias'])
     else:
         y = dec_embeds
-    dec_out = decoder(p, cfg, y, enc_out, enc_keep, dec_keep)
+    dec_out = decoder(p, cfg, y, enc_out, enc_keep, dec_keep, masks)
     return dec_out, enc_out
 
 

@@ -31,7 +31,12 @@ class GemmDesc(C.Structure):
         ("r_stride_h", C.c_longlong), ("r_stride_b", C.c_longlong),
         ("alpha", C.c_float), ("flags", C.c_int), ("split_k", C.c_int), ("causal", C.c_int),
         ("block_n", C.c_int), ("aux", C.c_void_p), ("ldaux", C.c_longlong), ("r_row_mod", C.c_int),
+        ("drop_seed", C.c_void_p), ("drop_op", C.c_uint), ("drop_thresh", C.c_uint), ("drop_scale", C.c_float),
     ]
+
+
+class DropSite(C.Structure):
+    _fields_ = [("seed", C.c_void_p), ("op", C.c_uint), ("thresh", C.c_uint), ("scale", C.c_float)]
 
 
 class AttnDesc(C.Structure):

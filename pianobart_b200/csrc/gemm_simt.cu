@@ -3,6 +3,7 @@
 // whole path can be checked against the oracle at fp32 accuracy (north star: <= 1e-4 relative on
 // the loss); it is not the production path and makes no performance claim.
 #include "pb_internal.h"
+#include "dropout.cuh"
 #include <cuda_bf16.h>
 
 namespace {
@@ -21,6 +22,7 @@ struct P {
   int nh, nb;
   long long a_sh, a_sb, b_sh, b_sb, c_sh, c_sb, r_sh, r_sb;
   float alpha; int flags; int r_row_mod;
+  pbdrop::Site drop;
 };
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const P p) {
@@ -72,6 +74,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const P p) {
       if (p.flags & PB_GEMM_AUX_PREACT) p.aux[(long long)m * p.ldaux + n] = x;
       if (p.flags & PB_GEMM_GELU) x = gelu_erf(x);
       if (p.flags & PB_GEMM_MUL_DGELU) x *= dgelu_erf(p.aux[(long long)m * p.ldaux + n]);
+      if (p.drop.seed) {
+        const uint32_t key = pbdrop::site_key(*p.drop.seed, p.drop.op);
+        x = pbdrop::keep(key, (unsigned long long)m * (unsigned long long)p.N + n, p.drop.thresh) ? x * p.drop.scale : 0.f;
+      }
       if (p.residual) x += p.residual[(long long)bb * p.r_sb + (long long)h * p.r_sh + (long long)(p.r_row_mod > 0 ? m % p.r_row_mod : m) * p.ldr + n];
       float* c = p.c + (long long)bb * p.c_sb + (long long)h * p.c_sh + (long long)m * p.ldc + n;
       if (p.flags & PB_GEMM_ATOMIC_ACC) atomicAdd(c, x); else *c = x;
@@ -95,6 +101,7 @@ extern "C" int pb_gemm_f32(const pb_gemm_desc* d, void* stream_) {
   p.a_sh = d->a_stride_h; p.a_sb = d->a_stride_b; p.b_sh = d->b_stride_h; p.b_sb = d->b_stride_b;
   p.c_sh = d->c_stride_h; p.c_sb = d->c_stride_b; p.r_sh = d->r_stride_h; p.r_sb = d->r_stride_b;
   p.alpha = d->alpha; p.flags = d->flags; p.r_row_mod = d->r_row_mod;
+  p.drop.seed = d->drop_seed; p.drop.op = d->drop_op; p.drop.thresh = d->drop_thresh; p.drop.scale = d->drop_scale;
   if ((d->flags & (PB_GEMM_AUX_PREACT | PB_GEMM_MUL_DGELU)) && d->aux == nullptr)
     return pb_set_error("pb_gemm_f32: aux epilogue without aux buffer");
   dim3 grid((d->N + TN - 1) / TN, (d->M + TM - 1) / TM, p.nh * p.nb);

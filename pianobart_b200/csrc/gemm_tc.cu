@@ -25,6 +25,7 @@
 //     148 SMs.
 #include "ptx.cuh"
 #include "pb_internal.h"
+#include "dropout.cuh"
 
 #include <mutex>
 #include <unordered_map>
@@ -53,6 +54,7 @@ struct GemmKParams {
   void* aux;
   long long ldaux;
   int r_row_mod;
+  pbdrop::Site drop;
   int causal;  // 1: skip tiles entirely above the diagonal (n0 > m0 + BLOCK_M - 1); 2: limit k range to m0+BLOCK_M
 };
 
@@ -308,6 +310,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
+        if (p.drop.seed != nullptr) {
+          const uint32_t key = pbdrop::site_key(*p.drop.seed, p.drop.op);
+          const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = pbdrop::keep(key, base + j, p.drop.thresh) ? x[j] * p.drop.scale : 0.f;
+        }
         if (p.residual != nullptr && first_split) {
           if (res_f32) {
             const float* r = reinterpret_cast<const float*>(p.residual) + r_off + col0;
@@ -516,6 +524,8 @@ extern "C" int pb_gemm_bf16(const pb_gemm_desc* d, void* stream_) {
   kp.causal = d->causal;
   kp.aux = d->aux; kp.ldaux = d->ldaux;
   kp.r_row_mod = d->r_row_mod;
+  kp.drop.seed = d->drop_seed; kp.drop.op = d->drop_op; kp.drop.thresh = d->drop_thresh; kp.drop.scale = d->drop_scale;
+  if (d->drop_seed != nullptr && (nh * nb != 1 || kp.split_k > 1)) return pb_set_error("pb_gemm_bf16: dropout needs no batching / split_k");
   if ((d->flags & (PB_GEMM_AUX_PREACT | PB_GEMM_MUL_DGELU)) && (d->aux == nullptr || nh * nb != 1 || kp.split_k > 1))
     return pb_set_error("pb_gemm_bf16: aux epilogues need aux != NULL, no batching, no split_k");
   if (kp.causal && kp.split_k > 1) return pb_set_error("pb_gemm_bf16: causal with split_k");

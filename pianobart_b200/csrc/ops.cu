@@ -4,6 +4,7 @@
 // dtype casts.  All kernels are templated on the activation type T (float = fp32 parity mode,
 // __nv_bfloat16 = production mode), use 16-byte vector accesses and fp32 arithmetic.
 #include "pb_internal.h"
+#include "dropout.cuh"
 #include <cuda_bf16.h>
 #include <stdint.h>
 
@@ -111,11 +112,12 @@ template <typename T, int MAXP>
 __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, T* __restrict__ y,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                            long long M, int d, float eps) {
+                                                            long long M, int d, float eps, pbdrop::Site drop) {
   constexpr int N = Pack<T>::N;
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const uint32_t dkey = drop.seed ? pbdrop::site_key(*drop.seed, drop.op) : 0u;
   for (long long row = warp_global; row < M; row += nwarps) {
     const T* xr = x + row * d;
     float v[MAXP][N];
@@ -152,6 +154,11 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
         float o[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) o[j] = (v[k][j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
+        if (drop.seed) {
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+            o[j] = pbdrop::keep(dkey, (unsigned long long)row * d + c + j, drop.thresh) ? o[j] * drop.scale : 0.f;
+        }
         store_pack(yr + c, o);
       }
     }
@@ -166,11 +173,14 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, T* __restrict__ dx,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            float* __restrict__ dbias, long long M, int d) {
+                                                            T* __restrict__ dx_drop, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                            long long M, int d, pbdrop::Site din, pbdrop::Site dout) {
   constexpr int N = Pack<T>::N;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const uint32_t kin = din.seed ? pbdrop::site_key(*din.seed, din.op) : 0u;
+  const uint32_t kout = dout.seed ? pbdrop::site_key(*dout.seed, dout.op) : 0u;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   float ag[MAXP][N], ab[MAXP][N], ax[MAXP][N];
@@ -189,6 +199,11 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
         float xv[N], dv[N];
         load_pack(x + row * d + c, xv);
         load_pack(dy + row * d + c, dv);
+        if (din.seed) {   // dy is the gradient of dropout(LayerNorm(x)): undo through the same mask
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+            dv[j] = pbdrop::keep(kin, (unsigned long long)row * d + c + j, din.thresh) ? dv[j] * din.scale : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < N; ++j) {
           xh[k][j] = (xv[j] - mean) * rstd;
@@ -208,8 +223,16 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
       if (c < d) {
         float o[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) { o[j] = rstd * (g[k][j] - s1 - xh[k][j] * s2); ax[k][j] += o[j]; }
+        for (int j = 0; j < N; ++j) o[j] = rstd * (g[k][j] - s1 - xh[k][j] * s2);
         store_pack(dx + row * d + c, o);
+        if (dout.seed) {  // gradient of the dropped-out Linear output that (plus the residual) fed this LayerNorm
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+            o[j] = pbdrop::keep(kout, (unsigned long long)row * d + c + j, dout.thresh) ? o[j] * dout.scale : 0.f;
+          store_pack(dx_drop + row * d + c, o);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) ax[k][j] += o[j];
       }
     }
   }
@@ -558,18 +581,19 @@ static int ln_packs(int d, int dtype) {
 
 template <typename T, int MAXP>
 static void ln_fwd_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                          long long M, int d, float eps, cudaStream_t st) {
+                          long long M, int d, float eps, pbdrop::Site drop, cudaStream_t st) {
   const int grid = grid_for(M, 4, 16);
-  layernorm_fwd_kernel<T, MAXP><<<grid, 128, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, M, d, eps);
+  layernorm_fwd_kernel<T, MAXP><<<grid, 128, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, M, d, eps, drop);
 }
 template <typename T, int MAXP>
 static void ln_bwd_launch(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
-                          float* dgamma, float* dbeta, float* dbias, long long M, int d, cudaStream_t st) {
+                          void* dx_drop, float* dgamma, float* dbeta, float* dbias, long long M, int d, pbdrop::Site din,
+                          pbdrop::Site dout, cudaStream_t st) {
   // one 16-warp block per SM: the per-column partial sums are reduced through shared memory first, so only
   // #SM atomics per column reach L2 (the 12 KB gradient row is a contention hot spot otherwise)
   const int grid = grid_for(M, LNB_WARPS * 2, 1);
-  layernorm_bwd_kernel<T, MAXP><<<grid, LNB_WARPS * 32, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
-                                                      dbias, M, d);
+  layernorm_bwd_kernel<T, MAXP><<<grid, LNB_WARPS * 32, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx,
+                                                                 (T*)dx_drop, dgamma, dbeta, dbias, M, d, din, dout);
 }
 
 #define LN_DISPATCH(FN, ...)                                                         \
@@ -581,21 +605,55 @@ static void ln_bwd_launch(const void* dy, const void* x, const float* gamma, con
                   case 4: FN<float, 4>(__VA_ARGS__); break; default: FN<float, 8>(__VA_ARGS__); }     \
   }
 
-extern "C" int pb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                                long long M, int d, float eps, int dtype, void* stream) {
-  const int mp = ln_packs(d, dtype);
-  if (mp < 0) return -1;
-  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, y, mean, rstd, M, d, eps, PB_STREAM(stream));
-  return pb_check_launch("layernorm_fwd");
+static pbdrop::Site to_site(const pb_drop_site* s) {
+  pbdrop::Site r;
+  r.seed = s ? s->seed : nullptr; r.op = s ? s->op : 0; r.thresh = s ? s->thresh : 0; r.scale = s ? s->scale : 1.f;
+  return r;
 }
 
+extern "C" int pb_layernorm_fwd_drop(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                     long long M, int d, float eps, const pb_drop_site* out_site, int dtype, void* stream) {
+  const int mp = ln_packs(d, dtype);
+  if (mp < 0) return -1;
+  const pbdrop::Site ds = to_site(out_site);
+  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, y, mean, rstd, M, d, eps, ds, PB_STREAM(stream));
+  return pb_check_launch("layernorm_fwd");
+}
+extern "C" int pb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                long long M, int d, float eps, int dtype, void* stream) {
+  return pb_layernorm_fwd_drop(x, gamma, beta, y, mean, rstd, M, d, eps, nullptr, dtype, stream);
+}
+
+extern "C" int pb_layernorm_bwd_drop(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                     void* dx, void* dx_drop, float* dgamma, float* dbeta, float* dbias, long long M, int d,
+                                     const pb_drop_site* in_site, const pb_drop_site* out_site, int dtype, void* stream) {
+  const int mp = ln_packs(d, dtype);
+  if (mp < 0) return -1;
+  const pbdrop::Site di = to_site(in_site), dso = to_site(out_site);
+  if (dso.seed && dx_drop == nullptr) return pb_set_error("layernorm_bwd: out dropout site needs dx_drop");
+  LN_DISPATCH(ln_bwd_launch, dy, x, gamma, mean, rstd, dx, dx_drop, dgamma, dbeta, dbias, M, d, di, dso, PB_STREAM(stream));
+  return pb_check_launch("layernorm_bwd");
+}
 extern "C" int pb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                                 void* dx, float* dgamma, float* dbeta, float* dbias, long long M, int d, int dtype,
                                 void* stream) {
-  const int mp = ln_packs(d, dtype);
-  if (mp < 0) return -1;
-  LN_DISPATCH(ln_bwd_launch, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dbias, M, d, PB_STREAM(stream));
-  return pb_check_launch("layernorm_bwd");
+  return pb_layernorm_bwd_drop(dy, x, gamma, mean, rstd, dx, nullptr, dgamma, dbeta, dbias, M, d, nullptr, nullptr, dtype, stream);
+}
+
+__global__ void dropout_mask_kernel(const unsigned long long* seed, uint32_t op, uint32_t thresh, unsigned char* mask, long long n) {
+  const uint32_t key = pbdrop::site_key(*seed, op);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    mask[i] = pbdrop::keep(key, (unsigned long long)i, thresh) ? 1 : 0;
+}
+extern "C" int pb_dropout_mask(const unsigned long long* seed, unsigned int op, unsigned int thresh, unsigned char* mask,
+                               long long n, void* stream) {
+  dropout_mask_kernel<<<grid_for(n, 256 * 8, 8), 256, 0, PB_STREAM(stream)>>>(seed, op, thresh, mask, n);
+  return pb_check_launch("dropout_mask");
+}
+__global__ void add_u64_kernel(unsigned long long* p, unsigned long long inc) { *p += inc; }
+extern "C" int pb_add_u64(unsigned long long* ptr, unsigned long long inc, void* stream) {
+  add_u64_kernel<<<1, 1, 0, PB_STREAM(stream)>>>(ptr, inc);
+  return pb_check_launch("add_u64");
 }
 
 extern "C" int pb_softmax_fwd(const float* scores, void* probs, const uint8_t* key_keep, int B, int H, int Sq, int Sk,

@@ -168,7 +168,7 @@ class Plan:
     # ---- op recorders ------------------------------------------------------------------
     def gemm(self, a, b, c, M, N, K, lda, ldb, ldc, bias=0, residual=0, ldr=0, a_mn=0, b_mn=0, flags=0, alpha=1.0,
              batch_h=1, batch_b=1, a_sh=0, a_sb=0, b_sh=0, b_sb=0, c_sh=0, c_sb=0, r_sh=0, r_sb=0, split_k=1,
-             causal=0, aux=0, ldaux=0, r_row_mod=0, block_n=0, name='gemm'):
+             causal=0, aux=0, ldaux=0, r_row_mod=0, block_n=0, drop=None, name='gemm'):
         d = L.GemmDesc()
         d.a, d.b, d.c = a, b, c
         d.bias = bias or None
@@ -183,6 +183,8 @@ class Plan:
         d.aux = aux or None
         d.ldaux = ldaux
         d.r_row_mod = r_row_mod
+        if drop is not None:
+            d.drop_seed, d.drop_op, d.drop_thresh, d.drop_scale = drop
         self._keep.append(d)
         fn = self.lib.pb_gemm_bf16 if self.dtype == PB_BF16 else self.lib.pb_gemm_f32
         self._add(name, fn, C.byref(d))
@@ -205,14 +207,27 @@ class Plan:
         self._add('embed_bwd', self.lib.pb_octuple_embed_bwd, C.c_void_p(ids), 0, C.c_void_p(dx), C.c_void_p(dtable),
                   C.c_longlong(M), ntok_arr, C.c_float(scale), self.dtype)
 
-    def ln_fwd(self, x, gamma, beta, y, mean, rstd, M, d):
-        self._add('ln_fwd', self.lib.pb_layernorm_fwd, C.c_void_p(x), C.c_void_p(gamma), C.c_void_p(beta),
-                  C.c_void_p(y), C.c_void_p(mean), C.c_void_p(rstd), C.c_longlong(M), d, C.c_float(1e-5), self.dtype)
+    def _site(self, drop):
+        if drop is None:
+            return None
+        st = L.DropSite()
+        st.seed, st.op, st.thresh, st.scale = drop
+        self._keep.append(st)
+        return C.byref(st)
 
-    def ln_bwd(self, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, d, dbias=0):
-        self._add('ln_bwd', self.lib.pb_layernorm_bwd, C.c_void_p(dy), C.c_void_p(x), C.c_void_p(gamma),
-                  C.c_void_p(mean), C.c_void_p(rstd), C.c_void_p(dx), C.c_void_p(dgamma), C.c_void_p(dbeta),
-                  C.c_void_p(dbias or None), C.c_longlong(M), d, self.dtype)
+    def ln_fwd(self, x, gamma, beta, y, mean, rstd, M, d, drop=None):
+        self._add('ln_fwd', self.lib.pb_layernorm_fwd_drop, C.c_void_p(x), C.c_void_p(gamma), C.c_void_p(beta),
+                  C.c_void_p(y), C.c_void_p(mean), C.c_void_p(rstd), C.c_longlong(M), d, C.c_float(1e-5),
+                  self._site(drop), self.dtype)
+
+    def ln_bwd(self, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, d, dbias=0, dx_drop=0, in_drop=None, out_drop=None):
+        self._add('ln_bwd', self.lib.pb_layernorm_bwd_drop, C.c_void_p(dy), C.c_void_p(x), C.c_void_p(gamma),
+                  C.c_void_p(mean), C.c_void_p(rstd), C.c_void_p(dx), C.c_void_p(dx_drop or None), C.c_void_p(dgamma),
+                  C.c_void_p(dbeta), C.c_void_p(dbias or None), C.c_longlong(M), d, self._site(in_drop),
+                  self._site(out_drop), self.dtype)
+
+    def add_u64(self, ptr, inc):
+        self._add('add_u64', self.lib.pb_add_u64, C.c_void_p(ptr), C.c_ulonglong(inc))
 
     def softmax_fwd(self, s, p, keep, B, H, Sq, Sk, causal):
         self._add('softmax_fwd', self.lib.pb_softmax_fwd, C.c_void_p(s), C.c_void_p(p), C.c_void_p(keep or None), B, H,
@@ -272,7 +287,7 @@ class BackboneGraph:
     for fixed shapes.  All tensors are addressed by raw device pointers."""
 
     def __init__(self, layout, heads, dtype, device, B, S_enc, S_dec, w_act, w_f32, g_f32, with_heads,
-                 need_backward=True, dec_embed=None):
+                 need_backward=True, dec_embed=None, drop_p=0.0, drop_seed=None):
         """w_act: working weights (activation dtype, emb region pre-scaled by 16); w_f32: fp32 master
         (biases / LayerNorm parameters are read from it); g_f32: flat fp32 gradient buffer."""
         self.lay, self.H, self.dtype, self.device = layout, heads, dtype, device
@@ -293,6 +308,11 @@ class BackboneGraph:
         self.has_dec = S_dec > 0
         self.ntok_arr = (C.c_int * 8)(*N_TOKENS)
         self.dec_embed = dec_embed
+        # training-mode dropout (HF BartConfig.dropout): masks are regenerated from (seed, site, index)
+        self.drop_p = float(drop_p)
+        self.drop_seed = drop_seed
+        if self.drop_p > 0.0:
+            assert drop_seed is not None and 0.0 < self.drop_p < 1.0
         # inputs (filled by the caller before run)
         self.enc_ids = torch.zeros(B * S_enc * 8, device=device, dtype=torch.int32)
         self.enc_keep = torch.ones(B * S_enc, device=device, dtype=torch.uint8)
@@ -304,6 +324,14 @@ class BackboneGraph:
         self.bwd = Plan(dtype) if need_backward else None
         self._bwd_chunks = []
         self._build()
+
+    def site(self, side, layer, which):
+        """Dropout site descriptor (seed ptr, op id, threshold, scale) or None when dropout is off."""
+        if self.drop_p <= 0.0:
+            return None
+        op = (0 if side == 'encoder' else 1) * 1000 + (layer + 1) * 10 + which
+        thresh = min(int((1.0 - self.drop_p) * 4294967296.0), 4294967295)
+        return (self.drop_seed.data_ptr(), op, thresh, 1.0 / (1.0 - self.drop_p))
 
     # pointer helpers -----------------------------------------------------------------------
     def W(self, name):   # working-dtype weight pointer
@@ -324,6 +352,8 @@ class BackboneGraph:
         f, bw = self.fwd, self.bwd
         back = []  # list of closures recording backward ops; executed in reverse order at the end
 
+        if self.drop_p > 0.0:
+            f.add_u64(self.drop_seed.data_ptr(), 1)   # new masks every forward; backward re-reads the same seed
         # ---- encoder stream
         Me = B * self.Se
         enc_out, enc_back = self._stream('encoder', self.enc_ids, self.enc_keep, self.Se, None, None, 0)
@@ -389,7 +419,7 @@ class BackboneGraph:
         else:
             self.dec_embed.record_forward(self, f, Y0, M, S)
         f.ln_fwd(_ptr(Y0), self.Pf(pre + '.layernorm_embedding.weight'), self.Pf(pre + '.layernorm_embedding.bias'),
-                 _ptr(H0), _ptr(st0), _ptr(st0, M), M, d)
+                 _ptr(H0), _ptr(st0), _ptr(st0, M), M, d, drop=self.site(side, -1, 0))
 
         Smax = max(self.Se, self.Sd)
         Mmax = B * Smax
@@ -422,7 +452,8 @@ class BackboneGraph:
                        a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd, c_sb=S * d,
                        causal=2 if is_dec else 0, name=ln('pv'))
             f.gemm(_ptr(O), self.W(lp + '.self_attn.out_proj.weight'), _ptr(A), M, d, d, d, d, d,
-                   bias=self.Pf(lp + '.self_attn.out_proj.bias'), residual=_ptr(h_in), ldr=d, name=ln('out_proj'))
+                   bias=self.Pf(lp + '.self_attn.out_proj.bias'), residual=_ptr(h_in), ldr=d,
+                   drop=self.site(side, l, 1), name=ln('out_proj'))
             f.ln_fwd(_ptr(A), self.Pf(lp + '.self_attn_layer_norm.weight'), self.Pf(lp + '.self_attn_layer_norm.bias'),
                      _ptr(H1), _ptr(st1), _ptr(st1, M), M, d)
             rec.update(h_in=h_in, QKV=QKV, P=Pm, lse=lse, O=O, A=A, H1=H1, st1=st1)
@@ -454,7 +485,8 @@ class BackboneGraph:
                            a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=hd, c_sb=S * d,
                            name=ln('pv_c'))
                 f.gemm(_ptr(Oc), self.W(ca + '.out_proj.weight'), _ptr(Ac), M, d, d, d, d, d,
-                       bias=self.Pf(ca + '.out_proj.bias'), residual=_ptr(H1), ldr=d, name=ln('out_proj_c'))
+                       bias=self.Pf(ca + '.out_proj.bias'), residual=_ptr(H1), ldr=d, drop=self.site(side, l, 2),
+                       name=ln('out_proj_c'))
                 f.ln_fwd(_ptr(Ac), self.Pf(lp + '.encoder_attn_layer_norm.weight'),
                          self.Pf(lp + '.encoder_attn_layer_norm.bias'), _ptr(Hc), _ptr(stc), _ptr(stc, M), M, d)
                 rec.update(Qc=Qc, KVc=KVc, Pc=Pc, lse_c=lse_c, Oc=Oc, Ac=Ac, Hc=Hc, stc=stc)
@@ -468,7 +500,7 @@ class BackboneGraph:
             f.gemm(_ptr(h_mid), self.W(lp + '.fc1.weight'), _ptr(Gt), M, F, d, d, d, F, bias=self.Pf(lp + '.fc1.bias'),
                    flags=L.PB_GEMM_GELU | L.PB_GEMM_AUX_PREACT, aux=_ptr(Z), ldaux=F, name=ln('fc1'))
             f.gemm(_ptr(Gt), self.W(lp + '.fc2.weight'), _ptr(A2), M, d, F, F, F, d, bias=self.Pf(lp + '.fc2.bias'),
-                   residual=_ptr(h_mid), ldr=d, name=ln('fc2'))
+                   residual=_ptr(h_mid), ldr=d, drop=self.site(side, l, 3), name=ln('fc2'))
             f.ln_fwd(_ptr(A2), self.Pf(lp + '.final_layer_norm.weight'), self.Pf(lp + '.final_layer_norm.bias'),
                      _ptr(Hn), _ptr(st2), _ptr(st2, M), M, d)
             rec.update(h_mid=h_mid, Z=Z, G=Gt, A2=A2, Hn=Hn, st2=st2, lp=lp)
@@ -481,6 +513,8 @@ class BackboneGraph:
             bw = self.bwd
             # scratch gradient buffers shared by all layers of both stacks
             dA = self.buf('g.dA', Mmax, d)
+            # gradient of the dropped-out sub-layer output (== dA when dropout is off)
+            dAd = self.buf('g.dAd', Mmax, d) if self.drop_p > 0.0 else dA
             dZ = self.buf('g.dZ', Mmax, F)
             dH1 = self.buf('g.dH1', Mmax, d)
             dO = self.buf('g.dO', Mmax, d)
@@ -495,9 +529,10 @@ class BackboneGraph:
                 # -- FFN backward
                 bw.ln_bwd(_ptr(dcur), _ptr(r['A2']), self.Pf(lp + '.final_layer_norm.weight'), _ptr(r['st2']),
                           _ptr(r['st2'], M), _ptr(dA), self.G(lp + '.final_layer_norm.weight'),
-                          self.G(lp + '.final_layer_norm.bias'), M, d, dbias=self.G(lp + '.fc2.bias'))
-                bw.wgrad(_ptr(dA), _ptr(r['G']), self.G(lp + '.fc2.weight'), d, F, M, d, F, name=ln('dW_fc2'))
-                bw.gemm(_ptr(dA), self.W(lp + '.fc2.weight'), _ptr(dZ), M, F, d, d, F, F, b_mn=1,
+                          self.G(lp + '.final_layer_norm.bias'), M, d, dbias=self.G(lp + '.fc2.bias'),
+                          dx_drop=_ptr(dAd), out_drop=self.site(side, l, 3))
+                bw.wgrad(_ptr(dAd), _ptr(r['G']), self.G(lp + '.fc2.weight'), d, F, M, d, F, name=ln('dW_fc2'))
+                bw.gemm(_ptr(dAd), self.W(lp + '.fc2.weight'), _ptr(dZ), M, F, d, d, F, F, b_mn=1,
                         flags=L.PB_GEMM_MUL_DGELU, aux=_ptr(r['Z']), ldaux=F, name=ln('dZ'))
                 bw.colsum(_ptr(dZ), self.G(lp + '.fc1.bias'), M, F, F)
                 bw.wgrad(_ptr(dZ), _ptr(r['h_mid']), self.G(lp + '.fc1.weight'), F, d, M, F, d, name=ln('dW_fc1'))
@@ -511,9 +546,10 @@ class BackboneGraph:
                     dKVc = self.buf('g.dKVc', Mmax, 2 * d)
                     bw.ln_bwd(_ptr(dmid), _ptr(r['Ac']), self.Pf(lp + '.encoder_attn_layer_norm.weight'),
                               _ptr(r['stc']), _ptr(r['stc'], M), _ptr(dA), self.G(lp + '.encoder_attn_layer_norm.weight'),
-                              self.G(lp + '.encoder_attn_layer_norm.bias'), M, d, dbias=self.G(ca + '.out_proj.bias'))
-                    bw.wgrad(_ptr(dA), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
-                    bw.gemm(_ptr(dA), self.W(ca + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dOc'))
+                              self.G(lp + '.encoder_attn_layer_norm.bias'), M, d, dbias=self.G(ca + '.out_proj.bias'),
+                              dx_drop=_ptr(dAd), out_drop=self.site(side, l, 2))
+                    bw.wgrad(_ptr(dAd), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
+                    bw.gemm(_ptr(dAd), self.W(ca + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dOc'))
                     # dP = dO V^T ; dV = P^T dO ; dS = softmax'(P, dP) ; dQ = scale dS K ; dK = scale dS^T Q
                     if self.flash:
                         dvec = self.buf('g.dvec', B * H * Smax, dtype=torch.float32)
@@ -550,9 +586,10 @@ class BackboneGraph:
                 cz = 1 if is_dec else 0
                 bw.ln_bwd(_ptr(dmid), _ptr(r['A']), self.Pf(lp + '.self_attn_layer_norm.weight'), _ptr(r['st1']),
                           _ptr(r['st1'], M), _ptr(dA), self.G(lp + '.self_attn_layer_norm.weight'),
-                          self.G(lp + '.self_attn_layer_norm.bias'), M, d, dbias=self.G(sa + '.out_proj.bias'))
-                bw.wgrad(_ptr(dA), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
-                bw.gemm(_ptr(dA), self.W(sa + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dO'))
+                          self.G(lp + '.self_attn_layer_norm.bias'), M, d, dbias=self.G(sa + '.out_proj.bias'),
+                          dx_drop=_ptr(dAd), out_drop=self.site(side, l, 1))
+                bw.wgrad(_ptr(dAd), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
+                bw.gemm(_ptr(dAd), self.W(sa + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dO'))
                 QKV, Pm = r['QKV'], r['P']
                 if self.flash:
                     dvec = self.buf('g.dvec', B * H * Smax, dtype=torch.float32)
@@ -583,7 +620,7 @@ class BackboneGraph:
             dY0 = dA
             bw.ln_bwd(_ptr(dcur), _ptr(Y0), self.Pf(pre + '.layernorm_embedding.weight'), _ptr(st0), _ptr(st0, M),
                       _ptr(dY0), self.G(pre + '.layernorm_embedding.weight'), self.G(pre + '.layernorm_embedding.bias'),
-                      M, d, dbias=0 if custom_dec else self.G('encoder_linear.bias'))
+                      M, d, dbias=0 if custom_dec else self.G('encoder_linear.bias'), in_drop=self.site(side, -1, 0))
             # d pos[s+2] += sum_b dY0[b, s]  == column sums of dY0 viewed as [B, S*d]
             bw.colsum(_ptr(dY0), self.G(pre + '.embed_positions.weight') + 2 * d * 4, B, S * d, S * d)
             if not custom_dec:

@@ -60,7 +60,7 @@ class Generator:
         self.attn_tickets = z(B * H, dt=i32)
         self.self_cache = [z(B, S, 2 * d) for _ in range(lay.dec_layers)]
         self.cross_kv = [z(B * S_enc, 2 * d) for _ in range(lay.dec_layers)]
-        self.enc_graph = pb._graph(B, S_enc, 0, False, False)
+        self.enc_graph = pb._graph(B, S_enc, 0, False, False, 0.0)  # no dropout (demo.py:149-150 behaviour)
         self.ntok_arr = (C.c_int * 8)(*E.N_TOKENS)
         self.pad_arr = (C.c_int * 8)(*[int(x) for x in pb.pad_word_np])
         self.temp_arr = (C.c_float * 8)(*[float(x) for x in SAMPLE_T])

@@ -179,6 +179,7 @@ class PianoBart(nn.Module):
         self._live_graph = None
         self._wver = None
         self._anchor = None
+        self._drop_seed = None
 
     # ------------------------------------------------------------------ flat storage
     def _named_flat_params(self):
@@ -283,15 +284,24 @@ class PianoBart(nn.Module):
         self._grad.zero_()
 
     # ------------------------------------------------------------------ graphs
-    def _graph(self, B, Se, Sd, with_heads, need_bwd):
-        key = (B, Se, Sd, with_heads, need_bwd)
+    def dropout_p(self):
+        """HF BartConfig.dropout (0.1 by default) is active in train() mode, exactly like the reference's BartModel."""
+        return float(getattr(self.bartConfig, 'dropout', 0.0)) if self.training else 0.0
+
+    def _graph(self, B, Se, Sd, with_heads, need_bwd, drop_p=None):
+        drop_p = self.dropout_p() if drop_p is None else float(drop_p)
+        key = (B, Se, Sd, with_heads, need_bwd, drop_p)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= 3:
                 self._graphs.clear()  # bound activation memory
                 self._live_graph = None
+            if self._drop_seed is None or self._drop_seed.device != self._flat.device:
+                self._drop_seed = torch.tensor([torch.initial_seed() & 0x7fffffffffffffff], dtype=torch.int64,
+                                               device=self._flat.device)
             g = E.BackboneGraph(self.layout, self.heads, self.pb_dtype, self._flat.device, B, Se, Sd, self._wact,
-                                self._flat, self._grad, with_heads, need_backward=need_bwd)
+                                self._flat, self._grad, with_heads, need_backward=need_bwd, drop_p=drop_p,
+                                drop_seed=self._drop_seed)
             self._graphs[key] = g
         return g
 

@@ -86,7 +86,8 @@ class FusedAdamW:
 class PretrainStep:
     """One fused device step for a fixed (batch, seq) shape."""
 
-    def __init__(self, lm, B, S, optimizer=None, mask_percent=0.15, process_group=None):
+    def __init__(self, lm, B, S, optimizer=None, mask_percent=0.15, process_group=None, dropout=None):
+        """dropout: None = follow lm.training (HF config.dropout in train() mode, 0 in eval()), or an explicit p."""
         self.lm, self.pb = lm, lm.pianobart
         pb = self.pb
         pb._ensure_packed()
@@ -101,7 +102,7 @@ class PretrainStep:
         dev = pb._flat.device
         self.dev = dev
         self.lib = L.lib()
-        self.graph = pb._graph(B, S, S, True, True)
+        self.graph = pb._graph(B, S, S, True, True, dropout)
         M = B * S
         self.M = M
         # pinned host staging + device inputs
@@ -251,7 +252,7 @@ class Pretrainer:
         self._train_mode = True
 
     def _step(self, B, S):
-        k = (B, S)
+        k = (B, S, self.model.training)
         if k not in self._steps:
             self._steps[k] = PretrainStep(self.model, B, S, self.optim, self.mask_percent, self.pg)
         return self._steps[k]

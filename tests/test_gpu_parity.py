@@ -329,3 +329,54 @@ def test_padding_invariance_property():
         y2 = torch.cat(lm(enc2, dec, em, dm), -1)
     valid = dm != 0
     assert torch.allclose(y1[valid], y2[valid], atol=1e-5)
+
+
+def test_training_mode_dropout_matches_oracle_with_same_masks():
+    """Train-mode step (dropout p=0.1 at every HF site): the masks the kernels regenerate from (seed, site, index)
+    are dumped through pb_dropout_mask and injected into the oracle - loss and gradients must agree (fp32 mode)."""
+    from oracle import params as P
+    from oracle import pianobart_oracle as O
+    from pianobart_b200.pretrain import PretrainStep
+    L, lib = _lib()
+    g = load_golden('fwd_tiny')
+    cfgt = [int(x) for x in g['cfg']]
+    pb, lm = build_cuda_model(g['cfg'], int(g['seed']), 'fp32')
+    lm.train()
+    enc, dec, ori, lmask, em, dm = golden_inputs(g)
+    B, S = enc.shape[0], enc.shape[1]
+    d = cfgt[0]
+    st = PretrainStep(lm, B, S, None, 0.15)
+    assert st.graph.drop_p == pytest.approx(0.1)
+    st.set_device_batch(enc, dec, ori, lmask, em, dm)
+    st.run(train=True)
+    total, losses, accs = st.fetch_stats()
+    # regenerate every mask with the seed the step used
+    gph = st.graph
+    masks = {}
+    P_ = C.c_void_p
+    for side, nl in (('encoder', cfgt[1]), ('decoder', cfgt[2])):
+        sites = [(-1, 0)] + [(l, w) for l in range(nl) for w in ((1, 3) if side == 'encoder' else (1, 2, 3))]
+        for l, w in sites:
+            seed_ptr, op, thresh, scale = gph.site(side, l, w)
+            mk = torch.empty(B * S * d, dtype=torch.uint8, device='cuda:0')
+            L.check(lib.pb_dropout_mask(P_(seed_ptr), op, thresh, P_(mk.data_ptr()), C.c_longlong(mk.numel()), L.stream_ptr()), 'mask')
+            masks[(side, l, w)] = (mk.view(B, S, d).float() * scale).cpu()
+    keep_frac = float(np.mean([m.gt(0).float().mean().item() for m in masks.values()]))
+    assert abs(keep_frac - 0.9) < 0.01
+    assert len({tuple(m.flatten()[:64].tolist()) for m in masks.values()}) == len(masks)   # sites are decorrelated
+    prm = P.make_params(cfgt[0], cfgt[1], cfgt[2], cfgt[4], cfgt[5], int(g['seed']))
+    p = {k: torch.from_numpy(v).requires_grad_(True) for k, v in prm.items() if not k.startswith('decoder_linear')}
+    p['decoder_linear.weight'], p['decoder_linear.bias'] = p['encoder_linear.weight'], p['encoder_linear.bias']
+    h, _ = O.pianobart_forward(p, O.Cfg(*cfgt), enc.cpu(), dec.cpu(), em.cpu(), dm.cpu(), masks=masks)
+    ref_total, _ = O.pretrain_loss(O.lm_heads(p, h), ori.cpu(), lmask.cpu())
+    assert abs(total - ref_total.item()) / abs(ref_total.item()) < 1e-4
+    assert abs(total - float(g['total'])) / float(g['total']) > 1e-3        # and it really differs from eval mode
+    ref_total.backward()
+    for n in ('encoder_linear.weight', 'bart.decoder.layers.1.fc2.weight', 'bart.encoder.layers.0.self_attn.out_proj.bias',
+              'bart.decoder.layers.0.encoder_attn.out_proj.weight', 'bart.encoder.layernorm_embedding.weight',
+              'bart.decoder.layers.1.self_attn.q_proj.weight', 'word_emb.0.lut.weight'):
+        assert _rel(pb.flat_grad(n).cpu().numpy(), p[n].grad.numpy()) < 2e-4, n
+    # a second step draws different masks
+    st.run(train=True)
+    total2, _, _ = st.fetch_stats()
+    assert abs(total2 - total) > 1e-6

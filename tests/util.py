@@ -33,6 +33,7 @@ def build_cuda_model(cfg, seed, dtype, lm=True, suppress_specials=False, device=
             sd[kk] = torch.from_numpy(v.copy())
     model.load_state_dict(sd)
     model.to(device)
+    model.eval()   # parity fixtures are eval-mode arithmetic; dropout tests call .train() explicitly
     return pb, model
 
 
