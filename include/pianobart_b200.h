@@ -178,6 +178,9 @@ int pb_sumsq(const float* g, long long n, float* out, void* stream);
 int pb_adamw(float* p, float* m, float* v, const float* g, void* p_bf16, long long n, float lr, float beta1,
              float beta2, float eps, float wd, int step, const float* gnorm_sq, float max_norm, float grad_scale,
              float bf16_scale, void* stream);
+/* y[m,:] = x[m,:] + table[m % S,:]  (decoder input embeddings supplied by the caller - reference
+ * PianoBart.change_decoder_embedding, PianoBart.py:63-66,88-91 - plus BartLearnedPositionalEmbedding rows) */
+int pb_add_rows_mod(const void* x, const void* table, void* y, long long M, int d, int S, int dtype, void* stream);
 int pb_cast_from_f32(const float* src, void* dst, long long n, float scale, int dtype, void* stream);
 int pb_cast_to_f32(const void* src, float* dst, long long n, int dtype, void* stream);
 

@@ -517,6 +517,24 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
   }
 }
 
+// y[m, :] = x[m, :] + table[m % S, :]   (external decoder input embeddings + learned positions)
+template <typename T>
+__global__ void __launch_bounds__(256) add_rows_mod_kernel(const T* __restrict__ x, const T* __restrict__ table, T* __restrict__ y,
+                                                           long long M, int d, int S) {
+  constexpr int N = Pack<T>::N;
+  const long long packs = M * (d / N);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < packs; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / (d / N);
+    const int c = (int)(i % (d / N)) * N;
+    float a[N], b[N];
+    load_pack(x + m * d + c, a);
+    load_pack(table + (m % S) * d + c, b);
+#pragma unroll
+    for (int j = 0; j < N; ++j) a[j] += b[j];
+    store_pack(y + m * d + c, a);
+  }
+}
+
 template <typename TO>
 __global__ void __launch_bounds__(256) cast_scale_kernel(const float* __restrict__ src, TO* __restrict__ dst, long long n,
                                                          float scale) {
@@ -730,6 +748,15 @@ extern "C" int pb_adamw(float* p, float* m, float* v, const float* g, void* p_bf
   const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
   adamw_kernel<<<grid_for(n, 256 * 8, 8), 256, 0, PB_STREAM(stream)>>>(p, m, v, g, (bf16*)p_bf16, n, lr, beta1, beta2, eps, wd, step_size, gnorm_sq, max_norm, grad_scale, bf16_scale);
   return pb_check_launch("adamw");
+}
+
+extern "C" int pb_add_rows_mod(const void* x, const void* table, void* y, long long M, int d, int S, int dtype, void* stream) {
+  const int pn = dtype == PB_DTYPE_BF16 ? 8 : 4;
+  if (d % pn != 0) return pb_set_error("add_rows_mod: d must be a multiple of the pack width");
+  const int grid = grid_for(M * (d / pn), 256 * 4, 8);
+  if (dtype == PB_DTYPE_BF16) add_rows_mod_kernel<bf16><<<grid, 256, 0, PB_STREAM(stream)>>>((const bf16*)x, (const bf16*)table, (bf16*)y, M, d, S);
+  else add_rows_mod_kernel<float><<<grid, 256, 0, PB_STREAM(stream)>>>((const float*)x, (const float*)table, (float*)y, M, d, S);
+  return pb_check_launch("add_rows_mod");
 }
 
 extern "C" int pb_cast_from_f32(const float* src, void* dst, long long n, float scale, int dtype, void* stream) {

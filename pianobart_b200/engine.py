@@ -405,7 +405,7 @@ class BackboneGraph:
         OUT32 = L.PB_GEMM_OUT_F32
         nm = lambda s: '%s.%s' % (side, s)
 
-        custom_dec = is_dec and self.dec_embed is not None
+        custom_dec = is_dec and bool(self.dec_embed)
         # ---- front end (PianoBart.py:60-71) + positions + layernorm_embedding
         Y0 = self.buf(nm('Y0'), M, d)
         H0 = self.buf(nm('H0'), M, d)
@@ -417,7 +417,11 @@ class BackboneGraph:
                    bias=self.Pf('encoder_linear.bias'), residual=self.W(pre + '.embed_positions.weight') + 2 * d * self.es,
                    ldr=d, r_row_mod=S, name=nm('in_linear'))
         else:
-            self.dec_embed.record_forward(self, f, Y0, M, S)
+            # decoder input embeddings come from the caller (PianoBart.change_decoder_embedding path)
+            self.dec_in = self.buf('decoder.ext_in', M, d)
+            f._add('add_pos', f.lib.pb_add_rows_mod, C.c_void_p(_ptr(self.dec_in)),
+                   C.c_void_p(self.W(pre + '.embed_positions.weight') + 2 * d * self.es), C.c_void_p(_ptr(Y0)),
+                   C.c_longlong(M), d, S, self.dtype)
         f.ln_fwd(_ptr(Y0), self.Pf(pre + '.layernorm_embedding.weight'), self.Pf(pre + '.layernorm_embedding.bias'),
                  _ptr(H0), _ptr(st0), _ptr(st0, M), M, d, drop=self.site(side, -1, 0))
 
@@ -630,7 +634,7 @@ class BackboneGraph:
                         name=nm('dX'))
                 bw.embed_bwd(_ptr(ids), _ptr(dX), self.G('emb'), M, self.ntok_arr, 16.0)
             else:
-                self.dec_embed.record_backward(self, bw, dY0, M, S)
+                self.d_dec_in = dY0      # gradient wrt the caller's decoder input embeddings
             bw.marker('grads_final', *self.lay.ranges['%s.front' % side])
 
         return out, record_backward
@@ -645,7 +649,8 @@ class BackboneGraph:
         else:
             self.enc_keep.copy_((enc_keep.reshape(-1) != 0), non_blocking=True)
         if self.has_dec:
-            self.dec_ids.copy_(dec_ids.reshape(-1), non_blocking=True)
+            if dec_ids is not None:
+                self.dec_ids.copy_(dec_ids.reshape(-1), non_blocking=True)
             if dec_keep is None:
                 self.dec_keep.fill_(1)
             else:

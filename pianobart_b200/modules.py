@@ -80,8 +80,12 @@ class _BackboneFn(torch.autograd.Function):
     backs every Parameter.grad."""
 
     @staticmethod
-    def forward(ctx, anchor, owner, graph, want_logits):
+    def forward(ctx, anchor, dec_embeds, owner, graph, want_logits):
         ctx.owner, ctx.graph = owner, graph
+        ctx.has_dec_embeds = dec_embeds is not None
+        if dec_embeds is not None:
+            n = dec_embeds.numel()
+            graph.dec_in[:n].copy_(dec_embeds.reshape(-1))
         graph.forward()
         src = graph.logits if want_logits else graph.out
         width = E.VOCAB if want_logits else graph.d
@@ -104,7 +108,11 @@ class _BackboneFn(torch.autograd.Function):
         n = g_out.numel()
         dst[:n].copy_(g_out.reshape(-1))
         graph.backward()
-        return None, None, None, None
+        g_dec = None
+        if ctx.has_dec_embeds:
+            M = graph.B * graph.Sd
+            g_dec = graph.d_dec_in[:M * graph.d].view(graph.B, graph.Sd, graph.d).to(torch.float32, copy=True)
+        return None, g_dec, None, None, None
 
 
 class PianoBart(nn.Module):
@@ -129,7 +137,6 @@ class PianoBart(nn.Module):
         self.sos_word_np = np.array([self.e2w[t]['%s <SOS>' % t] for t in self.classes], dtype=np.int64)
         self.eos_word_np = np.array([self.e2w[t]['%s <EOS>' % t] for t in self.classes], dtype=np.int64)
         self.decoder_emb = None
-        self.decoder_linear_custom = None
 
         c = bartConfig
         if c.encoder_ffn_dim != c.decoder_ffn_dim or c.encoder_attention_heads != c.decoder_attention_heads:
@@ -288,9 +295,9 @@ class PianoBart(nn.Module):
         """HF BartConfig.dropout (0.1 by default) is active in train() mode, exactly like the reference's BartModel."""
         return float(getattr(self.bartConfig, 'dropout', 0.0)) if self.training else 0.0
 
-    def _graph(self, B, Se, Sd, with_heads, need_bwd, drop_p=None):
+    def _graph(self, B, Se, Sd, with_heads, need_bwd, drop_p=None, custom_dec=False):
         drop_p = self.dropout_p() if drop_p is None else float(drop_p)
-        key = (B, Se, Sd, with_heads, need_bwd, drop_p)
+        key = (B, Se, Sd, with_heads, need_bwd, drop_p, custom_dec)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= 3:
@@ -301,25 +308,28 @@ class PianoBart(nn.Module):
                                                device=self._flat.device)
             g = E.BackboneGraph(self.layout, self.heads, self.pb_dtype, self._flat.device, B, Se, Sd, self._wact,
                                 self._flat, self._grad, with_heads, need_backward=need_bwd, drop_p=drop_p,
-                                drop_seed=self._drop_seed)
+                                drop_seed=self._drop_seed, dec_embed=custom_dec)
             self._graphs[key] = g
         return g
 
     def _run(self, input_ids_encoder, input_ids_decoder, encoder_attention_mask, decoder_attention_mask, want_logits):
         self._ensure_packed()
+        dec_embeds = None
         if self.decoder_emb is not None and input_ids_decoder is not None:
-            raise NotImplementedError('change_decoder_embedding() path (TokenClassification with class_num >= 5) is '
-                                      'not built yet in pianobart_b200')
+            # PianoBart.py:63-66,71: decoder stream = decoder_linear(decoder_emb(ids)); tiny (class_num x 64 table,
+            # 64 -> d projection), kept in PyTorch; the result enters the kernel path as decoder input embeddings
+            dec_embeds = self.decoder_linear(self.decoder_emb(input_ids_decoder))
         B, Se = input_ids_encoder.shape[0], input_ids_encoder.shape[1]
         Sd = 0 if input_ids_decoder is None else input_ids_decoder.shape[1]
         if max(Se, Sd) + 2 > self.layout.max_pos + 2:
             raise ValueError('sequence length exceeds max_position_embeddings')
         need_bwd = torch.is_grad_enabled()
-        g = self._graph(B, Se, Sd, want_logits, need_bwd)
+        g = self._graph(B, Se, Sd, want_logits, need_bwd, custom_dec=dec_embeds is not None)
         self._sync_weights()
-        g.set_inputs(input_ids_encoder, encoder_attention_mask, input_ids_decoder, decoder_attention_mask)
+        g.set_inputs(input_ids_encoder, encoder_attention_mask,
+                     None if dec_embeds is not None else input_ids_decoder, decoder_attention_mask)
         self._live_graph = g
-        out, enc = _BackboneFn.apply(self._anchor, self, g, want_logits)
+        out, enc = _BackboneFn.apply(self._anchor, dec_embeds, self, g, want_logits)
         return out, enc
 
     def forward(self, input_ids_encoder, input_ids_decoder=None, encoder_attention_mask=None,
@@ -336,9 +346,10 @@ class PianoBart(nn.Module):
         return np.array(rand)
 
     def change_decoder_embedding(self, new_embedding, new_linear=None):
+        """PianoBart.py:88-91."""
         self.decoder_emb = new_embedding
         if new_linear is not None:
-            self.decoder_linear_custom = new_linear
+            self.decoder_linear = new_linear
 
 
 class MLM(nn.Module):

@@ -86,8 +86,11 @@ class FusedAdamW:
 class PretrainStep:
     """One fused device step for a fixed (batch, seq) shape."""
 
-    def __init__(self, lm, B, S, optimizer=None, mask_percent=0.15, process_group=None, dropout=None):
-        """dropout: None = follow lm.training (HF config.dropout in train() mode, 0 in eval()), or an explicit p."""
+    def __init__(self, lm, B, S, optimizer=None, mask_percent=0.15, process_group=None, dropout=None,
+                 loss_weights=None, loss_norm=None):
+        """dropout: None = follow lm.training (HF config.dropout in train() mode, 0 in eval()), or an explicit p.
+        loss_weights / loss_norm: total = sum_i w_i L_i / loss_norm (default: pretrain.py:184-189, w = n_tok in e2w key
+        order, norm = sum(n_tok); finetune_generation.py:238-250 passes w_i = extra_i * n_tok_i with the same norm)."""
         self.lm, self.pb = lm, lm.pianobart
         pb = self.pb
         pb._ensure_packed()
@@ -125,7 +128,11 @@ class PretrainStep:
         self.mask = (C.c_int * 8)(*[int(x) for x in pb.mask_word_np])
         self.sos = (C.c_int * 8)(*[int(x) for x in pb.sos_word_np])
         self.seg = (C.c_int * 8)(*E.N_TOKENS)
-        self.w = (C.c_float * 8)(*[float(x) for x in LOSS_WEIGHTS])
+        self.loss_weights = [float(x) for x in (loss_weights or LOSS_WEIGHTS)]
+        self.loss_norm = float(loss_norm if loss_norm is not None else sum(self.loss_weights))
+        self.w = (C.c_float * 8)(*self.loss_weights)
+        # the kernel normalises by sum(w); rescale when the caller's normaliser differs
+        self.grad_scale = sum(self.loss_weights) / self.loss_norm
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.launches = 0
         self.h2d_bytes = 0
@@ -187,7 +194,7 @@ class PretrainStep:
         L.check(lib.pb_heads_ce(P(g.logits.data_ptr()), P(self.targets.data_ptr()), P(self.loss_mask.data_ptr()),
                                 P(self.stats.data_ptr() + 64), P(self.stats.data_ptr()), P(self.stats.data_ptr() + 32),
                                 P(g.dlogits.data_ptr()) if train else P(None), P(None), C.c_longlong(M), 8, self.seg,
-                                self.w, C.c_float(1.0), pb.pb_dtype, s), 'heads_ce')
+                                self.w, C.c_float(self.grad_scale), pb.pb_dtype, s), 'heads_ce')
         n += 2
         if train:
             pb._grad.zero_()
@@ -218,7 +225,7 @@ class PretrainStep:
         with np.errstate(divide='ignore', invalid='ignore'):
             losses = num / den
             accs = cor / den
-        total = float(np.sum(losses * np.array(LOSS_WEIGHTS)) / np.sum(LOSS_WEIGHTS))
+        total = float(np.sum(losses * np.array(self.loss_weights)) / self.loss_norm)
         return total, losses, accs
 
 

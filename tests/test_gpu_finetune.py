@@ -1,0 +1,84 @@
+"""GPU parity of the finetune wrappers against fixtures recorded from the reference
+(tests/golden/cls_tiny.npz) and against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import params as P
+from util import build_cuda_model, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def _load_extra(module, prefix, names, seed):
+    sd = module.state_dict()
+    for k in names:
+        sd[k] = torch.from_numpy(P.gen_tensor(prefix + k, tuple(sd[k].shape), seed)).to(sd[k].device)
+    module.load_state_dict(sd)
+
+
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_sequence_classification_matches_reference(dtype):
+    from pianobart_b200.modules import SequenceClassification
+    g = load_golden('cls_tiny')
+    pb, _ = build_cuda_model(g['cfg'], int(g['seed']), dtype, lm=False)
+    sc = SequenceClassification(pb, class_num=4, hs=int(g['cfg'][0])).cuda()
+    _load_extra(sc, 'seqcls.', ['attention.ws1.weight', 'attention.ws2.weight', 'classifier.1.weight', 'classifier.1.bias',
+                                'classifier.3.weight', 'classifier.3.bias'], 9)
+    sc.eval()
+    ids = torch.from_numpy(g['ids'].astype(np.int64)).cuda()
+    mask = (ids[:, :, 0] != pb.bar_pad_word).float()
+    with torch.no_grad():
+        out = sc(ids, mask)
+    assert _rel(out.cpu().numpy(), g['seqcls_logits']) < (1e-4 if dtype == 'fp32' else 3e-2)
+
+
+@pytest.mark.parametrize('cn', [4, 8])
+def test_token_classification_matches_reference(cn):
+    """cn=4: decoder ids = encoder ids; cn=8: PianoBart.change_decoder_embedding path (label embedding 8x64 + Linear)."""
+    from pianobart_b200.modules import TokenClassification
+    g = load_golden('cls_tiny')
+    pb, _ = build_cuda_model(g['cfg'], int(g['seed']), 'fp32', lm=False)
+    tc = TokenClassification(pb, class_num=cn, hs=int(g['cfg'][0])).cuda()
+    names = ['classifier.1.weight', 'classifier.1.bias', 'classifier.3.weight', 'classifier.3.bias']
+    if cn >= 5:
+        names += ['pianobart.decoder_emb.lut.weight', 'pianobart.decoder_linear.weight', 'pianobart.decoder_linear.bias']
+    _load_extra(tc, 'tokcls%d.' % cn, names, 9)
+    tc.eval()
+    ids = torch.from_numpy(g['ids'].astype(np.int64)).cuda()
+    mask = (ids[:, :, 0] != pb.bar_pad_word).float()
+    if cn >= 5:
+        dec_in = torch.from_numpy(g['tokcls%d_dec_in' % cn].astype(np.int64)).cuda()
+        out = tc(ids, dec_in, mask, mask)
+        out.sum().backward()                       # gradient reaches the replacement decoder front end
+        assert tc.pianobart.decoder_emb.lut.weight.grad.abs().sum().item() > 0
+    else:
+        with torch.no_grad():
+            out = tc(ids, ids, mask, mask)
+    assert _rel(out.detach().cpu().numpy(), g['tokcls%d_logits' % cn]) < 1e-4
+
+
+def test_generation_finetune_loss_matches_oracle():
+    """finetune_generation.py:140-258 semantics (y_shift = x, decoder-mask loss, extra per-head factors)."""
+    from oracle import pianobart_oracle as O
+    from pianobart_b200.finetune_generation import GenerationTrainer
+    g = load_golden('fwd_tiny')
+    cfgt = [int(v) for v in g['cfg']]
+    pb, lm = build_cuda_model(g['cfg'], int(g['seed']), 'fp32')
+    tr = GenerationTrainer(pb, None, None, None, 1e-4, None, False, [0], model=lm, verbose=False)
+    x = torch.from_numpy(g['ori'].astype(np.int64))
+    y = torch.from_numpy(P.synth_ids(x.shape[0], x.shape[1], 77))
+    lm.eval()
+    loss, losses, accs = tr.step(x, y, train=False)
+    prm = P.make_params(cfgt[0], cfgt[1], cfgt[2], cfgt[4], cfgt[5], int(g['seed']))
+    p = {k: torch.from_numpy(v) for k, v in prm.items()}
+    keep = (x[:, :, 0] != 256).float()
+    h, _ = O.pianobart_forward(p, O.Cfg(*cfgt), x, x, keep, keep)
+    ref_total, ref_losses = O.generation_finetune_loss(O.lm_heads(p, h), y, keep)
+    assert abs(loss - ref_total.item()) / abs(ref_total.item()) < 1e-5
+    assert np.allclose(losses, [l.item() * e for l, e in zip(ref_losses, O.GEN_EXTRA_W)], rtol=1e-5)
