@@ -9,10 +9,12 @@
 // QK^T / PV attention products, and all of their backward products (dX, dW).
 //
 // Design (B200-first, not a translation of anything in the reference, which has no kernels):
-//   * persistent grid, one CTA per SM, 192 threads = 6 warps with fixed roles:
+//   * persistent grid, one CTA per SM, 320 threads = 10 warps with fixed roles:
 //       warp 0   TMA producer   (cp.async.bulk.tensor 4D, 128B swizzle, mbarrier complete_tx)
 //       warp 1   MMA issuer     (one elected thread issues tcgen05.mma, commits to mbarriers)
-//       warp 2-5 epilogue       (tcgen05.ld TMEM->registers, bias/GELU/residual, global stores)
+//       warp 2-9 epilogue       (tcgen05.ld TMEM->registers, bias/GELU/residual/dropout, global stores;
+//                                8 warps = lane quadrant x column half so two warps share a scheduler and
+//                                hide each other's load latency; bias staged in smem once per tile)
 //   * CTA tile 128 x BLOCK_N (128 or 256), BLOCK_K = 64 bf16 = one 128-byte swizzle row,
 //     multi-stage smem ring (full/empty mbarriers), two TMEM accumulators (2 x BLOCK_N columns)
 //     so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -37,7 +39,8 @@ namespace pb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;          // (TMEM lane quadrant) x (column half): two warps per scheduler
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
 struct GemmKParams {
   int M, N, K;
@@ -86,6 +89,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_bias[2][BLOCK_N];   // per accumulator stage: bias of the tile's columns (0 when absent)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,7 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -210,7 +214,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;        // which half of the tile's column chunks this warp handles
+    constexpr int CH_PER_WARP = BLOCK_N / 64;
+    const int etid = threadIdx.x - 64;       // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool out_f32 = p.flags & PB_GEMM_OUT_F32;
@@ -230,8 +237,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const long long r_off = (long long)b * p.r_stride_b + (long long)h * p.r_stride_h +
                               (long long)(p.r_row_mod > 0 ? row % p.r_row_mod : row) * p.ldr;
       const bool first_split = (split == 0);
+      // stage this tile's bias slice in shared memory (read by every row, otherwise 8 dependent global loads
+      // per chunk sit on the epilogue's critical path)
+      for (int i = etid; i < BLOCK_N; i += NUM_EPI_WARPS * 32) {
+        const int col = n_blk * BLOCK_N + i;
+        s_bias[acc][i] = (p.bias != nullptr && first_split && col < p.N) ? __ldg(p.bias + col) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      for (int chi = 0; chi < CH_PER_WARP; ++chi) {
+        const int ch = half * CH_PER_WARP + chi;
         uint32_t v[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked body below
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + ch * 32), v);
@@ -242,22 +257,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
         const bool full = (col0 + 32 <= p.N);
-        if (p.bias != nullptr && first_split) {
-          if (full) {
+        {
+          const float* sb = &s_bias[acc][ch * 32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              x[j] += bv.x; x[j + 1] += bv.y; x[j + 2] += bv.z; x[j + 3] += bv.w;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) x[j] += __ldg(p.bias + col0 + j);
-          }
+          for (int j = 0; j < 32; ++j) x[j] += sb[j];
         }
         if (p.flags & PB_GEMM_AUX_PREACT) {
           const long long a_off = (long long)row * p.ldaux + col0;
           if (out_f32) {
             float* ax = reinterpret_cast<float*>(p.aux) + a_off;
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) ax[j] = x[j];
           } else {
@@ -272,6 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 *reinterpret_cast<uint4*>(ax + j) = o;
               }
             } else {
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) ax[j] = __float2bfloat16(x[j]);
             }
@@ -288,6 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const long long a_off = (long long)row * p.ldaux + col0;
           if (out_f32) {
             const float* ax = reinterpret_cast<const float*>(p.aux) + a_off;
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) x[j] *= dgelu_erf(ax[j]);
           } else {
@@ -305,6 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
               }
             } else {
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) x[j] *= dgelu_erf(__bfloat162float(ax[j]));
             }
@@ -319,6 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (p.residual != nullptr && first_split) {
           if (res_f32) {
             const float* r = reinterpret_cast<const float*>(p.residual) + r_off + col0;
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) x[j] += r[j];
           } else {
@@ -336,6 +349,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
               }
             } else {
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) x[j] += __bfloat162float(r[j]);
             }
@@ -349,6 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int j = 0; j < 32; j += 4)   // 16-byte vector reduction (red.global.add.v4.f32, sm_90+)
                 atomicAdd(reinterpret_cast<float4*>(c + j), make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]));
             } else {
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) atomicAdd(c + j, x[j]);
             }
@@ -357,6 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(c + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) c[j] = x[j];
           }
@@ -372,6 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               *reinterpret_cast<uint4*>(c + j) = o;
             }
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) c[j] = __float2bfloat16(x[j]);
           }
