@@ -248,10 +248,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int chi = 0; chi < CH_PER_WARP; ++chi) {
         const int ch = half * CH_PER_WARP + chi;
         uint32_t v[32];
+        const int col0 = n_blk * BLOCK_N + ch * 32;
+        // issue the global loads this chunk needs (residual row, gelu' operand) before waiting on TMEM so their
+        // latency overlaps the accumulator read
+        const bool pf_ok = row_ok && (col0 + 32 <= p.N) && !out_f32;
+        const bool pf_res = pf_ok && p.residual != nullptr && first_split && !res_f32 && ((p.ldr & 7) == 0);
+        const bool pf_aux = pf_ok && (p.flags & PB_GEMM_MUL_DGELU) && ((p.ldaux & 7) == 0);
+        uint4 rres[4], raux[4];
+        if (pf_res) {
+          const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rres[g] = r[g];
+        }
+        if (pf_aux) {
+          const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) raux[g] = r[g];
+        }
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked body below
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + ch * 32), v);
         tmem_ld_wait();
-        const int col0 = n_blk * BLOCK_N + ch * 32;
         if (!row_ok || col0 >= p.N) continue;
         float x[32];
 #pragma unroll
@@ -306,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (full && ((p.ldaux & 7) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(ax + j);
+                const uint4 rv = pf_aux ? raux[j >> 3] : *reinterpret_cast<const uint4*>(ax + j);
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -339,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (full && ((p.ldr & 7) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(r + j);
+                const uint4 rv = pf_res ? rres[j >> 3] : *reinterpret_cast<const uint4*>(r + j);
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
