@@ -204,6 +204,13 @@ int pb_noise_apply(const int16_t* ori, const int* src, const int* rand_tok, cons
 int pb_decode_finalize(float* acc, const float* bias, const void* residual, const void* pos_table, const int* t_dev,
                        const float* gamma, const float* beta, void* out, float* out_f32, int B, int N, int gelu,
                        void* stream);
+/* Small-batch (B <= 8) projection for the decode step: y[b,n] = epi(sum_k x[b,k] W[n,k]).  x_raw fp32 [B,K]; if gamma
+ * != NULL the kernel first applies LayerNorm(gamma, beta) to x_raw (and stores the normalised vectors to x_norm_out,
+ * the residual of the next sub-layer); W bf16 [N,K]; epilogue: + bias, GELU, + residual fp32 [B,N], + pos_table[t+2];
+ * outputs fp32 and/or bf16 [B,N].  HBM-bound: each weight row is read once by one warp with 16-byte loads. */
+int pb_decode_gemv(const float* x_raw, const float* gamma, const float* beta, float* x_norm_out, const void* W,
+                   const float* bias, const float* residual, const void* pos_table, const int* t_dev, float* y_f32,
+                   void* y_bf16, int B, int N, int K, int gelu, void* stream);
 /* one query token per (batch, head).  q: bf16 [B, q_ld], head h at column h*hd.  Cache row j of batch b, head h at
  * k_cache + b*kv_batch_stride + j*kv_ld + h*hd (same for v).  append != 0: k_new/v_new (addressed like q) are
  * written to row t and keys 0..t are attended (HF BartAttention with past_key_values); else n_keys keys gated by
@@ -213,7 +220,7 @@ int pb_decode_attn(const void* q, int q_ld, const void* k_new, const void* v_new
                    long long kv_batch_stride, int kv_ld, const uint8_t* key_keep, int n_keys, const int* t_dev,
                    int append, void* out, int out_ld, int B, int H, int hd, float scale, int max_keys,
                    float* workspace /* B*H*ceil(max_keys/128)*(hd+2) floats */, int* tickets /* B*H ints, zeroed once */,
-                   void* stream);
+                   float* out_f32 /* optional fp32 copy of the output (either output may be NULL) */, void* stream);
 /* PianoBartLM.sample (model.py:68-78) + sampling/nucleus (model.py:84-107) for step t: logits fp32 [B, 1280];
  * uniforms double [B,S,8] drawn on the host from numpy's stream (one per attribute per step, as np.random.choice
  * consumes them); forced int32 [B,S,8] or NULL (teacher forcing).  Writes cur_tok int32 [B,8], sampled [B,S,8]. */

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const bf16* __restrict
                                                           const uint8_t* __restrict__ key_keep, int n_keys,
                                                           const int* __restrict__ t_dev, int append, bf16* __restrict__ out,
                                                           int out_ld, int hd, float scale, int max_keys,
-                                                          float* __restrict__ ws, int* __restrict__ tickets) {
+                                                          float* __restrict__ ws, int* __restrict__ tickets,
+                                                          float* __restrict__ out_f32) {
   __shared__ float qs[128];
   __shared__ float pr[DK];
   __shared__ float red[8];
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const bf16* __restrict
   if (j < n && (!keep || keep[j])) {
     const bf16* krow = (j == t) ? (k_new + (long long)b * q_ld + h * hd) : (K + (long long)j * kv_ld);
     float d = 0.f;
+#pragma unroll 16
     for (int i = 0; i < hd; i += 8) {
       const uint4 kv = *reinterpret_cast<const uint4*>(krow + i);
       const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
@@ -140,15 +142,31 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const bf16* __restrict
   pr[tid] = e;
   const float sum = block_sum(e, red);   // contains the __syncthreads that publishes pr[]
   const int cnt = min(DK, n - j0);
-  float o = 0.f;
-  if (tid < hd && cnt > 0) {
-#pragma unroll 4
-    for (int jj = 0; jj < cnt; ++jj) {
-      const int key = j0 + jj;
-      const bf16* vrow = (key == t) ? (v_new + (long long)b * q_ld + h * hd) : (V + (long long)key * kv_ld);
-      o += pr[jj] * __bfloat162float(vrow[tid]);
+  // P.V for this key chunk: warp w owns keys [32w, 32w+32), lane owns 4 consecutive head dims (8-byte loads,
+  // 8 keys in flight), then the 4 warps are summed through shared memory
+  __shared__ float po[4][128];
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const int d0 = lane * 4;
+    if (d0 < hd) {
+      const int jb = warp * 32, je = min(cnt, jb + 32);
+#pragma unroll 32
+      for (int jj = jb; jj < je; ++jj) {
+        const int key = j0 + jj;
+        const bf16* vrow = (key == t) ? (v_new + (long long)b * q_ld + h * hd) : (V + (long long)key * kv_ld);
+        const uint2 vv = *reinterpret_cast<const uint2*>(vrow + d0);
+        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv);
+        const float2 f0 = __bfloat1622float2(v2[0]), f1 = __bfloat1622float2(v2[1]);
+        const float pj = pr[jj];
+        a0 += pj * f0.x; a1 += pj * f0.y; a2 += pj * f1.x; a3 += pj * f1.y;
+      }
+      po[warp][d0] = a0; po[warp][d0 + 1] = a1; po[warp][d0 + 2] = a2; po[warp][d0 + 3] = a3;
     }
   }
+  __syncthreads();
+  float o = 0.f;
+  if (tid < hd) o = po[0][tid] + po[1][tid] + po[2][tid] + po[3][tid];
   float* w = ws + (((long long)b * H + h) * NS + z) * (hd + 2);
   if (tid < hd) w[2 + tid] = o;
   if (tid == 0) { w[0] = mx; w[1] = sum; }
@@ -173,7 +191,106 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const bf16* __restrict
       tot += wb[s2 * (hd + 2) + 1] * f;
       acc += wb[s2 * (hd + 2) + 2 + tid] * f;
     }
-    out[(long long)b * out_ld + h * hd + tid] = __float2bfloat16(tot > 0.f ? acc / tot : 0.f);
+    const float res = tot > 0.f ? acc / tot : 0.f;
+    if (out) out[(long long)b * out_ld + h * hd + tid] = __float2bfloat16(res);
+    if (out_f32) out_f32[(long long)b * out_ld + h * hd + tid] = res;
+  }
+}
+
+// Skinny GEMV for small decode batches (B <= 8): every weight row is streamed from HBM exactly once by one warp
+// (16-byte loads, 4 in flight per lane), all B activation vectors live in shared memory as fp32.
+//   prologue (optional): x <- LayerNorm(x_raw) with (gamma, beta); CTA 0 also publishes the normalised vector
+//                        (it is the residual of the next sub-layer) - this removes the separate finalize launches
+//   epilogue: y = acc + bias; GELU; + residual; + position row (t+2); written as fp32 (the next kernel's raw input)
+//             and/or bf16
+constexpr int GV_MAXB = 8;
+template <int B>
+__global__ void __launch_bounds__(256) decode_gemv_kernel(const float* __restrict__ x_raw, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ x_norm_out,
+                                                          const bf16* __restrict__ W, const float* __restrict__ bias,
+                                                          const float* __restrict__ residual, const bf16* __restrict__ pos_table,
+                                                          const int* __restrict__ t_dev, float* __restrict__ y_f32,
+                                                          bf16* __restrict__ y_bf16, int N, int K, int gelu, float eps) {
+  extern __shared__ float xs[];  // B * K
+  __shared__ float red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  // the weight rows do not depend on the prologue: put this warp's first row in flight now (8 x 16 B per lane
+  // covers K <= 2048) so the HBM latency overlaps the activation load + LayerNorm below
+  constexpr int MAXU = 8;
+  uint4 wv[MAXU];
+  int n = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (n < N) {
+    const bf16* wr = W + (long long)n * K;
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int k = lane * 8 + u * 256;
+      wv[u] = (k < K) ? *reinterpret_cast<const uint4*>(wr + k) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (int i = tid; i < B * K; i += blockDim.x) xs[i] = x_raw[i];
+  __syncthreads();
+  if (gamma != nullptr) {
+    for (int b = 0; b < B; ++b) {
+      float s = 0.f;
+      for (int i = tid; i < K; i += blockDim.x) s += xs[b * K + i];
+      const float mean = block_sum(s, red) / K;
+      float q = 0.f;
+      for (int i = tid; i < K; i += blockDim.x) { const float d = xs[b * K + i] - mean; q += d * d; }
+      const float rstd = rsqrtf(block_sum(q, red) / K + eps);
+      for (int i = tid; i < K; i += blockDim.x) {
+        const float v = (xs[b * K + i] - mean) * rstd * gamma[i] + beta[i];
+        xs[b * K + i] = v;
+        if (x_norm_out != nullptr && blockIdx.x == 0) x_norm_out[b * K + i] = v;
+      }
+    }
+    __syncthreads();
+  }
+  const bf16* pos = pos_table ? pos_table + (long long)(*t_dev + 2) * N : nullptr;
+  for (; n < N; n += nwarps) {
+    float acc[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) acc[b] = 0.f;
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int k = lane * 8 + u * 256;
+      if (k < K) {
+        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv[u]);
+        float wf[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(w2[j]); wf[2 * j] = f.x; wf[2 * j + 1] = f.y; }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          const float4 xa = *reinterpret_cast<const float4*>(&xs[b * K + k]);
+          const float4 xb = *reinterpret_cast<const float4*>(&xs[b * K + k + 4]);
+          acc[b] += wf[0] * xa.x + wf[1] * xa.y + wf[2] * xa.z + wf[3] * xa.w + wf[4] * xb.x + wf[5] * xb.y + wf[6] * xb.z +
+                    wf[7] * xb.w;
+        }
+      }
+    }
+    // next row of this warp (if any) goes in flight while the reduction / epilogue of this one runs
+    if (n + nwarps < N) {
+      const bf16* wr = W + (long long)(n + nwarps) * K;
+#pragma unroll
+      for (int u = 0; u < MAXU; ++u) {
+        const int k = lane * 8 + u * 256;
+        wv[u] = (k < K) ? *reinterpret_cast<const uint4*>(wr + k) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      float v = acc[b];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) {
+        if (bias) v += bias[n];
+        if (gelu) v = gelu_erf(v);
+        if (residual) v += residual[(long long)b * N + n];
+        if (pos) v += __bfloat162float(pos[n]);
+        if (y_f32) y_f32[(long long)b * N + n] = v;
+        if (y_bf16) y_bf16[(long long)b * N + n] = __float2bfloat16(v);
+      }
+    }
   }
 }
 
@@ -204,14 +321,11 @@ __global__ void __launch_bounds__(256) decode_sample_kernel(const float* __restr
   s = block_sum(s, red);
   for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = p[i] / s;
   __syncthreads();
-  __shared__ float tot_sh;
-  if (threadIdx.x == 0) {
-    float tot = 0.f;                       // model.py:85  probs /= (sum(probs) + 1e-5), float32 sequential sum
-    for (int i = 0; i < n; ++i) tot += p[i];
-    tot_sh = tot + 1e-5f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = p[i] / tot_sh;
+  // model.py:85  probs /= (sum(probs) + 1e-5)
+  float part = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) part += p[i];
+  const float tot1 = block_sum(part, red) + 1e-5f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = p[i] / tot1;
   __syncthreads();
   // descending rank sort (np.argsort(probs)[::-1]: among equal values the higher index comes first)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -222,26 +336,56 @@ __global__ void __launch_bounds__(256) decode_sample_kernel(const float* __restr
     si[r] = i;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // warp 0: lane l owns sorted entries [16 l, 16 l + 16); prefix sums by local scan + warp shuffle scan
+    const int lane = threadIdx.x;
+    const int k0 = lane * 16;
+    float loc[16];
+    float run = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { run += (k0 + i < n) ? sp[k0 + i] : 0.f; loc[i] = run; }
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+    const float excl = incl - run;
     int last = 1;
     if (meta.top_p[a] < 1.0f) {            // p == 1: cumsum > 1 never holds -> top-1 (reference quirk)
-      float c = 0.f;
-      bool hit = false;
-      for (int k = 0; k < n; ++k) { c += sp[k]; if (c > meta.top_p[a]) { last = k + 1; hit = true; break; } }
-      if (!hit) last = 1;
+      int first = 0x7fffffff;
+#pragma unroll
+      for (int i = 15; i >= 0; --i) if (k0 + i < n && excl + loc[i] > meta.top_p[a]) first = k0 + i;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+      last = (first == 0x7fffffff) ? 1 : first + 1;
     }
-    float cs = 0.f;
-    for (int k = 0; k < last; ++k) cs += sp[k];
+    // candidate mass cs = sum of the first `last` sorted probabilities
+    float csl = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) if (k0 + i < last) csl += sp[k0 + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) csl += __shfl_xor_sync(0xffffffffu, csl, o);
+    const float cs = csl;
     // np.random.choice(cand, size=1, p): cdf = cumsum(p) (double), cdf /= cdf[-1], searchsorted(u, 'right')
-    double tot = 0.0;
-    for (int k = 0; k < last; ++k) tot += (double)(sp[k] / cs);
+    double dloc[16];
+    double drun = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { drun += (k0 + i < last) ? (double)(sp[k0 + i] / cs) : 0.0; dloc[i] = drun; }
+    double dincl = drun;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, dincl, o); if (lane >= o) dincl += up; }
+    const double dexcl = dincl - drun;
+    const double dtot = __shfl_sync(0xffffffffu, dincl, 31);
     const double u = uniforms[((long long)b * S + t) * 8 + a];
-    double c2 = 0.0;
-    int pick = last - 1;
-    for (int k = 0; k < last; ++k) { c2 += (double)(sp[k] / cs); if (c2 / tot > u) { pick = k; break; } }
-    const int tok = si[pick];
-    sampled[((long long)b * S + t) * 8 + a] = tok;
-    cur_tok[b * 8 + a] = forced ? forced[((long long)b * S + t) * 8 + a] : tok;
+    int pick = 0x7fffffff;
+#pragma unroll
+    for (int i = 15; i >= 0; --i) if (k0 + i < last && (dexcl + dloc[i]) / dtot > u) pick = k0 + i;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pick = min(pick, __shfl_xor_sync(0xffffffffu, pick, o));
+    if (pick == 0x7fffffff) pick = last - 1;
+    if (lane == 0) {
+      const int tok = si[pick];
+      sampled[((long long)b * S + t) * 8 + a] = tok;
+      cur_tok[b * 8 + a] = forced ? forced[((long long)b * S + t) * 8 + a] : tok;
+    }
   }
 }
 
@@ -278,16 +422,53 @@ extern "C" int pb_decode_finalize(float* acc, const float* bias, const void* res
   return pb_check_launch("decode_finalize");
 }
 
+template <int B>
+static void gemv_launch(const float* x_raw, const float* gamma, const float* beta, float* x_norm_out, const void* W,
+                        const float* bias, const float* residual, const void* pos_table, const int* t_dev, float* y_f32,
+                        void* y_bf16, int N, int K, int gelu, cudaStream_t st) {
+  const int smem = B * K * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(decode_gemv_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4);
+    attr = true;
+  }
+  int grid = (N + 7) / 8;                       // 8 warps per CTA, one weight row per warp per pass
+  const int cap = pb_num_sms() * 4;
+  if (grid > cap) grid = cap;
+  decode_gemv_kernel<B><<<grid, 256, smem, st>>>(x_raw, gamma, beta, x_norm_out, (const bf16*)W, bias, residual,
+                                                 (const bf16*)pos_table, t_dev, y_f32, (bf16*)y_bf16, N, K, gelu, 1e-5f);
+}
+
+extern "C" int pb_decode_gemv(const float* x_raw, const float* gamma, const float* beta, float* x_norm_out, const void* W,
+                              const float* bias, const float* residual, const void* pos_table, const int* t_dev, float* y_f32,
+                              void* y_bf16, int B, int N, int K, int gelu, void* stream) {
+  if (B < 1 || B > GV_MAXB) return pb_set_error("decode_gemv: batch must be in [1, 8]");
+  if (K % 8 != 0 || K > 2048) return pb_set_error("decode_gemv: K must be a multiple of 8 and <= 2048");
+  cudaStream_t st = PB_STREAM(stream);
+  switch (B) {
+    case 1: gemv_launch<1>(x_raw, gamma, beta, x_norm_out, W, bias, residual, pos_table, t_dev, y_f32, y_bf16, N, K, gelu, st); break;
+    case 2: gemv_launch<2>(x_raw, gamma, beta, x_norm_out, W, bias, residual, pos_table, t_dev, y_f32, y_bf16, N, K, gelu, st); break;
+    case 3: gemv_launch<3>(x_raw, gamma, beta, x_norm_out, W, bias, residual, pos_table, t_dev, y_f32, y_bf16, N, K, gelu, st); break;
+    case 4: gemv_launch<4>(x_raw, gamma, beta, x_norm_out, W, bias, residual, pos_table, t_dev, y_f32, y_bf16, N, K, gelu, st); break;
+    case 5: gemv_launch<5>(x_raw, gamma, beta, x_norm_out, W, bias, residual, pos_table, t_dev, y_f32, y_bf16, N, K, gelu, st); break;
+    case 6: gemv_launch<6>(x_raw, gamma, beta, x_norm_out, W, bias, residual, pos_table, t_dev, y_f32, y_bf16, N, K, gelu, st); break;
+    case 7: gemv_launch<7>(x_raw, gamma, beta, x_norm_out, W, bias, residual, pos_table, t_dev, y_f32, y_bf16, N, K, gelu, st); break;
+    default: gemv_launch<8>(x_raw, gamma, beta, x_norm_out, W, bias, residual, pos_table, t_dev, y_f32, y_bf16, N, K, gelu, st); break;
+  }
+  return pb_check_launch("decode_gemv");
+}
+
 extern "C" int pb_decode_attn(const void* q, int q_ld, const void* k_new, const void* v_new, void* k_cache, void* v_cache,
                               long long kv_batch_stride, int kv_ld, const uint8_t* key_keep, int n_keys, const int* t_dev,
                               int append, void* out, int out_ld, int B, int H, int hd, float scale, int max_keys,
-                              float* workspace, int* tickets, void* stream) {
+                              float* workspace, int* tickets, float* out_f32, void* stream) {
   if (hd > 128 || (hd % 8) != 0) return pb_set_error("decode_attn: head_dim must be a multiple of 8 and <= 128");
+  if ((q_ld % 4) != 0 || (kv_ld % 4) != 0) return pb_set_error("decode_attn: row strides must be multiples of 4 elements");
   const int NS = (max_keys + DK - 1) / DK;
   dim3 grid(H, B, NS);
   decode_attn_kernel<<<grid, 128, 0, PB_STREAM(stream)>>>(
       (const bf16*)q, q_ld, (const bf16*)k_new, (const bf16*)v_new, (bf16*)k_cache, (bf16*)v_cache, kv_batch_stride, kv_ld, key_keep,
-      n_keys, t_dev, append, (bf16*)out, out_ld, hd, scale, max_keys, workspace, tickets);
+      n_keys, t_dev, append, (bf16*)out, out_ld, hd, scale, max_keys, workspace, tickets, out_f32);
   return pb_check_launch("decode_attn");
 }
 

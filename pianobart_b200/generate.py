@@ -23,7 +23,7 @@ SAMPLE_P = [1, 1, 1, 0.9, 0.9, 1, 1, 0.9]      # model.py:71
 
 
 class Generator:
-    def __init__(self, lm, B, S_enc, S_max=None, use_graph=True):
+    def __init__(self, lm, B, S_enc, S_max=None, use_graph=True, force_gemm=False):
         pb = lm.pianobart
         pb._ensure_packed()
         if pb.pb_dtype != E.PB_BF16:
@@ -32,6 +32,7 @@ class Generator:
         self.B, self.Se = B, S_enc
         self.S = S_max or S_enc
         self.use_graph = use_graph
+        self.force_gemm = force_gemm     # use the tcgen05 split-K path even for tiny batches (tests)
         lay = pb.layout
         d, F, H = lay.d, lay.ffn, pb.heads
         self.d, self.F, self.H, self.hd = d, F, H, d // H
@@ -96,14 +97,81 @@ class Generator:
                   P(b or None), P(E._ptr(out) if out is not None else None),
                   P(E._ptr(out_f32) if out_f32 is not None else None), self.B, N, gelu)
 
-    def _attn(self, plan, q, q_ld, k_new, v_new, kc, vc, kv_bs, kv_ld, keep, n_keys, append, out, max_keys):
+    def _attn(self, plan, q, q_ld, k_new, v_new, kc, vc, kv_bs, kv_ld, keep, n_keys, append, out, max_keys, out_f32=None):
         P = C.c_void_p
         plan._add('decode_attn', self.lib.pb_decode_attn, P(q), q_ld, P(k_new or None), P(v_new or None), P(kc), P(vc),
-                  C.c_longlong(kv_bs), kv_ld, P(keep or None), n_keys, P(E._ptr(self.t_dev)), append, P(E._ptr(out)), self.d,
+                  C.c_longlong(kv_bs), kv_ld, P(keep or None), n_keys, P(E._ptr(self.t_dev)), append,
+                  P(E._ptr(out) if out is not None else None), self.d,
                   self.B, self.H, self.hd, C.c_float(self.hd ** -0.5), max_keys, P(E._ptr(self.attn_ws)),
-                  P(E._ptr(self.attn_tickets)))
+                  P(E._ptr(self.attn_tickets)), P(E._ptr(out_f32) if out_f32 is not None else None))
+
+    def _gemv(self, plan, x_raw, W, N, K, ln=None, x_norm_out=None, bias=0, residual=None, pos=0, y_f32=None, y_bf16=None,
+              gelu=0):
+        P = C.c_void_p
+        g, b = (self._Pf(ln + '.weight'), self._Pf(ln + '.bias')) if ln else (0, 0)
+        tp = lambda t: P(E._ptr(t) if t is not None else None)
+        plan._add('decode_gemv', self.lib.pb_decode_gemv, tp(x_raw), P(g or None), P(b or None), tp(x_norm_out), P(W),
+                  P(bias or None), tp(residual), P(pos or None), P(E._ptr(self.t_dev)), tp(y_f32), tp(y_bf16), self.B, N, K, gelu)
+
+    def _build_small_batch(self):
+        """B <= 8: HBM-bound GEMV path - one launch per projection, LayerNorms fused into the consumer's prologue."""
+        pb, lay = self.pb, self.pb.layout
+        B, d, F, Se, S = self.B, self.d, self.F, self.Se, self.S
+        eg = self.enc_graph
+        f32 = torch.float32
+        z = lambda *s: torch.zeros(*s, device=self.dev, dtype=f32)
+        self.x_emb32 = z(B, 2048)
+        self.raw = [z(B, d) for _ in range(4)]
+        self.hn, self.h1n, self.h2n = z(B, d), z(B, d), z(B, d)
+        self.ao32, self.f1_32 = z(B, d), z(B, F)
+        for l in range(lay.dec_layers):
+            ca = 'bart.decoder.layers.%d.encoder_attn' % l
+            self.prefill.gemm(E._ptr(eg.enc_out), self._W(ca + '.wkv'), E._ptr(self.cross_kv[l]), B * Se, 2 * d, d, d, d, 2 * d,
+                              bias=self._Pf(ca + '.bkv'), name='kv_c%d' % l)
+        st = self.step
+        P = C.c_void_p
+        st._add('embed', self.lib.pb_octuple_embed_fwd, P(E._ptr(self.cur_tok)), 0, P(self._W('emb')), P(E._ptr(self.x_emb)),
+                C.c_longlong(B), self.ntok_arr, E.PB_BF16, P(None))
+        st._add('cast', self.lib.pb_cast_to_f32, P(E._ptr(self.x_emb)), P(E._ptr(self.x_emb32)), C.c_longlong(B * 2048), E.PB_BF16)
+        h_raw = self.raw[0]
+        self._gemv(st, self.x_emb32, self._W('encoder_linear.weight'), d, 2048, bias=self._Pf('encoder_linear.bias'),
+                   pos=self._W('bart.decoder.embed_positions.weight'), y_f32=h_raw)
+        ln_prev = 'bart.decoder.layernorm_embedding'
+        for l in range(lay.dec_layers):
+            lp = 'bart.decoder.layers.%d' % l
+            sa, ca = lp + '.self_attn', lp + '.encoder_attn'
+            r1, r2, r3 = self.raw[1], self.raw[2], self.raw[3] if h_raw is self.raw[0] else self.raw[0]
+            self._gemv(st, h_raw, self._W(sa + '.wqkv'), 3 * d, d, ln=ln_prev, x_norm_out=self.hn, bias=self._Pf(sa + '.bqkv'),
+                       y_bf16=self.qkv)
+            cache = self.self_cache[l]
+            self._attn(st, E._ptr(self.qkv), 3 * d, E._ptr(self.qkv, d), E._ptr(self.qkv, 2 * d), E._ptr(cache), E._ptr(cache, d),
+                       S * 2 * d, 2 * d, 0, 0, 1, None, S, out_f32=self.ao32)
+            self._gemv(st, self.ao32, self._W(sa + '.out_proj.weight'), d, d, bias=self._Pf(sa + '.out_proj.bias'),
+                       residual=self.hn, y_f32=r1)
+            self._gemv(st, r1, self._W(ca + '.q_proj.weight'), d, d, ln=lp + '.self_attn_layer_norm', x_norm_out=self.h1n,
+                       bias=self._Pf(ca + '.q_proj.bias'), y_bf16=self.qc)
+            kv = self.cross_kv[l]
+            self._attn(st, E._ptr(self.qc), d, 0, 0, E._ptr(kv), E._ptr(kv, d), Se * 2 * d, 2 * d, E._ptr(eg.enc_keep), Se, 0,
+                       None, Se, out_f32=self.ao32)
+            self._gemv(st, self.ao32, self._W(ca + '.out_proj.weight'), d, d, bias=self._Pf(ca + '.out_proj.bias'),
+                       residual=self.h1n, y_f32=r2)
+            self._gemv(st, r2, self._W(lp + '.fc1.weight'), F, d, ln=lp + '.encoder_attn_layer_norm', x_norm_out=self.h2n,
+                       bias=self._Pf(lp + '.fc1.bias'), y_f32=self.f1_32, gelu=1)
+            self._gemv(st, self.f1_32, self._W(lp + '.fc2.weight'), d, F, bias=self._Pf(lp + '.fc2.bias'), residual=self.h2n,
+                       y_f32=r3)
+            h_raw, ln_prev = r3, lp + '.final_layer_norm'
+        self._gemv(st, h_raw, self._W('heads.w'), E.VOCAB, d, ln=ln_prev, bias=self._Pf('heads.b'), y_f32=self.logits)
+        self._sample_idx = len(st.ops)
+        st._add('sample', self.lib.pb_decode_sample, P(E._ptr(self.logits)), P(E._ptr(self.uniforms)), P(None),
+                P(E._ptr(self.t_dev)), P(E._ptr(self.cur_tok)), P(E._ptr(self.sampled)), B, S, self.ntok_arr, self.temp_arr,
+                self.p_arr)
+        st._add('advance', self.lib.pb_decode_advance, P(E._ptr(self.cur_tok)), P(E._ptr(self.result)), P(E._ptr(self.done)),
+                P(E._ptr(self.t_dev)), P(E._ptr(self.n_written)), B, S, self.pad_arr)
+        self.launches_per_step = len(st.ops)
 
     def _build(self):
+        if self.B <= 8 and not self.force_gemm:
+            return self._build_small_batch()
         pb, lay = self.pb, self.pb.layout
         B, d, F, Se, S = self.B, self.d, self.F, self.Se, self.S
         eg = self.enc_graph

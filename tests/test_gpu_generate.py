@@ -100,7 +100,7 @@ def test_batched_decode_teacher_forced():
     res = g['result_seed0'].astype(np.int64)
     n = int((res[0, :, 0] != 256).sum())
     B = 3
-    gen = Generator(lm, B, S, S, use_graph=True)
+    gen = Generator(lm, B, S, S, use_graph=True, force_gemm=True)   # tcgen05 split-K decode path (used for large batches)
     gen.start(enc.expand(B, S, 8).contiguous(), mask.expand(B, S).contiguous(), np.zeros((B, S, 8)),
               torch.from_numpy(res).expand(B, S, 8).contiguous())
     ref = g['tf_logits'][0]
