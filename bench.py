@@ -317,11 +317,18 @@ def main():
         'step_frac_of_bf16_sustained': per_gpu_tflops / peaks['bf16_tflops_sustained'],
         'step_frac_of_bf16_burst': per_gpu_tflops / peaks['bf16_tflops'],
     }
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'r1_gemm_traffic.json')
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get('dram_bytes_per_launch_avg')
     if gemm_n:
         ach = gemm_flops / (gemm_ms / 1e3) / 1e12
         line['roofline'] = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel (all %d tcgen05 GEMM launches of one step)' % gemm_n,
                             'achieved': ach, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                            'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
+                            'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': traffic,
+                            'traffic_note': 'avg dram read+write bytes per GEMM launch from one ncu --set full capture '
+                                            '(profiles/r1_gemm_traffic.json); algorithmic flops per launch avg = %.3e' % (gemm_flops / gemm_n),
                             'peak_source': peak_src + ' (sustained: kernel timed inside a long step)',
                             'share_of_step': gemm_ms / (ms / args.steps)}
     if world == 1 and not args.no_decode:

@@ -168,6 +168,18 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += dy*xhat, dbeta += dy,
 // dbias (optional) += dx  - the bias gradient of the Linear whose output (+ residual) fed this LayerNorm.
 constexpr int LNB_WARPS = 8;
+template <typename T> struct RawPack;
+template <> struct RawPack<float> { typedef float4 type; };
+template <> struct RawPack<bf16> { typedef uint4 type; };
+__device__ __forceinline__ void unpack_raw(const float4& r, float (&f)[4]) { f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w; }
+__device__ __forceinline__ void unpack_raw(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+// One warp per row, rows software-pipelined: the 16-byte loads of row r+1 are in flight while row r is reduced
+// (the kernel is latency-bound otherwise: 8 warps per SM because of the per-column accumulators in registers).
 template <typename T, int MAXP>
 __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma,
@@ -177,6 +189,8 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
                                                             float* __restrict__ dbeta, float* __restrict__ dbias,
                                                             long long M, int d, pbdrop::Site din, pbdrop::Site dout) {
   constexpr int N = Pack<T>::N;
+  typedef typename RawPack<T>::type Raw;
+  extern __shared__ float sh_red[];   // LNB_WARPS * d floats
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t kin = din.seed ? pbdrop::site_key(*din.seed, din.op) : 0u;
@@ -188,29 +202,44 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
   for (int k = 0; k < MAXP; ++k)
 #pragma unroll
     for (int j = 0; j < N; ++j) { ag[k][j] = 0.f; ab[k][j] = 0.f; ax[k][j] = 0.f; }
-  for (long long row = warp_global; row < M; row += nwarps) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[MAXP][N], g[MAXP][N];
+  Raw rx[MAXP], rdy[MAXP];
+  float mean = 0.f, rstd = 0.f;
+  auto fetch = [&](long long row) {
+#pragma unroll
+    for (int k = 0; k < MAXP; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < d) {
+        rx[k] = *reinterpret_cast<const Raw*>(x + row * d + c);
+        rdy[k] = *reinterpret_cast<const Raw*>(dy + row * d + c);
+      }
+    }
+    mean = mean_in[row];
+    rstd = rstd_in[row];
+  };
+  long long row = warp_global;
+  if (row < M) fetch(row);
+  for (; row < M; row += nwarps) {
+    Raw cx[MAXP], cdy[MAXP];
+#pragma unroll
+    for (int k = 0; k < MAXP; ++k) { cx[k] = rx[k]; cdy[k] = rdy[k]; }
+    const float cm = mean, cr = rstd;
+    if (row + nwarps < M) fetch(row + nwarps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
         float xv[N], dv[N];
-        load_pack(x + row * d + c, xv);
-        load_pack(dy + row * d + c, dv);
-        if (din.seed) {   // dy is the gradient of dropout(LayerNorm(x)): undo through the same mask
-#pragma unroll
-          for (int j = 0; j < N; ++j)
-            dv[j] = pbdrop::keep(kin, (unsigned long long)row * d + c + j, din.thresh) ? dv[j] * din.scale : 0.f;
-        }
+        unpack_raw(cx[k], xv);
+        unpack_raw(cdy[k], dv);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          xh[k][j] = (xv[j] - mean) * rstd;
-          g[k][j] = dv[j] * __ldg(gamma + c + j);
-          s1 += g[k][j];
-          s2 += g[k][j] * xh[k][j];
-          ag[k][j] += dv[j] * xh[k][j];
+          if (din.seed) dv[j] = pbdrop::keep(kin, (unsigned long long)row * d + c + j, din.thresh) ? dv[j] * din.scale : 0.f;
+          const float xh = (xv[j] - cm) * cr;
+          const float g = dv[j] * __ldg(gamma + c + j);
+          s1 += g;
+          s2 += g * xh;
+          ag[k][j] += dv[j] * xh;
           ab[k][j] += dv[j];
         }
       }
@@ -221,9 +250,15 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
     for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
-        float o[N];
+        float xv[N], dv[N], o[N];
+        unpack_raw(cx[k], xv);
+        unpack_raw(cdy[k], dv);
 #pragma unroll
-        for (int j = 0; j < N; ++j) o[j] = rstd * (g[k][j] - s1 - xh[k][j] * s2);
+        for (int j = 0; j < N; ++j) {
+          if (din.seed) dv[j] = pbdrop::keep(kin, (unsigned long long)row * d + c + j, din.thresh) ? dv[j] * din.scale : 0.f;
+          const float xh = (xv[j] - cm) * cr;
+          o[j] = cr * (dv[j] * __ldg(gamma + c + j) - s1 - xh * s2);
+        }
         store_pack(dx + row * d + c, o);
         if (dout.seed) {  // gradient of the dropped-out Linear output that (plus the residual) fed this LayerNorm
 #pragma unroll
@@ -236,28 +271,26 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
       }
     }
   }
-  // block-level reduction of the per-warp partials, then one atomic per column per block
-  __shared__ float sh[LNB_WARPS][32 * 8 + 1];
+  // block reduction of the per-warp column partials: every warp publishes its d partials, then all threads
+  // sum the LNB_WARPS copies of their columns and issue one atomic per column per block
   for (int pass = 0; pass < 3; ++pass) {
     float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
     if (out == nullptr) continue;
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
-      __syncthreads();
       if (c < d) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) sh[warp][lane * N + j] = pass == 0 ? ag[k][j] : (pass == 1 ? ab[k][j] : ax[k][j]);
+        for (int j = 0; j < N; ++j) sh_red[warp * d + c + j] = pass == 0 ? ag[k][j] : (pass == 1 ? ab[k][j] : ax[k][j]);
       }
-      __syncthreads();
-      if (warp == 0 && c < d) {
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float t = 0.f;
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          float t = 0.f;
-          for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w][lane * N + j];
-          atomicAdd(out + c + j, t);
-        }
-      }
+      for (int w = 0; w < LNB_WARPS; ++w) t += sh_red[w * d + c];
+      atomicAdd(out + c, t);
     }
   }
 }
@@ -610,7 +643,9 @@ static void ln_bwd_launch(const void* dy, const void* x, const float* gamma, con
   // one 16-warp block per SM: the per-column partial sums are reduced through shared memory first, so only
   // #SM atomics per column reach L2 (the 12 KB gradient row is a contention hot spot otherwise)
   const int grid = grid_for(M, LNB_WARPS * 2, 1);
-  layernorm_bwd_kernel<T, MAXP><<<grid, LNB_WARPS * 32, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx,
+  const int smem = LNB_WARPS * d * (int)sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<T, MAXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  layernorm_bwd_kernel<T, MAXP><<<grid, LNB_WARPS * 32, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx,
                                                                  (T*)dx_drop, dgamma, dbeta, dbias, M, d, din, dout);
 }
 
