@@ -78,6 +78,7 @@ typedef struct pb_gemm_desc {
   unsigned int drop_op;
   unsigned int drop_thresh;
   float drop_scale;
+  int cta_group; /* tcgen05 path: 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2, 256 x 256 tiles) */
 } pb_gemm_desc;
 
 /* bf16 operands, tcgen05/TMEM/TMA kernel */

@@ -32,6 +32,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float), ("flags", C.c_int), ("split_k", C.c_int), ("causal", C.c_int),
         ("block_n", C.c_int), ("aux", C.c_void_p), ("ldaux", C.c_longlong), ("r_row_mod", C.c_int),
         ("drop_seed", C.c_void_p), ("drop_op", C.c_uint), ("drop_thresh", C.c_uint), ("drop_scale", C.c_float),
+        ("cta_group", C.c_int),
     ]
 
 

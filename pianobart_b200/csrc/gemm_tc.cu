@@ -33,6 +33,7 @@
 #include <unordered_map>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 
 namespace pb {
 
@@ -61,12 +62,16 @@ struct GemmKParams {
   int causal;  // 1: skip tiles entirely above the diagonal (n0 > m0 + BLOCK_M - 1); 2: limit k range to m0+BLOCK_M
 };
 
-template <int BLOCK_N>
+// CG2: cta_group::2 - a pair of CTAs (one TPC) computes a 256 x BLOCK_N tile; each CTA stages its own 128 rows of A and
+// HALF of the B tile, so per SM the shared-memory traffic (TMA writes + MMA operand reads) drops from ~192 to ~128 B/clk,
+// which is what lifts the kernel off the shared-memory roof.
+template <int BLOCK_N, bool CG2 = false>
 struct SmemCfg {
+  static constexpr int B_ROWS = CG2 ? BLOCK_N / 2 : BLOCK_N;   // rows of the B tile staged by one CTA
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int STAGES = (STAGE_BYTES >= 48 * 1024) ? 4 : 6;
   static constexpr int DYN_BYTES = STAGES * STAGE_BYTES + 1024;
 };
 
@@ -75,11 +80,15 @@ __device__ __forceinline__ float dgelu_erf(float z) {
   return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmKParams p) {
-  using Cfg = SmemCfg<BLOCK_N>;
+  using Cfg = SmemCfg<BLOCK_N, CG2>;
+  constexpr int M_TILE = CG2 ? 2 * BLOCK_M : BLOCK_M;      // rows of C per scheduling unit
+  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs of the pair)
+  const long long unit0 = CG2 ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long unit_stride = CG2 ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
   constexpr int STAGES = Cfg::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 256 or 512: power of two >= 32
 
@@ -109,13 +118,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], CG2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  if (warp == 2) {
+    if constexpr (CG2) tmem_alloc_2cta(&tmem_base_smem, TMEM_COLS); else tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -135,8 +146,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto k_range = [&](int m_blk, int n_blk, int split, int& kb0, int& kb1) {
     kb0 = split * p.kb_per_split;
     kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
-    if (p.causal == 2) kb1 = min(kb1, ((m_blk + 1) * BLOCK_M + BLOCK_K - 1) / BLOCK_K);
-    if (p.causal == 1 && n_blk * BLOCK_N > m_blk * BLOCK_M + BLOCK_M - 1) kb1 = kb0;  // fully masked tile
+    if (p.causal == 2) kb1 = min(kb1, ((m_blk + 1) * M_TILE + BLOCK_K - 1) / BLOCK_K);
+    if (p.causal == 1 && n_blk * BLOCK_N > m_blk * M_TILE + M_TILE - 1) kb1 = kb0;  // fully masked tile
   };
 
   if (warp == 0) {
@@ -144,30 +155,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long w = blockIdx.x; w < p.total_units; w += gridDim.x) {
+      for (long long w = unit0; w < p.total_units; w += unit_stride) {
         int m_blk, n_blk, split, h, b, kb0, kb1;
         decode(w, m_blk, n_blk, split, h, b);
         k_range(m_blk, n_blk, split, kb0, kb1);
-        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        // this CTA's 128 rows of A and its share of the B tile
+        const int m0 = m_blk * M_TILE + (int)rank * BLOCK_M, n0 = n_blk * BLOCK_N + (int)rank * Cfg::B_ROWS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem_gen + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           const int k0 = kb * BLOCK_K;
-          if constexpr (!A_MN) {
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], k0, m0, h, b);
-          } else {
+          if constexpr (!CG2) {
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_4d(sa, &tmap_a, &full_bar[stage], k0, m0, h, b);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_4d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + 64 * j, k0, h, b);
-          }
-          if constexpr (!B_MN) {
-            tma_load_4d(sb, &tmap_b, &full_bar[stage], k0, n0, h, b);
-          } else {
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_4d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + 64 * j, k0, h, b);
+            }
+            if constexpr (!B_MN) {
+              tma_load_4d(sb, &tmap_b, &full_bar[stage], k0, n0, h, b);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_4d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + 64 * j, k0, h, b);
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_4d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + 64 * j, k0, h, b);
+            }
+          } else {
+            // both CTAs' bytes are accounted on the LEADER's full barrier; only the leader arms it
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if constexpr (!A_MN) {
+              tma_load_4d_2cta(sa, &tmap_a, lbar, k0, m0, h, b);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_4d_2cta(sa + j * (BLOCK_K * 128), &tmap_a, lbar, m0 + 64 * j, k0, h, b);
+            }
+            if constexpr (!B_MN) {
+              tma_load_4d_2cta(sb, &tmap_b, lbar, k0, n0, h, b);
+            } else {
+#pragma unroll
+              for (int j = 0; j < Cfg::B_ROWS / 64; ++j)
+                tma_load_4d_2cta(sb + j * (BLOCK_K * 128), &tmap_b, lbar, n0 + 64 * j, k0, h, b);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -175,13 +207,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(M_TILE, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long w = blockIdx.x; w < p.total_units; w += gridDim.x) {
+      for (long long w = unit0; w < p.total_units; w += unit_stride) {
         int m_blk, n_blk, split, h, b, kb0, kb1;
         decode(w, m_blk, n_blk, split, h, b);
         k_range(m_blk, n_blk, split, kb0, kb1);
@@ -202,12 +234,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                         : make_smem_desc_sw128(sa + kk * (UMMA_K * 2), 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + kk * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                         : make_smem_desc_sw128(sb + kk * (UMMA_K * 2), 16, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            if constexpr (CG2) umma_bf16_2cta(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          // smem slot is free (in both CTAs of a pair) once these MMAs retire
+          if constexpr (CG2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CG2) umma_commit_2cta(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -224,14 +259,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool do_gelu = p.flags & PB_GEMM_GELU;
     const bool atomic_acc = p.flags & PB_GEMM_ATOMIC_ACC;
     const bool res_f32 = p.flags & PB_GEMM_RES_F32;
-    for (long long w = blockIdx.x; w < p.total_units; w += gridDim.x) {
+    for (long long w = unit0; w < p.total_units; w += unit_stride) {
       int m_blk, n_blk, split, h, b, kb0, kb1;
       decode(w, m_blk, n_blk, split, h, b);
       k_range(m_blk, n_blk, split, kb0, kb1);
       if (kb1 <= kb0) continue;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const int row = m_blk * M_TILE + (int)rank * BLOCK_M + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const long long c_off = (long long)b * p.c_stride_b + (long long)h * p.c_stride_h + (long long)row * p.ldc;
       const long long r_off = (long long)b * p.r_stride_b + (long long)h * p.r_stride_h +
@@ -412,15 +447,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));  // leader's barrier
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if constexpr (CG2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -509,18 +549,37 @@ static inline int make_tmap(CUtensorMap* out, const void* base, uint64_t inner, 
   return pb_make_tmap_bf16(out, base, inner, rows, ld, nh, stride_h, nb, stride_b, box_inner, box_rows);
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CG2>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, cudaStream_t stream) {
-  using Cfg = SmemCfg<BLOCK_N>;
+  using Cfg = SmemCfg<BLOCK_N, CG2>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CG2>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::DYN_BYTES);
     if (e != cudaSuccess) return pb_set_cuda_error("cudaFuncSetAttribute(gemm_tc)", e);
     attr_set = true;
   }
-  long long grid = kp.total_units < (long long)pb_num_sms() ? kp.total_units : (long long)pb_num_sms();
-  kern<<<(unsigned)grid, NUM_THREADS, Cfg::DYN_BYTES, stream>>>(ta, tb, kp);
+  if constexpr (!CG2) {
+    long long grid = kp.total_units < (long long)pb_num_sms() ? kp.total_units : (long long)pb_num_sms();
+    kern<<<(unsigned)grid, NUM_THREADS, Cfg::DYN_BYTES, stream>>>(ta, tb, kp);
+  } else {
+    // one CTA pair (cluster of 2 = one TPC) per scheduling unit slot
+    const long long pairs_max = pb_num_sms() / 2;
+    const long long pairs = kp.total_units < pairs_max ? kp.total_units : pairs_max;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::DYN_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, kp);
+    if (e != cudaSuccess) return pb_set_cuda_error("cudaLaunchKernelEx(gemm_tc cta_group::2)", e);
+  }
   return pb_check_launch("gemm_tc_kernel");
 }
 
@@ -535,7 +594,12 @@ extern "C" int pb_gemm_bf16(const pb_gemm_desc* d, void* stream_) {
   const int block_n = (d->block_n == 128 || d->block_n == 256) ? d->block_n : (d->N <= 128 ? 128 : 256);
   GemmKParams kp;
   kp.M = d->M; kp.N = d->N; kp.K = d->K;
-  kp.num_m_blocks = (d->M + BLOCK_M - 1) / BLOCK_M;
+  // cta_group::2 (CTA pairs, 256-row tiles): large non-causal problems with the 256-wide N tile
+  static const int cg2_env = getenv("PIANOBART_B200_CG2") ? atoi(getenv("PIANOBART_B200_CG2")) : 1;
+  bool cg2 = d->cta_group == 2 || (d->cta_group == 0 && cg2_env && d->M >= 1024);
+  if (block_n != 256 || d->causal) cg2 = false;
+  const int m_tile = cg2 ? 2 * BLOCK_M : BLOCK_M;
+  kp.num_m_blocks = (d->M + m_tile - 1) / m_tile;
   kp.num_n_blocks = (d->N + block_n - 1) / block_n;
   kp.num_k_blocks = (d->K + BLOCK_K - 1) / BLOCK_K;
   int split = d->split_k > 1 ? d->split_k : 1;
@@ -574,26 +638,33 @@ extern "C" int pb_gemm_bf16(const pb_gemm_desc* d, void* stream_) {
   if (rc) return rc;
   if (!d->b_mn_major)
     rc = make_tmap(&tb, d->b, (uint64_t)d->K, (uint64_t)d->N, d->ldb, nh, d->b_stride_h, nb, d->b_stride_b, 64,
-                   (uint32_t)block_n);
+                   (uint32_t)(cg2 ? block_n / 2 : block_n));
   else
     rc = make_tmap(&tb, d->b, (uint64_t)d->N, (uint64_t)d->K, d->ldb, nh, d->b_stride_h, nb, d->b_stride_b, 64,
                    BLOCK_K);
   if (rc) return rc;
 
   const int variant = (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
-  if (block_n == 256) {
+  if (cg2) {
     switch (variant) {
-      case 0: return launch<256, false, false>(ta, tb, kp, stream);
-      case 1: return launch<256, false, true>(ta, tb, kp, stream);
-      case 2: return launch<256, true, false>(ta, tb, kp, stream);
-      default: return launch<256, true, true>(ta, tb, kp, stream);
+      case 0: return launch<256, false, false, true>(ta, tb, kp, stream);
+      case 1: return launch<256, false, true, true>(ta, tb, kp, stream);
+      case 2: return launch<256, true, false, true>(ta, tb, kp, stream);
+      default: return launch<256, true, true, true>(ta, tb, kp, stream);
+    }
+  } else if (block_n == 256) {
+    switch (variant) {
+      case 0: return launch<256, false, false, false>(ta, tb, kp, stream);
+      case 1: return launch<256, false, true, false>(ta, tb, kp, stream);
+      case 2: return launch<256, true, false, false>(ta, tb, kp, stream);
+      default: return launch<256, true, true, false>(ta, tb, kp, stream);
     }
   } else {
     switch (variant) {
-      case 0: return launch<128, false, false>(ta, tb, kp, stream);
-      case 1: return launch<128, false, true>(ta, tb, kp, stream);
-      case 2: return launch<128, true, false>(ta, tb, kp, stream);
-      default: return launch<128, true, true>(ta, tb, kp, stream);
+      case 0: return launch<128, false, false, false>(ta, tb, kp, stream);
+      case 1: return launch<128, false, true, false>(ta, tb, kp, stream);
+      case 2: return launch<128, true, false, false>(ta, tb, kp, stream);
+      default: return launch<128, true, true, false>(ta, tb, kp, stream);
     }
   }
 }

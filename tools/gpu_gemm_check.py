@@ -13,7 +13,7 @@ fails = 0
 
 
 def run(M, N, K, a_mn=0, b_mn=0, block_n=0, bias=False, gelu=False, res=False, out_f32=False, atomic=False,
-        split_k=1, alpha=1.0, H=1, B=1, causal=0, tag=""):
+        split_k=1, alpha=1.0, H=1, B=1, causal=0, tag="", cg=1):
     global fails
     # logical A [B,H,M,K], Bm [B,H,N,K]
     A = (torch.randn(B, H, M, K, device=dev) * 0.5).bfloat16()
@@ -55,7 +55,7 @@ def run(M, N, K, a_mn=0, b_mn=0, block_n=0, bias=False, gelu=False, res=False, o
     d.r_stride_h = M * N; d.r_stride_b = H * M * N
     d.alpha = alpha
     d.flags = (L.PB_GEMM_OUT_F32 if out_f32 else 0) | (L.PB_GEMM_GELU if gelu else 0) | (L.PB_GEMM_ATOMIC_ACC if atomic else 0)
-    d.split_k = split_k; d.causal = causal; d.block_n = block_n
+    d.split_k = split_k; d.causal = causal; d.block_n = block_n; d.cta_group = cg
     rc = lib.pb_gemm_bf16(C.byref(d), L.stream_ptr())
     if rc != 0:
         print("FAIL launch", tag, lib.pb_last_error().decode()); fails += 1; return
@@ -91,6 +91,13 @@ run(256, 128, 128, H=8, B=2, alpha=0.088388, out_f32=True, tag="batched QK^T-lik
 run(256, 128, 256, b_mn=1, H=8, B=2, tag="batched PV-like (B MN-major)")
 run(1024, 1024, 128, H=2, B=1, out_f32=True, causal=1, tag="causal scores skip")
 run(2048, 3072, 1024, bias=True, tag="QKV proj")
+for a_mn in (0, 1):
+    for b_mn in (0, 1):
+        run(512, 512, 256, a_mn, b_mn, 256, out_f32=True, tag="cta_group::2 layouts", cg=2)
+run(1000, 1280, 1024, bias=True, tag="cg2 M tail + bias", cg=2)
+run(2048, 3072, 1024, bias=True, gelu=True, tag="cg2 bias+gelu", cg=2)
+run(1024, 1024, 2048, bias=True, res=True, tag="cg2 bias+residual", cg=2)
+run(1024, 1024, 4096, a_mn=1, b_mn=1, out_f32=True, atomic=True, split_k=8, tag="cg2 dW split-K atomic", cg=2)
 
 # strided per-head views of a fused QKV activation [B,S,3,H,hd]
 Bz, S, Hh, hd = 2, 256, 8, 128
@@ -113,7 +120,7 @@ print("%s strided fused-QKV heads rel_err=%.3e rc=%d %s" % ("ok  " if rel < 2e-3
 if not (rel < 2e-3 and rc == 0): fails += 1
 
 # throughput
-def bench(M, N, K, a_mn=0, b_mn=0, bn=256, iters=20, split_k=1, atomic=False):
+def bench(M, N, K, a_mn=0, b_mn=0, bn=256, iters=20, split_k=1, atomic=False, cg=1):
     A = torch.randn((K, M) if a_mn else (M, K), device=dev).bfloat16()
     Bm = torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16()
     Cc = torch.zeros(M, N, device=dev, dtype=torch.float32 if atomic else torch.bfloat16)
@@ -122,7 +129,7 @@ def bench(M, N, K, a_mn=0, b_mn=0, bn=256, iters=20, split_k=1, atomic=False):
     d.M, d.N, d.K = M, N, K
     d.a_mn_major, d.b_mn_major = a_mn, b_mn
     d.lda = M if a_mn else K; d.ldb = N if b_mn else K; d.ldc = N
-    d.alpha = 1.0; d.split_k = split_k; d.block_n = bn
+    d.alpha = 1.0; d.split_k = split_k; d.block_n = bn; d.cta_group = cg
     d.flags = (L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC) if atomic else 0
     for _ in range(3): lib.pb_gemm_bf16(C.byref(d), L.stream_ptr())
     torch.cuda.synchronize()
@@ -131,7 +138,7 @@ def bench(M, N, K, a_mn=0, b_mn=0, bn=256, iters=20, split_k=1, atomic=False):
     for _ in range(iters): lib.pb_gemm_bf16(C.byref(d), L.stream_ptr())
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    print("bench M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d split=%d: %.3f ms  %.1f TFLOP/s" % (M, N, K, a_mn, b_mn, bn, split_k, ms, 2.0 * M * N * K / ms / 1e9))
+    print("bench cg=%d M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d split=%d: %.3f ms  %.1f TFLOP/s" % (cg, M, N, K, a_mn, b_mn, bn, split_k, ms, 2.0 * M * N * K / ms / 1e9))
 
 bench(16384, 1024, 1024)
 bench(16384, 1024, 1024, bn=128)
@@ -142,5 +149,13 @@ bench(16384, 1024, 1024, b_mn=1)
 bench(1024, 1024, 16384, a_mn=1, b_mn=1, split_k=5, atomic=True)
 bench(2048, 1024, 16384, a_mn=1, b_mn=1, split_k=2, atomic=True)
 bench(8192, 8192, 8192)
+for cgv in (2,):
+    bench(16384, 1024, 1024, cg=cgv)
+    bench(16384, 3072, 1024, cg=cgv)
+    bench(16384, 2048, 1024, cg=cgv)
+    bench(16384, 1024, 2048, cg=cgv)
+    bench(16384, 1024, 1024, b_mn=1, cg=cgv)
+    bench(2048, 1024, 16384, a_mn=1, b_mn=1, split_k=2, atomic=True, cg=cgv)
+    bench(8192, 8192, 8192, cg=cgv)
 print("FAILS", fails)
 sys.exit(1 if fails else 0)
