@@ -1,0 +1,150 @@
+"""Sequence- / token-classification finetuning, mirroring reference finetune.py (`FinetuneTrainer`, :75-274).
+
+The backbone forward/backward run on the kernel path through the autograd bridge (modules._BackboneFn); the small
+classifier heads and their loss are PyTorch.  Reference behaviour kept: TokenClassification is built
+with class_num+1 (finetune.py:98), velocity (class_num >= 5) feeds shifted labels through the replacement decoder front
+end (:194-198), otherwise decoder ids = encoder ids (:211-212); loss = CE masked by encoder non-pad / sum(mask) for token
+tasks, mean CE for sequence tasks (:125-132); optional L2-norm regulariser (:241-243); NO gradient clipping (:250);
+optimizer: HF-semantics AdamW(lr, weight_decay=0.01) over all parameters.
+"""
+import copy
+import shutil
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .modules import SequenceClassification, TokenClassification
+
+
+class HFAdamW(torch.optim.Optimizer):
+    """transformers 4.29 `AdamW` semantics (eps added before bias correction, decay after the update with plain lr);
+    torch.optim.AdamW differs."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self):
+        for g in self.param_groups:
+            b1, b2 = g['betas']
+            for p in g['params']:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(p)
+                    st['exp_avg_sq'] = torch.zeros_like(p)
+                st['step'] += 1
+                st['exp_avg'].mul_(b1).add_(p.grad, alpha=1 - b1)
+                st['exp_avg_sq'].mul_(b2).addcmul_(p.grad, p.grad, value=1 - b2)
+                denom = st['exp_avg_sq'].sqrt().add_(g['eps'])
+                step_size = g['lr'] * (1 - b2 ** st['step']) ** 0.5 / (1 - b1 ** st['step'])
+                p.addcdiv_(st['exp_avg'], denom, value=-step_size)
+                if g['weight_decay'] > 0:
+                    p.add_(p, alpha=-g['lr'] * g['weight_decay'])
+
+
+class FinetuneTrainer:
+    def __init__(self, pianobart, train_dataloader, valid_dataloader, test_dataloader, lr, class_num, hs, testset_shape,
+                 cpu, cuda_devices=None, model=None, SeqClass=False, error=False, weight=None):
+        if cpu or not torch.cuda.is_available():
+            raise L.PBError('pianobart_b200.FinetuneTrainer has no CPU path (sm_100a kernels only)')
+        dev = 'cuda'
+        if cuda_devices is not None and len(cuda_devices) >= 1:
+            dev += ':' + str(cuda_devices[0])
+        self.device = torch.device(dev)
+        self.pianobart, self.SeqClass, self.class_num = pianobart, SeqClass, class_num
+        if model is not None:
+            self.model = model.to(self.device)
+        elif SeqClass:
+            self.model = SequenceClassification(pianobart, class_num, hs).to(self.device)
+        else:
+            self.model = TokenClassification(pianobart, class_num + 1, hs).to(self.device)
+        self.train_data, self.valid_data, self.test_data = train_dataloader, valid_dataloader, test_dataloader
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        self.optim = HFAdamW(params, lr=lr, weight_decay=0.01)
+        self.loss_func = nn.CrossEntropyLoss(reduction='none')
+        self.testset_shape = testset_shape if not error else (testset_shape[:-1] if testset_shape is not None else None)
+        self.weight, self.error = weight, error
+
+    def compute_loss(self, predict, target, loss_mask, seq):
+        loss = self.loss_func(predict, target)
+        if not seq:
+            loss = loss * loss_mask
+            return torch.sum(loss) / torch.sum(loss_mask)
+        return torch.sum(loss) / loss.shape[0]
+
+    def train(self):
+        self.model.train()
+        return self.iteration(self.train_data, 0, self.SeqClass)
+
+    def valid(self):
+        self.model.eval()
+        return self.iteration(self.valid_data, 1, self.SeqClass)
+
+    def test(self):
+        self.model.eval()
+        return self.iteration(self.test_data, 2, self.SeqClass)
+
+    def step(self, x, y, mode=0):
+        """One batch (finetune.py:168-251).  Returns (loss tensor, #correct, #counted, argmax output)."""
+        seq = self.SeqClass
+        x, y = x.to(self.device).long(), y.to(self.device).long()
+        if self.error:
+            y = torch.squeeze(y, dim=-1)
+        attn = (x[:, :, 0] != self.pianobart.bar_pad_word).float()
+        with torch.set_grad_enabled(mode == 0):
+            if seq:
+                y_hat = self.model(input_ids_encoder=x, encoder_attention_mask=attn)
+            else:
+                if self.class_num >= 5:
+                    y_shift = torch.zeros_like(y) + self.class_num
+                    y_shift[:, 1:] = y[:, :-1]
+                    attn_shift = torch.zeros_like(attn)
+                    attn_shift[:, 1:] = attn[:, :-1]
+                    attn_shift[:, 0] = attn[:, 0]
+                else:
+                    y_shift, attn_shift = x.clone(), attn.clone()
+                y_hat = self.model(input_ids_encoder=x, input_ids_decoder=y_shift, encoder_attention_mask=attn,
+                                   decoder_attention_mask=attn_shift)
+            output = y_hat.argmax(-1)
+            if not seq:
+                correct, count = torch.sum((y == output).float() * attn), torch.sum(attn).item()
+                loss = self.compute_loss(y_hat.permute(0, 2, 1), y, attn, seq)
+            else:
+                correct, count = torch.sum((y == output).float()), y.shape[0]
+                loss = self.compute_loss(y_hat, y, attn, seq)
+            if self.weight is not None:
+                for param in self.model.parameters():
+                    loss = loss + self.weight * torch.norm(param, p=2)
+            if mode == 0:
+                self.model.zero_grad()
+                loss.backward()          # no clipping in the reference (finetune.py:250)
+                self.optim.step()
+        return loss.detach(), correct, count, output
+
+    def iteration(self, training_data, mode, seq):
+        total_acc, total_cnt, total_loss, nb = 0.0, 0, 0.0, 0
+        all_output, cnt = (torch.empty(self.testset_shape), 0) if mode == 2 else (None, 0)
+        for x, y in training_data:
+            loss, correct, count, output = self.step(x, y, mode)
+            if mode == 2:
+                all_output[cnt:cnt + x.shape[0]] = output.cpu()
+                cnt += x.shape[0]
+            total_loss += loss.item()
+            total_acc += float(correct)
+            total_cnt += count
+            nb += 1
+        res = (round(total_loss / max(nb, 1), 4), round(total_acc / max(total_cnt, 1), 4))
+        return res + (all_output,) if mode == 2 else res
+
+    def save_checkpoint(self, epoch, train_acc, valid_acc, valid_loss, train_loss, is_best, filename):
+        state = {'epoch': epoch + 1, 'state_dict': {k: v.detach().clone() for k, v in self.model.state_dict().items()},
+                 'valid_acc': valid_acc, 'valid_loss': valid_loss, 'train_loss': train_loss, 'train_acc': train_acc,
+                 'optimizer': self.optim.state_dict()}
+        torch.save(state, filename)
+        if is_best:
+            shutil.copyfile(filename, filename.split('.')[0] + '_best.ckpt')
