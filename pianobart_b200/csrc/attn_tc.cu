@@ -99,6 +99,20 @@ __device__ __forceinline__ uint32_t chunk_mask(uint32_t keep_word, bool causal, 
   if (lim >= 31) return keep_word;
   return keep_word & ((2u << lim) - 1u);
 }
+// key-padding flag of key kc (thread tid < 128 owns key kg0 + tid of a block): loaded one block ahead so the global
+// load latency is off the critical path
+__device__ __forceinline__ bool load_keep(const AttnParams& p, int b, int kc, int tid) {
+  if (tid >= AT) return false;
+  bool kp = kc < p.Sk;
+  if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc] != 0;
+  return kp;
+}
+__device__ __forceinline__ void publish_keep_bits(uint32_t* s_bits, bool kp, int tid) {
+  if (tid < AT) {
+    const uint32_t w = __ballot_sync(0xffffffffu, kp);
+    if ((tid & 31) == 0) s_bits[tid >> 5] = w;
+  }
+}
 // compute threads 0..127 publish the key-padding bitmap of key block kg0 as four 32-bit words
 __device__ __forceinline__ void build_keep_bits(uint32_t* s_bits, const AttnParams& p, int b, int kg0, int tid) {
   if (tid < AT) {
@@ -118,16 +132,22 @@ __device__ __forceinline__ void carve(uint8_t* raw, Smem4& s, int n) {
 }
 
 // ===================================================================================== forward
+// Software-pipelined: the MMA warp issues S(j+1) = Q K(j+1)^T (second TMEM buffer, double-buffered K/V tiles) while
+// the softmax warps work on S(j); the output accumulates in TMEM across key blocks (O += P V) and is only rescaled
+// when the running row maximum grows by more than 2^8 ("lazy rescale"), so the per-block critical path of the softmax
+// warps is  ld S -> max -> exp2 -> P to smem -> arrive  with no accumulator round trip.
+constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 domain: probabilities stay <= 256 between rescales
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                 const __grid_constant__ CUtensorMap tv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, k_full, v_full, k_empty, v_empty, s_full, p_full, o_full;
+  __shared__ __align__(8) uint64_t q_full, k_full[2], v_full[2], k_empty[2], v_empty[2], s_full[2], p_full, pv_done;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t s_bits[4];
+  __shared__ uint32_t s_bits2[2][4];
   __shared__ float s_red[2][AT];
   Smem4 sm;
-  carve(smem_raw, sm, 4);  // 0 Q, 1 K, 2 V, 3 P
+  carve(smem_raw, sm, 6);  // 0 Q, 1-2 K ring, 3-4 V ring, 5 P
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * AT;
@@ -136,45 +156,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); }
   if (warp == 1 && lane == 0) {
-    mbar_init(&q_full, 1); mbar_init(&k_full, 1); mbar_init(&v_full, 1); mbar_init(&k_empty, 1); mbar_init(&v_empty, 1);
-    mbar_init(&s_full, 1); mbar_init(&p_full, NCOMPUTE); mbar_init(&o_full, 1);
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(&p_full, NCOMPUTE); mbar_init(&pv_done, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
-  const uint32_t tS = tmem, tO = tmem + 128;
+  const uint32_t tS0 = tmem, tO = tmem + 256;   // S buffers at columns 0 and 128, O at 256
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(&q_full, TILE_BYTES);
       load_tile(sm.t[0], &tq, &q_full, q0, h, b);
       for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&k_empty, (j & 1) ^ 1);
-        mbar_expect_tx(&k_full, TILE_BYTES);
-        load_tile(sm.t[1], &tk, &k_full, j * AT, h, b);
-        mbar_wait(&v_empty, (j & 1) ^ 1);
-        mbar_expect_tx(&v_full, TILE_BYTES);
-        load_tile(sm.t[2], &tv, &v_full, j * AT, h, b);
+        const int st = j & 1;
+        const uint32_t n = (uint32_t)(j >> 1);
+        mbar_wait(&k_empty[st], (n & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], TILE_BYTES);
+        load_tile(sm.t[1 + st], &tk, &k_full[st], j * AT, h, b);
+        mbar_wait(&v_empty[st], (n & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], TILE_BYTES);
+        load_tile(sm.t[3 + st], &tv, &v_full[st], j * AT, h, b);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       mbar_wait(&q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      mma_tile<false, false>(tS0, sm.a[0], sm.a[1], false);                  // S(0) = Q K(0)^T
+      umma_commit(&s_full[0]);
+      umma_commit(&k_empty[0]);
       for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&k_full, j & 1);
-        tc_fence_after();
-        mma_tile<false, false>(tS, sm.a[0], sm.a[1], false);      // S = Q K^T
-        umma_commit(&s_full);
-        umma_commit(&k_empty);
+        if (j + 1 < nkb) {
+          const int st = (j + 1) & 1;
+          mbar_wait(&k_full[st], (uint32_t)((j + 1) >> 1) & 1);
+          tc_fence_after();
+          // buffer st was last read by the softmax of block j-1, which finished before p_full(j-1) fired
+          mma_tile<false, false>(tS0 + st * 128, sm.a[0], sm.a[1 + st], false);   // S(j+1), overlaps softmax(j)
+          umma_commit(&s_full[st]);
+          umma_commit(&k_empty[st]);
+        }
         mbar_wait(&p_full, j & 1);
-        mbar_wait(&v_full, j & 1);
+        mbar_wait(&v_full[j & 1], (uint32_t)(j >> 1) & 1);
         tc_fence_after();
-        mma_tile<false, true>(tO, sm.a[3], sm.a[2], false);       // O_part = P V   (V as MN-major B)
-        umma_commit(&o_full);
-        umma_commit(&v_empty);
+        mma_tile<false, true>(tO, sm.a[5], sm.a[3 + (j & 1)], j > 0);        // O += P V   (V as MN-major B)
+        umma_commit(&pv_done);
+        umma_commit(&v_empty[j & 1]);
       }
     }
   } else {
@@ -186,88 +221,118 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     const int qg = q0 + r;                   // global query index
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float sl2 = p.scale * LOG2E;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f;
+    float m_used = -INFINITY, l = 0.f;       // scaling reference of the accumulator / partial row sum of this half
+    // key-padding bitmaps are published one block ahead: bits of block j+1 ride on the barrier of block j
+    publish_keep_bits(s_bits2[0], load_keep(p, b, tid, tid), tid);
+    bool kp_next = load_keep(p, b, AT + tid, tid);
+    compute_bar_sync();
     for (int j = 0; j < nkb; ++j) {
       const int kg0 = j * AT;
-      build_keep_bits(s_bits, p, b, kg0, tid);
-      compute_bar_sync();
       uint32_t msk[2];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) msk[c] = chunk_mask(s_bits[hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32);
-      mbar_wait(&s_full, j & 1);
+      for (int c = 0; c < 2; ++c) msk[c] = chunk_mask(s_bits2[j & 1][hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32);
+      mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
+      const uint32_t tS = tS0 + (j & 1) * 128;
       float t[64];
       float bm = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_addr + hf * 64 + c * 32, v);
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tS + lane_addr + hf * 64, v0);
+        tmem_ld32(tS + lane_addr + hf * 64 + 32, v1);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float x = ((msk[c] >> i) & 1u) ? __uint_as_float(v[i]) * sl2 : -INFINITY;
-          t[c * 32 + i] = x;
-          bm = fmaxf(bm, x);
+          const float x0 = ((msk[0] >> i) & 1u) ? __uint_as_float(v0[i]) * sl2 : -INFINITY;
+          const float x1 = ((msk[1] >> i) & 1u) ? __uint_as_float(v1[i]) * sl2 : -INFINITY;
+          t[i] = x0;
+          t[32 + i] = x1;
+          bm = fmaxf(bm, fmaxf(x0, x1));
         }
       }
       s_red[hf][r] = bm;
+      publish_keep_bits(s_bits2[(j + 1) & 1], kp_next, tid);
+      kp_next = load_keep(p, b, (j + 2) * AT + tid, tid);
       compute_bar_sync();
-      const float m_new = fmaxf(m, fmaxf(s_red[0][r], s_red[1][r]));
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m == -INFINITY) ? 0.f : ex2(m - m_use);
+      bm = fmaxf(s_red[0][r], s_red[1][r]);
+      // lazy rescale: keep the old reference unless the maximum grew by more than 2^8
+      float f = 1.0f;
+      bool need = false;
+      if (m_used == -INFINITY) {
+        m_used = bm;                                      // nothing non-zero accumulated so far
+      } else if (bm > m_used + RESCALE_THRESHOLD) {
+        f = ex2(m_used - bm);
+        m_used = bm;
+        need = true;
+      }
+      bool waited_pv = false;
+      if (__any_sync(0xffffffffu, need)) {
+        mbar_wait(&pv_done, (j - 1) & 1);                 // j > 0 here: the previous P V must have landed in O
+        waited_pv = true;
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tO + lane_addr + hf * 64 + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          tmem_st32(tO + lane_addr + hf * 64 + c * 32, v);
+        }
+        tmem_st_wait();
+        l *= f;
+      }
+      const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
       float rs = 0.f;
+      float x[2][32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           // masked entries are -inf -> ex2 gives 0; the row sum uses the bf16-rounded value the tensor core sees
-          x[i] = __bfloat162float(__float2bfloat16(ex2(t[c * 32 + i] - m_use)));
-          rs += x[i];
+          x[c][i] = __bfloat162float(__float2bfloat16(ex2(t[c * 32 + i] - m_safe)));
+          rs += x[c][i];
         }
-        store_chunk(sm.t[3], r, hf * 64 + c * 32, x);
       }
-      l = l * alpha + rs;
-      m = m_new;
+      l += rs;
+      if (j > 0 && !waited_pv) mbar_wait(&pv_done, (j - 1) & 1);   // P buffer is free once P V (j-1) retired
+#pragma unroll
+      for (int c = 0; c < 2; ++c) store_chunk(sm.t[5], r, hf * 64 + c * 32, x[c]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full);
-      mbar_wait(&o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tO + lane_addr + hf * 64 + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
     }
+    mbar_wait(&pv_done, (nkb - 1) & 1);
+    tc_fence_after();
     compute_bar_sync();
     s_red[hf][r] = l;
     compute_bar_sync();
     l = s_red[0][r] + s_red[1][r];
-    if (qg < p.Sq) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      __nv_bfloat16* orow = p.o + (long long)b * p.o_sb + (long long)qg * p.ldo + h * AT + hf * 64;
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat16* orow = p.o + (long long)b * p.o_sb + (long long)qg * p.ldo + h * AT + hf * 64;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 v;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_addr + hf * 64 + c * 32, v);
+      tmem_ld_wait();
+      if (qg < p.Sq) {
 #pragma unroll
-        for (int tt = 0; tt < 4; ++tt) h2[tt] = __floats2bfloat162_rn(o[g * 8 + 2 * tt] * inv, o[g * 8 + 2 * tt + 1] * inv);
-        *reinterpret_cast<uint4*>(orow + g * 8) = v;
+        for (int g = 0; g < 4; ++g) {
+          uint4 o4;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o4);
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt)
+            h2[tt] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * tt]) * inv, __uint_as_float(v[g * 8 + 2 * tt + 1]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o4;
+        }
       }
-      if (hf == 0) p.lse[((long long)b * p.H + h) * p.Sq + qg] = (l > 0.f) ? (m + log2f(l)) : INFINITY;
     }
+    if (qg < p.Sq && hf == 0) p.lse[((long long)b * p.H + h) * p.Sq + qg] = (l > 0.f) ? (m_used + log2f(l)) : INFINITY;
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 256);
+  if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
 // ===================================================================================== backward: dK, dV
@@ -418,7 +483,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t qdo_full, kv_full, kv_empty, sdp_full, ds_full, acc_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t s_bits[4];
+  __shared__ uint32_t s_bits2[2][4];
   __shared__ float s_red[2][AT];
   Smem4 sm;
   carve(smem_raw, sm, 5);  // 0 Q, 1 dO, 2 K, 3 V, 4 dS
@@ -482,15 +547,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const long long ridx = ((long long)b * p.H + h) * p.Sq + qg;
     const float L = qok ? p.lse[ridx] : INFINITY;
     const float Dv = qok ? p.dvec[ridx] : 0.f;
+    publish_keep_bits(s_bits2[0], load_keep(p, b, tid, tid), tid);
+    bool kp_next = load_keep(p, b, AT + tid, tid);
     for (int j = 0; j < nkb; ++j) {
       const int kg0 = j * AT;
-      compute_bar_sync();                    // everyone finished reading the previous block's bitmap
-      build_keep_bits(s_bits, p, b, kg0, tid);
+      // one barrier per block: publishes bits(j) (written before it) and orders the reuse of the other buffer
       compute_bar_sync();
       uint32_t msk[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c)
-        msk[c] = qok ? chunk_mask(s_bits[hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32) : 0u;
+        msk[c] = qok ? chunk_mask(s_bits2[j & 1][hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32) : 0u;
+      publish_keep_bits(s_bits2[(j + 1) & 1], kp_next, tid);
+      kp_next = load_keep(p, b, (j + 2) * AT + tid, tid);
       mbar_wait(&sdp_full, j & 1);
       tc_fence_after();
 #pragma unroll
@@ -608,7 +676,7 @@ extern "C" int pb_attn_fwd(const pb_attn_desc* d, void* stream_) {
   AttnParams p;
   fill_params(p, d);
   static bool attr = false;
-  const int smem = 4 * TILE_BYTES + 1024;
+  const int smem = 6 * TILE_BYTES + 1024;
   if (set_smem(attn_fwd_kernel, smem, attr)) return -1;
   dim3 grid((d->Sq + AT - 1) / AT, d->H, d->B);
   attn_fwd_kernel<<<grid, NTHREADS, smem, stream>>>(tq, tk, tv, p);
