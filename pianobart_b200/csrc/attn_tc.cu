@@ -477,26 +477,39 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 }
 
 // ===================================================================================== backward: dQ
+// 64-key blocks, K/V tiles and the S / dP accumulators double-buffered: the MMA warp computes S, dP of block j+1 while
+// the softmax warps turn block j into dS, and TMA streams block j+2 - the three engines overlap instead of taking turns.
+constexpr int KB = 64;                          // keys per block in this kernel
+constexpr int KV_TILE_BYTES = KB * AT * 2;      // 16 KB: [64 keys x 128 head dims] as two 64-column halves of 8 KB
+constexpr int DS_TILE_BYTES = AT * KB * 2;      // 16 KB: [128 queries x 64 keys], one 128-byte row per query
+constexpr int NKV = 3;                          // K/V ring depth: a slot is released by the dQ MMA of block j and must
+                                                // be refilled before S/dP of block j+NKV-1 is issued -> 3 gives a full block of slack
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t qdo_full, kv_full, kv_empty, sdp_full, ds_full, acc_full;
+  __shared__ __align__(8) uint64_t qdo_full, kv_full[NKV], kv_empty[NKV], sdp_full[2], ds_full[2], dq_done[2], acc_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t s_bits2[2][4];
-  __shared__ float s_red[2][AT];
-  Smem4 sm;
-  carve(smem_raw, sm, 5);  // 0 Q, 1 dO, 2 K, 3 V, 4 dS
+  __shared__ uint32_t s_bits2[2][2];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // layout: Q 32K | dO 32K | K ring NKV x 16K | V ring NKV x 16K | dS0 16K | dS1 16K
+  const uint32_t aQ = base, adO = base + TILE_BYTES, aK = base + 2 * TILE_BYTES, aV = aK + NKV * KV_TILE_BYTES,
+                 adS = aV + NKV * KV_TILE_BYTES;
+  uint8_t* gQ = gen; uint8_t* gdO = gen + TILE_BYTES; uint8_t* gK = gen + 2 * TILE_BYTES; uint8_t* gV = gK + NKV * KV_TILE_BYTES;
+  uint8_t* gdS = gV + NKV * KV_TILE_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * AT;
-  int nkb = (p.Sk + AT - 1) / AT;
-  if (p.causal) nkb = min(nkb, qb + 1);
+  int nkb = (p.Sk + KB - 1) / KB;
+  if (p.causal) nkb = min(nkb, (q0 + AT + KB - 1) / KB);   // key blocks that intersect keys <= last query of the tile
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); }
   if (warp == 1 && lane == 0) {
-    mbar_init(&qdo_full, 1); mbar_init(&kv_full, 1); mbar_init(&kv_empty, 1); mbar_init(&sdp_full, 1);
-    mbar_init(&ds_full, NCOMPUTE); mbar_init(&acc_full, 1);
+    mbar_init(&qdo_full, 1); mbar_init(&acc_full, 1);
+    for (int i = 0; i < NKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&ds_full[i], NCOMPUTE); mbar_init(&dq_done[i], 1); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -504,40 +517,77 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+  // TMEM columns: S[2] at 0/64, dP[2] at 128/192, dQ at 256
+  const uint32_t tS0 = tmem, tdP0 = tmem + 128, tdQ = tmem + 256;
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(&qdo_full, 2 * TILE_BYTES);
-      load_tile(sm.t[0], &tq, &qdo_full, q0, h, b);
-      load_tile(sm.t[1], &tdo, &qdo_full, q0, h, b);
+      load_tile(gQ, &tq, &qdo_full, q0, h, b);
+      load_tile(gdO, &tdo, &qdo_full, q0, h, b);
       for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&kv_empty, (j & 1) ^ 1);
-        mbar_expect_tx(&kv_full, 2 * TILE_BYTES);
-        load_tile(sm.t[2], &tk, &kv_full, j * AT, h, b);
-        load_tile(sm.t[3], &tv, &kv_full, j * AT, h, b);
+        const int st = j % NKV;
+        mbar_wait(&kv_empty[st], ((uint32_t)(j / NKV) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * KV_TILE_BYTES);
+        // the K/V tensor maps use 128-row boxes; a 64-key block is loaded as two (64 col x 64 row) halves per tensor:
+        // rows beyond the block are simply not requested (box rows fixed at 128 would over-read) -> use the kv64 maps
+        tma_load_4d(gK + st * KV_TILE_BYTES, &tk, &kv_full[st], 0, j * KB, h, b);
+        tma_load_4d(gK + st * KV_TILE_BYTES + KV_TILE_BYTES / 2, &tk, &kv_full[st], 64, j * KB, h, b);
+        tma_load_4d(gV + st * KV_TILE_BYTES, &tv, &kv_full[st], 0, j * KB, h, b);
+        tma_load_4d(gV + st * KV_TILE_BYTES + KV_TILE_BYTES / 2, &tv, &kv_full[st], 64, j * KB, h, b);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(AT, KB, 0, 0);     // [128 q x 64 keys], both operands K-major
+      constexpr uint32_t idesc_q = make_idesc_bf16(AT, AT, 0, 1);     // dQ [128 q x 128 hd], B = K tile MN-major
+      auto issue_sdp = [&](int j) {
+        const int st = j & 1;                       // TMEM buffer
+        const int ks = j % NKV;                     // K/V ring slot
+        const uint32_t kt = aK + ks * KV_TILE_BYTES, vt = aV + ks * KV_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {   // contraction over head_dim: 16 columns per step, halves 16 KB (Q/dO) / 8 KB (K/V) apart
+          const uint64_t qd = make_smem_desc_sw128(aQ + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t kd = make_smem_desc_sw128(kt + (kk >> 2) * (KV_TILE_BYTES / 2) + (kk & 3) * 32, 16, 1024);
+          umma_bf16(tS0 + st * KB, qd, kd, idesc_s, kk > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t od = make_smem_desc_sw128(adO + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t vd = make_smem_desc_sw128(vt + (kk >> 2) * (KV_TILE_BYTES / 2) + (kk & 3) * 32, 16, 1024);
+          umma_bf16(tdP0 + st * KB, od, vd, idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&sdp_full[st]);
+      };
       mbar_wait(&qdo_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_sdp(0);
       for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&kv_full, j & 1);
+        const int st = j & 1;
+        if (j + 1 < nkb) {
+          mbar_wait(&kv_full[(j + 1) % NKV], (uint32_t)((j + 1) / NKV) & 1);
+          tc_fence_after();
+          issue_sdp(j + 1);              // its TMEM buffers were drained before ds_full(j-1) fired
+        }
+        mbar_wait(&ds_full[st], (uint32_t)(j >> 1) & 1);
         tc_fence_after();
-        mma_tile<false, false>(tS, sm.a[0], sm.a[2], false);    // S  = Q K^T
-        mma_tile<false, false>(tdP, sm.a[1], sm.a[3], false);   // dP = dO V^T
-        umma_commit(&sdp_full);
-        mbar_wait(&ds_full, j & 1);
-        tc_fence_after();
-        mma_tile<false, true>(tdQ, sm.a[4], sm.a[2], j > 0);    // dQ += dS K   (K as MN-major B)
-        umma_commit(&kv_empty);
+        const uint32_t dst = adS + st * DS_TILE_BYTES, kt = aK + (j % NKV) * KV_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {   // contraction over the 64 keys of the block
+          const uint64_t ad = make_smem_desc_sw128(dst + kk * 32, 16, 1024);                          // dS: K-major
+          const uint64_t bd = make_smem_desc_sw128(kt + kk * 2048, KV_TILE_BYTES / 2, 1024);          // K: MN-major
+          umma_bf16(tdQ, ad, bd, idesc_q, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&dq_done[st]);       // dS buffer st reusable
+        umma_commit(&kv_empty[j % NKV]); // K/V ring slot reusable
       }
       umma_commit(&acc_full);
     }
   } else {
     const int cw = warp - 2;
     const int quad = warp & 3;
-    const int hf = cw >> 2;
+    const int hf = cw >> 2;                  // 32-column half of the 64-key block
     const int r = quad * 32 + lane;
     const int tid = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -547,45 +597,61 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const long long ridx = ((long long)b * p.H + h) * p.Sq + qg;
     const float L = qok ? p.lse[ridx] : INFINITY;
     const float Dv = qok ? p.dvec[ridx] : 0.f;
-    publish_keep_bits(s_bits2[0], load_keep(p, b, tid, tid), tid);
-    bool kp_next = load_keep(p, b, AT + tid, tid);
+    auto keep_of = [&](int kc) {
+      bool kp = kc < p.Sk;
+      if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc] != 0;
+      return kp;
+    };
+    auto publish = [&](uint32_t* dst, bool kp) {
+      if (tid < KB) {
+        const uint32_t w = __ballot_sync(0xffffffffu, kp);
+        if ((tid & 31) == 0) dst[tid >> 5] = w;
+      }
+    };
+    bool kp_next = false;
+    if (tid < KB) { publish(s_bits2[0], keep_of(tid)); kp_next = keep_of(KB + tid); }
     for (int j = 0; j < nkb; ++j) {
-      const int kg0 = j * AT;
-      // one barrier per block: publishes bits(j) (written before it) and orders the reuse of the other buffer
-      compute_bar_sync();
-      uint32_t msk[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-        msk[c] = qok ? chunk_mask(s_bits2[j & 1][hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32) : 0u;
-      publish_keep_bits(s_bits2[(j + 1) & 1], kp_next, tid);
-      kp_next = load_keep(p, b, (j + 2) * AT + tid, tid);
-      mbar_wait(&sdp_full, j & 1);
+      const int kg0 = j * KB, st = j & 1;
+      compute_bar_sync();                    // publishes bits(j); orders reuse of the other bitmap buffer
+      const uint32_t msk = qok ? chunk_mask(s_bits2[st][hf], p.causal != 0, qg, kg0 + hf * 32) : 0u;
+      if (tid < KB) { publish(s_bits2[st ^ 1], kp_next); kp_next = keep_of((j + 2) * KB + tid); }
+      mbar_wait(&sdp_full[st], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
+      uint32_t sv[32], dv[32];
+      tmem_ld32(tS0 + st * KB + lane_addr + hf * 32, sv);
+      tmem_ld32(tdP0 + st * KB + lane_addr + hf * 32, dv);
+      tmem_ld_wait();
+      float ds[32];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tS + lane_addr + hf * 64 + c * 32, sv);
-        tmem_ld32(tdP + lane_addr + hf * 64 + c * 32, dv);
-        tmem_ld_wait();
-        float ds[32];
+      for (int i = 0; i < 32; ++i) {
+        const float pv = ((msk >> i) & 1u) ? ex2(__uint_as_float(sv[i]) * sl2 - L) : 0.f;
+        ds[i] = pv * (__uint_as_float(dv[i]) - Dv) * p.scale;
+      }
+      if (j >= 2) mbar_wait(&dq_done[st], (uint32_t)((j - 2) >> 1) & 1);   // dQ MMA of block j-2 released this buffer
+      {
+        // row r of the [128 x 64] dS tile: 128 bytes, 16-byte chunks XOR-swizzled by (r & 7)
+        uint8_t* rowp = gdS + st * DS_TILE_BYTES + r * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pv = ((msk[c] >> i) & 1u) ? ex2(__uint_as_float(sv[i]) * sl2 - L) : 0.f;
-          ds[i] = pv * (__uint_as_float(dv[i]) - Dv) * p.scale;
+        for (int g = 0; g < 4; ++g) {
+          uint4 v4;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v4);
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) h2[tt] = __floats2bfloat162_rn(ds[g * 8 + 2 * tt], ds[g * 8 + 2 * tt + 1]);
+          *reinterpret_cast<uint4*>(rowp + (((hf * 4 + g) ^ (r & 7)) << 4)) = v4;
         }
-        store_chunk(sm.t[4], r, hf * 64 + c * 32, ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&ds_full);
+      mbar_arrive(&ds_full[st]);
     }
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    __nv_bfloat16* dst = p.dq + (long long)b * p.dq_sb + (long long)qg * p.lddq + h * AT + hf * 64;
+    const int hq = cw >> 2;                  // 64-column half of head_dim written by this thread
+    __nv_bfloat16* dst = p.dq + (long long)b * p.dq_sb + (long long)qg * p.lddq + h * AT + hq * 64;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(tdQ + lane_addr + hf * 64 + c * 32, v);
+      tmem_ld32(tdQ + lane_addr + hq * 64 + c * 32, v);
       tmem_ld_wait();
       if (qok) {
 #pragma unroll
@@ -645,8 +711,8 @@ static int set_smem(K kern, int bytes, bool& done) {
 
 using namespace pb;
 
-static int attn_tmap(CUtensorMap* m, const void* ptr, int S, long long ld, int H, int B, long long sb) {
-  return pb_make_tmap_bf16(m, ptr, AT, (uint64_t)S, ld, H, AT, B, sb, 64, AT);
+static int attn_tmap(CUtensorMap* m, const void* ptr, int S, long long ld, int H, int B, long long sb, int box_rows = AT) {
+  return pb_make_tmap_bf16(m, ptr, AT, (uint64_t)S, ld, H, AT, B, sb, 64, (uint32_t)box_rows);
 }
 
 static int attn_check(const pb_attn_desc* d) {
@@ -701,13 +767,16 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
     if (pb_check_launch("attn_bwd_prep_kernel")) return -1;
   }
   static bool attr1 = false, attr2 = false;
-  const int smem1 = 6 * TILE_BYTES + 1024, smem2 = 5 * TILE_BYTES + 1024;
+  const int smem1 = 6 * TILE_BYTES + 1024, smem2 = 2 * TILE_BYTES + 2 * NKV * KV_TILE_BYTES + 2 * DS_TILE_BYTES + 1024;
   if (set_smem(attn_bwd_dkv_kernel, smem1, attr1)) return -1;
   if (set_smem(attn_bwd_dq_kernel, smem2, attr2)) return -1;
   dim3 g1((d->Sk + AT - 1) / AT, d->H, d->B);
   attn_bwd_dkv_kernel<<<g1, NTHREADS, smem1, stream>>>(tq, tk, tv, tdo, p);
   if (pb_check_launch("attn_bwd_dkv_kernel")) return -1;
+  CUtensorMap tk64, tv64;   // 64-key boxes for the dQ kernel
+  if (attn_tmap(&tk64, d->k, d->Sk, d->ldk, d->H, d->B, (long long)d->Sk * d->ldk, KB)) return -1;
+  if (attn_tmap(&tv64, d->v, d->Sk, d->ldv, d->H, d->B, (long long)d->Sk * d->ldv, KB)) return -1;
   dim3 g2((d->Sq + AT - 1) / AT, d->H, d->B);
-  attn_bwd_dq_kernel<<<g2, NTHREADS, smem2, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_dq_kernel<<<g2, NTHREADS, smem2, stream>>>(tq, tk64, tv64, tdo, p);
   return pb_check_launch("attn_bwd_dq_kernel");
 }
