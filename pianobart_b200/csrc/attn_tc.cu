@@ -336,27 +336,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 }
 
 // ===================================================================================== backward: dK, dV
+// Transposed formulation so that 64-query blocks keep every MMA at M = 128:  S^T = K Q^T and dP^T = V dO^T are
+// [128 keys x 64 queries] (TMEM lane = key), P^T / dS^T go to shared memory K-major and feed dV += P^T dO, dK += dS^T Q
+// with the 64-row Q / dO tiles as MN-major B operands.  Q/dO stream through a 3-deep ring, S^T/dP^T and P^T/dS^T are
+// double-buffered: TMA, the tensor pipe and the softmax warps overlap instead of taking turns (the v1 kernel spent 43%
+// of its samples waiting on the S/dP barrier, profiles/r1_summary.md).
+constexpr int QB = 64;                          // queries per block in this kernel
+constexpr int QT_BYTES = QB * AT * 2;           // 16 KB: [64 queries x 128 head dims], two 64-column halves of 8 KB
+constexpr int PT_BYTES = AT * QB * 2;           // 16 KB: [128 keys x 64 queries], one 128-byte row per key
+constexpr int NQ = 3;                           // Q/dO ring depth
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                     const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t kv_full, qdo_full, qdo_empty, sdp_full, pds_full, acc_full;
+  __shared__ __align__(8) uint64_t kv_full, qdo_full[NQ], qdo_empty[NQ], sdp_full[2], pds_full[2], pds_done[2], acc_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t s_bits[4];
-  __shared__ float s_red[2][AT];
-  Smem4 sm;
-  carve(smem_raw, sm, 6);  // 0 K, 1 V, 2 Q, 3 dO, 4 P, 5 dS
+  __shared__ __align__(16) float s_L[2][QB], s_D[2][QB];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // layout: K 32K | V 32K | Q ring NQ x 16K | dO ring NQ x 16K | P^T[2] 16K each | dS^T[2] 16K each
+  const uint32_t aK = base, aV = base + TILE_BYTES, aQ = base + 2 * TILE_BYTES, adO = aQ + NQ * QT_BYTES,
+                 aP = adO + NQ * QT_BYTES, adS = aP + 2 * PT_BYTES;
+  uint8_t* gK = gen; uint8_t* gV = gen + TILE_BYTES; uint8_t* gQ = gen + 2 * TILE_BYTES; uint8_t* gdO = gQ + NQ * QT_BYTES;
+  uint8_t* gP = gdO + NQ * QT_BYTES; uint8_t* gdS = gP + 2 * PT_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int k0 = kb * AT;
-  const int nqb = (p.Sq + AT - 1) / AT;
-  const int qb0 = p.causal ? kb : 0;       // causal: only query blocks at or below the diagonal see these keys
+  const int nqb = (p.Sq + QB - 1) / QB;
+  const int qb0 = p.causal ? (k0 / QB) : 0;   // causal: first 64-query block that can see key k0
   const int niter = nqb - qb0;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); }
   if (warp == 1 && lane == 0) {
-    mbar_init(&kv_full, 1); mbar_init(&qdo_full, 1); mbar_init(&qdo_empty, 1); mbar_init(&sdp_full, 1);
-    mbar_init(&pds_full, NCOMPUTE); mbar_init(&acc_full, 1);
+    mbar_init(&kv_full, 1); mbar_init(&acc_full, 1);
+    for (int i = 0; i < NQ; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&pds_full[i], NCOMPUTE); mbar_init(&pds_done[i], 1); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -364,88 +379,163 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 384;
+  // TMEM columns: S^T[2] at 0/64, dP^T[2] at 128/192, dV at 256, dK at 384
+  const uint32_t tS0 = tmem, tdP0 = tmem + 128, tdV = tmem + 256, tdK = tmem + 384;
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(&kv_full, 2 * TILE_BYTES);
-      load_tile(sm.t[0], &tk, &kv_full, k0, h, b);
-      load_tile(sm.t[1], &tv, &kv_full, k0, h, b);
+      load_tile(gK, &tk, &kv_full, k0, h, b);
+      load_tile(gV, &tv, &kv_full, k0, h, b);
       for (int it = 0; it < niter; ++it) {
-        mbar_wait(&qdo_empty, (it & 1) ^ 1);
-        mbar_expect_tx(&qdo_full, 2 * TILE_BYTES);
-        load_tile(sm.t[2], &tq, &qdo_full, (qb0 + it) * AT, h, b);
-        load_tile(sm.t[3], &tdo, &qdo_full, (qb0 + it) * AT, h, b);
+        const int st = it % NQ;
+        const int q0 = (qb0 + it) * QB;
+        mbar_wait(&qdo_empty[st], ((uint32_t)(it / NQ) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[st], 2 * QT_BYTES);
+        tma_load_4d(gQ + st * QT_BYTES, &tq, &qdo_full[st], 0, q0, h, b);
+        tma_load_4d(gQ + st * QT_BYTES + QT_BYTES / 2, &tq, &qdo_full[st], 64, q0, h, b);
+        tma_load_4d(gdO + st * QT_BYTES, &tdo, &qdo_full[st], 0, q0, h, b);
+        tma_load_4d(gdO + st * QT_BYTES + QT_BYTES / 2, &tdo, &qdo_full[st], 64, q0, h, b);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(AT, QB, 0, 0);     // [128 keys x 64 q], both operands K-major
+      constexpr uint32_t idesc_a = make_idesc_bf16(AT, AT, 0, 1);     // [128 keys x 128 hd], B = Q / dO tile MN-major
+      auto issue_sdp = [&](int it) {
+        const int st = it & 1;
+        const uint32_t qt = aQ + (it % NQ) * QT_BYTES, ot = adO + (it % NQ) * QT_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {   // contraction over head_dim
+          const uint64_t kd = make_smem_desc_sw128(aK + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t qd = make_smem_desc_sw128(qt + (kk >> 2) * (QT_BYTES / 2) + (kk & 3) * 32, 16, 1024);
+          umma_bf16(tS0 + st * QB, kd, qd, idesc_s, kk > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t vd = make_smem_desc_sw128(aV + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t od = make_smem_desc_sw128(ot + (kk >> 2) * (QT_BYTES / 2) + (kk & 3) * 32, 16, 1024);
+          umma_bf16(tdP0 + st * QB, vd, od, idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&sdp_full[st]);
+      };
       mbar_wait(&kv_full, 0);
+      if (niter > 0) {
+        mbar_wait(&qdo_full[0], 0);
+        tc_fence_after();
+        issue_sdp(0);
+      }
       for (int it = 0; it < niter; ++it) {
-        mbar_wait(&qdo_full, it & 1);
+        const int st = it & 1;
+        if (it + 1 < niter) {
+          mbar_wait(&qdo_full[(it + 1) % NQ], (uint32_t)((it + 1) / NQ) & 1);
+          tc_fence_after();
+          issue_sdp(it + 1);             // its TMEM buffers were drained before pds_full(it-1) fired
+        }
+        mbar_wait(&pds_full[st], (uint32_t)(it >> 1) & 1);
         tc_fence_after();
-        mma_tile<false, false>(tS, sm.a[2], sm.a[0], false);    // S  = Q K^T
-        mma_tile<false, false>(tdP, sm.a[3], sm.a[1], false);   // dP = dO V^T
-        umma_commit(&sdp_full);
-        mbar_wait(&pds_full, it & 1);
-        tc_fence_after();
-        mma_tile<true, true>(tdV, sm.a[4], sm.a[3], it > 0);    // dV += P^T dO
-        mma_tile<true, true>(tdK, sm.a[5], sm.a[2], it > 0);    // dK += dS^T Q
-        umma_commit(&qdo_empty);                                 // Q, dO, P, dS buffers reusable
+        const uint32_t pt = aP + st * PT_BYTES, dst = adS + st * PT_BYTES;
+        const uint32_t qt = aQ + (it % NQ) * QT_BYTES, ot = adO + (it % NQ) * QT_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {   // contraction over the 64 queries of the block
+          const uint64_t ad = make_smem_desc_sw128(pt + kk * 32, 16, 1024);                 // P^T: K-major
+          const uint64_t bd = make_smem_desc_sw128(ot + kk * 2048, QT_BYTES / 2, 1024);     // dO: MN-major
+          umma_bf16(tdV, ad, bd, idesc_a, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t ad = make_smem_desc_sw128(dst + kk * 32, 16, 1024);                // dS^T: K-major
+          const uint64_t bd = make_smem_desc_sw128(qt + kk * 2048, QT_BYTES / 2, 1024);     // Q: MN-major
+          umma_bf16(tdK, ad, bd, idesc_a, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&pds_done[st]);          // P^T / dS^T buffer st reusable
+        umma_commit(&qdo_empty[it % NQ]);    // Q / dO ring slot reusable
       }
       umma_commit(&acc_full);
     }
   } else {
     const int cw = warp - 2;
     const int quad = warp & 3;
-    const int hf = cw >> 2;
-    const int r = quad * 32 + lane;
+    const int hf = cw >> 2;                  // 32-query half of the 64-query block
+    const int r = quad * 32 + lane;          // key row = TMEM lane
     const int tid = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float sl2 = p.scale * LOG2E;
-    build_keep_bits(s_bits, p, b, k0, tid);
-    compute_bar_sync();
-    const uint32_t kw0 = s_bits[hf * 2], kw1 = s_bits[hf * 2 + 1];
+    const int kg = k0 + r;
+    bool kkeep = kg < p.Sk;
+    if (kkeep && p.key_keep) kkeep = p.key_keep[(long long)b * p.Sk + kg] != 0;
     const long long rbase = ((long long)b * p.H + h) * p.Sq;
-    float L_next = INFINITY, D_next = 0.f;
-    if (qb0 * AT + r < p.Sq) { L_next = p.lse[rbase + qb0 * AT + r]; D_next = p.dvec[rbase + qb0 * AT + r]; }
+    // per-query statistics (LSE, D) of block it+1 are staged in shared memory while block it is processed
+    auto load_L = [&](int q) { return (tid < QB && q < p.Sq) ? p.lse[rbase + q] : INFINITY; };
+    auto load_D = [&](int q) { return (tid < QB && q < p.Sq) ? p.dvec[rbase + q] : 0.f; };
+    float L_next = 0.f, D_next = 0.f;
+    if (tid < QB) {
+      s_L[0][tid] = load_L(qb0 * QB + tid); s_D[0][tid] = load_D(qb0 * QB + tid);
+      L_next = load_L((qb0 + 1) * QB + tid); D_next = load_D((qb0 + 1) * QB + tid);
+    }
     for (int it = 0; it < niter; ++it) {
-      const int qg = (qb0 + it) * AT + r;
-      const bool qok = qg < p.Sq;
-      const float L = L_next, Dv = D_next;
-      if (it + 1 < niter && qg + AT < p.Sq) { L_next = p.lse[rbase + qg + AT]; D_next = p.dvec[rbase + qg + AT]; }
-      else { L_next = INFINITY; D_next = 0.f; }
-      uint32_t msk[2];
-      msk[0] = qok ? chunk_mask(kw0, p.causal != 0, qg, k0 + hf * 64) : 0u;
-      msk[1] = qok ? chunk_mask(kw1, p.causal != 0, qg, k0 + hf * 64 + 32) : 0u;
-      mbar_wait(&sdp_full, it & 1);
+      const int st = it & 1;
+      const int qbase = (qb0 + it) * QB + hf * 32;     // query of column 0 of this thread's chunk
+      compute_bar_sync();                    // publishes stats(it); orders reuse of the other stats buffer
+      if (tid < QB) {
+        s_L[st ^ 1][tid] = L_next; s_D[st ^ 1][tid] = D_next;
+        L_next = load_L((qb0 + it + 2) * QB + tid); D_next = load_D((qb0 + it + 2) * QB + tid);
+      }
+      // bit i: key kg may be attended by query qbase + i  (key padding; causal: kg <= q)
+      uint32_t msk = kkeep ? 0xffffffffu : 0u;
+      if (p.causal) {
+        const int lim = kg - qbase;          // columns i < lim are masked
+        if (lim >= 32) msk = 0u;
+        else if (lim > 0) msk &= ~((1u << lim) - 1u);
+      }
+      mbar_wait(&sdp_full[st], (uint32_t)(it >> 1) & 1);
       tc_fence_after();
-      // P / dS smem of the previous iteration were consumed by MMAs that precede this iteration's S/dP in the
-      // in-order tensor pipe, so sdp_full implies the buffers are free.
+      uint32_t sv[32], dv[32];
+      tmem_ld32(tS0 + st * QB + lane_addr + hf * 32, sv);
+      tmem_ld32(tdP0 + st * QB + lane_addr + hf * 32, dv);
+      tmem_ld_wait();
+      float pr[32], ds[32];
+      const float4* L4 = reinterpret_cast<const float4*>(&s_L[st][hf * 32]);
+      const float4* D4 = reinterpret_cast<const float4*>(&s_D[st][hf * 32]);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tS + lane_addr + hf * 64 + c * 32, sv);
-        tmem_ld32(tdP + lane_addr + hf * 64 + c * 32, dv);
-        tmem_ld_wait();
-        float pr[32], ds[32];
+      for (int g = 0; g < 8; ++g) {
+        const float4 l4 = L4[g], d4 = D4[g];
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pv = ((msk[c] >> i) & 1u) ? ex2(__uint_as_float(sv[i]) * sl2 - L) : 0.f;
+        for (int t = 0; t < 4; ++t) {
+          const int i = g * 4 + t;
+          const float pv = ((msk >> i) & 1u) ? ex2(__uint_as_float(sv[i]) * sl2 - lv[t]) : 0.f;
           pr[i] = pv;
-          ds[i] = pv * (__uint_as_float(dv[i]) - Dv) * p.scale;
+          ds[i] = pv * (__uint_as_float(dv[i]) - dd[t]) * p.scale;
         }
-        store_chunk(sm.t[4], r, hf * 64 + c * 32, pr);
-        store_chunk(sm.t[5], r, hf * 64 + c * 32, ds);
+      }
+      if (it >= 2) mbar_wait(&pds_done[st], (uint32_t)((it - 2) >> 1) & 1);   // MMAs of block it-2 released this buffer
+      {
+        // row r of the [128 x 64] P^T / dS^T tiles: 128 bytes, 16-byte chunks XOR-swizzled by (r & 7)
+        uint8_t* prow = gP + st * PT_BYTES + r * 128;
+        uint8_t* drow = gdS + st * PT_BYTES + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v4, w4;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v4);
+          __nv_bfloat162* g2 = reinterpret_cast<__nv_bfloat162*>(&w4);
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            h2[tt] = __floats2bfloat162_rn(pr[g * 8 + 2 * tt], pr[g * 8 + 2 * tt + 1]);
+            g2[tt] = __floats2bfloat162_rn(ds[g * 8 + 2 * tt], ds[g * 8 + 2 * tt + 1]);
+          }
+          const int off = ((hf * 4 + g) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + off) = v4;
+          *reinterpret_cast<uint4*>(drow + off) = w4;
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&pds_full);
+      mbar_arrive(&pds_full[st]);
     }
     // epilogue: thread = (key row, 64-column half of head_dim)
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    const int kg = k0 + r;
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t tacc = which == 0 ? tdV : tdK;
@@ -454,8 +544,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tacc + lane_addr + hf * 64 + c * 32, v);
-        tmem_ld_wait();
+        if (niter > 0) {
+          tmem_ld32(tacc + lane_addr + hf * 64 + c * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
         if (kg < p.Sk) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -767,11 +862,14 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
     if (pb_check_launch("attn_bwd_prep_kernel")) return -1;
   }
   static bool attr1 = false, attr2 = false;
-  const int smem1 = 6 * TILE_BYTES + 1024, smem2 = 2 * TILE_BYTES + 2 * NKV * KV_TILE_BYTES + 2 * DS_TILE_BYTES + 1024;
+  const int smem1 = 2 * TILE_BYTES + 2 * NQ * QT_BYTES + 4 * PT_BYTES + 1024, smem2 = 2 * TILE_BYTES + 2 * NKV * KV_TILE_BYTES + 2 * DS_TILE_BYTES + 1024;
   if (set_smem(attn_bwd_dkv_kernel, smem1, attr1)) return -1;
   if (set_smem(attn_bwd_dq_kernel, smem2, attr2)) return -1;
+  CUtensorMap tq64, tdo64;   // 64-query boxes for the dK/dV kernel
+  if (attn_tmap(&tq64, d->q, d->Sq, d->ldq, d->H, d->B, (long long)d->Sq * d->ldq, QB)) return -1;
+  if (attn_tmap(&tdo64, d->dout, d->Sq, d->lddo, d->H, d->B, (long long)d->Sq * d->lddo, QB)) return -1;
   dim3 g1((d->Sk + AT - 1) / AT, d->H, d->B);
-  attn_bwd_dkv_kernel<<<g1, NTHREADS, smem1, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_dkv_kernel<<<g1, NTHREADS, smem1, stream>>>(tq64, tk, tv, tdo64, p);
   if (pb_check_launch("attn_bwd_dkv_kernel")) return -1;
   CUtensorMap tk64, tv64;   // 64-key boxes for the dQ kernel
   if (attn_tmap(&tk64, d->k, d->Sk, d->ldk, d->H, d->B, (long long)d->Sk * d->ldk, KB)) return -1;
