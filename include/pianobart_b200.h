@@ -50,6 +50,9 @@ void pb_reset_launch_count(void);
 #define PB_GEMM_RES_F32 8    /* residual is fp32 (default: same dtype as C)                  */
 #define PB_GEMM_AUX_PREACT 16 /* also store the pre-activation (after bias) to aux (dtype of C) */
 #define PB_GEMM_MUL_DGELU 32  /* multiply the result by gelu'(aux[m,n]) (fc1 backward)          */
+#define PB_GEMM_AUX_DGELU 64  /* with GELU: also store gelu'(pre-activation) to aux (dtype of C) - forward of fc1; the
+                                 erf / exp evaluation is shared with the activation itself                        */
+#define PB_GEMM_MUL_AUX 128   /* multiply the result by aux[m,n] (fc1 backward against a stored gelu')            */
 
 typedef struct pb_gemm_desc {
   const void* a;
@@ -68,7 +71,7 @@ typedef struct pb_gemm_desc {
   int split_k; /* >1 requires OUT_F32|ATOMIC_ACC */
   int causal;  /* 0 none; 1 skip output tiles with n > m (scores); 2 limit k to <= m (P.V)      */
   int block_n; /* 0 = auto, else 128 or 256 (tcgen05 path only)                                 */
-  void* aux;   /* see PB_GEMM_AUX_PREACT / PB_GEMM_MUL_DGELU; row stride ldaux, not batched      */
+  void* aux;   /* see PB_GEMM_AUX_* / PB_GEMM_MUL_*; row stride ldaux, not batched                 */
   long long ldaux;
   int r_row_mod; /* >0: residual row index = m % r_row_mod (learned position table broadcast over batch) */
   /* training-mode dropout on (acc + bias [+ activation]) BEFORE the residual is added (HF Bart*Layer.forward):

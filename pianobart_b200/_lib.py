@@ -15,6 +15,8 @@ PB_GEMM_ATOMIC_ACC = 4
 PB_GEMM_RES_F32 = 8
 PB_GEMM_AUX_PREACT = 16
 PB_GEMM_MUL_DGELU = 32
+PB_GEMM_AUX_DGELU = 64
+PB_GEMM_MUL_AUX = 128
 
 
 class GemmDesc(C.Structure):

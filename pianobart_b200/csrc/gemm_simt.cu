@@ -72,8 +72,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const P p) {
       float x = acc[i][j] * p.alpha;
       if (p.bias) x += p.bias[n];
       if (p.flags & PB_GEMM_AUX_PREACT) p.aux[(long long)m * p.ldaux + n] = x;
+      if (p.flags & PB_GEMM_AUX_DGELU) p.aux[(long long)m * p.ldaux + n] = dgelu_erf(x);
       if (p.flags & PB_GEMM_GELU) x = gelu_erf(x);
       if (p.flags & PB_GEMM_MUL_DGELU) x *= dgelu_erf(p.aux[(long long)m * p.ldaux + n]);
+      if (p.flags & PB_GEMM_MUL_AUX) x *= p.aux[(long long)m * p.ldaux + n];
       if (p.drop.seed) {
         const uint32_t key = pbdrop::site_key(*p.drop.seed, p.drop.op);
         x = pbdrop::keep(key, (unsigned long long)m * (unsigned long long)p.N + n, p.drop.thresh) ? x * p.drop.scale : 0.f;
@@ -102,7 +104,7 @@ extern "C" int pb_gemm_f32(const pb_gemm_desc* d, void* stream_) {
   p.c_sh = d->c_stride_h; p.c_sb = d->c_stride_b; p.r_sh = d->r_stride_h; p.r_sb = d->r_stride_b;
   p.alpha = d->alpha; p.flags = d->flags; p.r_row_mod = d->r_row_mod;
   p.drop.seed = d->drop_seed; p.drop.op = d->drop_op; p.drop.thresh = d->drop_thresh; p.drop.scale = d->drop_scale;
-  if ((d->flags & (PB_GEMM_AUX_PREACT | PB_GEMM_MUL_DGELU)) && d->aux == nullptr)
+  if ((d->flags & (PB_GEMM_AUX_PREACT | PB_GEMM_MUL_DGELU | PB_GEMM_AUX_DGELU | PB_GEMM_MUL_AUX)) && d->aux == nullptr)
     return pb_set_error("pb_gemm_f32: aux epilogue without aux buffer");
   dim3 grid((d->N + TN - 1) / TN, (d->M + TM - 1) / TM, p.nh * p.nb);
   if (grid.y > 65535 || grid.z > 65535) return pb_set_error("pb_gemm_f32: grid too large");

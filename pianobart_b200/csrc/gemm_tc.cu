@@ -60,6 +60,10 @@ struct GemmKParams {
   int r_row_mod;
   pbdrop::Site drop;
   int causal;  // 1: skip tiles entirely above the diagonal (n0 > m0 + BLOCK_M - 1); 2: limit k range to m0+BLOCK_M
+  // epilogue through TMA (bf16, 32 x 32 boxes staged in shared memory, 64-byte swizzle): see the kernel's epilogue
+  int tma_c;    // C is stored with tmap_c
+  int tma_pre;  // 0: none, 1: residual rows, 2: aux rows (MUL_AUX / MUL_DGELU operand) are loaded with tmap_pre
+  int tma_x;    // aux output (AUX_PREACT / AUX_DGELU) is stored with tmap_x
 };
 
 // CG2: cta_group::2 - a pair of CTAs (one TPC) computes a 256 x BLOCK_N tile; each CTA stages its own 128 rows of A and
@@ -71,19 +75,45 @@ struct SmemCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (STAGE_BYTES >= 48 * 1024) ? 4 : 6;
-  static constexpr int DYN_BYTES = STAGES * STAGE_BYTES + 1024;
+  // epilogue staging per epilogue warp: two 2 KB slots ([32 rows x 32 bf16] boxes) - both rotate as TMA store buffers,
+  // or one takes the TMA loads when the epilogue has a residual / aux input.  Sized so that the 32 KB-per-stage
+  // configurations keep a 6-deep operand ring (5 stages cost the long-K GEMMs ~5%).
+  static constexpr int EPI_WARP_BYTES = 2 * 2048;
+  static constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;
+  static constexpr int RING_BUDGET = 227 * 1024 - 1024 - EPI_BYTES - 1536;   // alignment slack, static shared
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 6 ? 6 : (RING_BUDGET / STAGE_BYTES);
+  static constexpr int DYN_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float dgelu_erf(float z) {
   return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
 }
+// erf GELU and its derivative from one shared evaluation: Phi(x) = 0.5 (1 + erf(x / sqrt 2)) with erf from Abramowitz &
+// Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution), whose exp(-x^2/2) factor is also the Gaussian density
+// the derivative needs:  gelu = x Phi,  gelu' = Phi + x exp(-x^2/2) / sqrt(2 pi).  ~17 FP32 ops + 2 MUFU per element,
+// against erff + expf (~35) for the two separate evaluations: the fc1 / dZ epilogues are issue-bound otherwise.
+__device__ __forceinline__ void gelu_fwd_grad(float x, float& g, float& d) {
+  const float z = x * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, fabsf(z), 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float phi = fmaf(copysignf(0.5f, z), erf_abs, 0.5f);
+  g = x * phi;
+  d = fmaf(x * 0.3989422804014327f, e, phi);
+}
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool CG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
+               const __grid_constant__ CUtensorMap tmap_x, const GemmKParams p) {
   using Cfg = SmemCfg<BLOCK_N, CG2>;
   constexpr int M_TILE = CG2 ? 2 * BLOCK_M : BLOCK_M;      // rows of C per scheduling unit
   const uint32_t rank = CG2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs of the pair)
@@ -98,7 +128,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_bias[2][BLOCK_N];   // per accumulator stage: bias of the tile's columns (0 when absent)
+  __shared__ float s_bias[BLOCK_N];      // bias of the current tile's columns (0 when absent)
+  __shared__ __align__(8) uint64_t epi_bar[NUM_EPI_WARPS];   // per epilogue warp: TMA load of its residual / aux box
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,6 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], CG2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
+    for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&epi_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -259,14 +291,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool do_gelu = p.flags & PB_GEMM_GELU;
     const bool atomic_acc = p.flags & PB_GEMM_ATOMIC_ACC;
     const bool res_f32 = p.flags & PB_GEMM_RES_F32;
+    // TMA epilogue: a thread owns one accumulator row, so direct global accesses touch 32 different rows per warp
+    // instruction (32 L1 wavefronts per request, partial sectors) and the LSU - not the tensor pipe - bounded every GEMM
+    // with a residual, aux operand or second output.  Instead each warp stages its [32 rows x 32 columns] bf16 box in
+    // shared memory (64-byte swizzle: conflict-free 16-byte accesses) and moves it with one bulk tensor copy.
+    const int ew = warp - 2;
+    uint8_t* st_buf = smem_gen + STAGES * Cfg::STAGE_BYTES + ew * Cfg::EPI_WARP_BYTES;   // slot 0 (stores)
+    uint8_t* ld_buf = st_buf + 2048;                                                      // slot 1 (loads, else stores)
+    const bool two_store_slots = (p.tma_pre == 0);
+    uint64_t* ld_bar = &epi_bar[ew];
+    uint32_t ld_phase = 0;
+    int st_slot = 0;
+    const int sw = (lane >> 1) & 3;          // 64-byte swizzle: 16-byte chunk g of row `lane` lives at chunk g ^ sw
+    if (lane == 0) {
+      if (p.tma_c) tma_prefetch_desc(&tmap_c);
+      if (p.tma_pre) tma_prefetch_desc(&tmap_pre);
+      if (p.tma_x) tma_prefetch_desc(&tmap_x);
+    }
     for (long long w = unit0; w < p.total_units; w += unit_stride) {
       int m_blk, n_blk, split, h, b, kb0, kb1;
       decode(w, m_blk, n_blk, split, h, b);
       k_range(m_blk, n_blk, split, kb0, kb1);
       if (kb1 <= kb0) continue;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = m_blk * M_TILE + (int)rank * BLOCK_M + quad * 32 + lane;
+      const int row0w = m_blk * M_TILE + (int)rank * BLOCK_M + quad * 32;   // first row of this warp's 32-row block
+      const int row = row0w + lane;
       const bool row_ok = row < p.M;
       const long long c_off = (long long)b * p.c_stride_b + (long long)h * p.c_stride_h + (long long)row * p.ldc;
       const long long r_off = (long long)b * p.r_stride_b + (long long)h * p.r_stride_h +
@@ -274,42 +322,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool first_split = (split == 0);
       // stage this tile's bias slice in shared memory (read by every row, otherwise 8 dependent global loads
       // per chunk sit on the epilogue's critical path)
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // every warp is done with the previous tile's bias
       for (int i = etid; i < BLOCK_N; i += NUM_EPI_WARPS * 32) {
         const int col = n_blk * BLOCK_N + i;
-        s_bias[acc][i] = (p.bias != nullptr && first_split && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        s_bias[i] = (p.bias != nullptr && first_split && col < p.N) ? __ldg(p.bias + col) : 0.f;
       }
+      // Global operands of the epilogue (residual rows, gelu' / aux operand) are fetched one 32-column chunk ahead -
+      // chunk 0 before the accumulator is even complete - so their latency never sits between the TMEM read and the
+      // stores.  One prefetch stream: the aux operand when the epilogue multiplies by it, else the residual; by TMA
+      // when the host could build a tensor map for it (p.tma_pre), else with per-thread vector loads.
+      const bool pre_tma = p.tma_pre != 0 && row0w < p.M;
+      const bool want_aux = row_ok && !out_f32 && (p.flags & (PB_GEMM_MUL_DGELU | PB_GEMM_MUL_AUX)) && ((p.ldaux & 7) == 0);
+      const bool want_res = !want_aux && row_ok && !out_f32 && p.residual != nullptr && first_split && !res_f32 && ((p.ldr & 7) == 0);
+      const __nv_bfloat16* res_row = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off;
+      const __nv_bfloat16* aux_row = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux;
+      const __nv_bfloat16* pre_row = want_aux ? aux_row : res_row;
+      auto issue_loads = [&](int chi, uint4 (&rr)[4]) {
+        const int c0 = n_blk * BLOCK_N + (half * CH_PER_WARP + chi) * 32;
+        if (pre_tma) {
+          if (lane == 0 && c0 < p.N) {
+            mbar_expect_tx(ld_bar, 2048);
+            tma_load_4d(ld_buf, &tmap_pre, ld_bar, c0, row0w, h, b);
+          }
+        } else if ((want_res || want_aux) && c0 + 32 <= p.N) {
+          const uint4* r = reinterpret_cast<const uint4*>(pre_row + c0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rr[g] = r[g];
+        }
+      };
+      // packs 32 fp32 values to bf16 and stores them as this thread's row of the warp's box through a TMA store
+      auto tma_store_row = [&](const CUtensorMap* tm, const float (&val)[32], int col0) {
+        if (lane == 0) {                             // the slot about to be overwritten has been read
+          if (two_store_slots) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
+        __syncwarp();
+        uint8_t* sb = st_buf + st_slot * 2048 + lane * 64;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(val[g * 8 + 2 * t], val[g * 8 + 2 * t + 1]);
+          *reinterpret_cast<uint4*>(sb + ((g ^ sw) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(tm, st_buf + st_slot * 2048, col0, row0w, h, b);
+          bulk_commit();
+        }
+        if (two_store_slots) st_slot ^= 1;
+      };
+      uint4 rpre[4], npre[4];
+      issue_loads(0, rpre);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
       asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
       for (int chi = 0; chi < CH_PER_WARP; ++chi) {
         const int ch = half * CH_PER_WARP + chi;
         uint32_t v[32];
         const int col0 = n_blk * BLOCK_N + ch * 32;
-        // issue the global loads this chunk needs (residual row, gelu' operand) before waiting on TMEM so their
-        // latency overlaps the accumulator read
-        const bool pf_ok = row_ok && (col0 + 32 <= p.N) && !out_f32;
-        const bool pf_res = pf_ok && p.residual != nullptr && first_split && !res_f32 && ((p.ldr & 7) == 0);
-        const bool pf_aux = pf_ok && (p.flags & PB_GEMM_MUL_DGELU) && ((p.ldaux & 7) == 0);
-        uint4 rres[4], raux[4];
-        if (pf_res) {
-          const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) rres[g] = r[g];
-        }
-        if (pf_aux) {
-          const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) raux[g] = r[g];
-        }
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked body below
+        if (col0 >= p.N || row0w >= p.M) break;       // warp-uniform: nothing of this chunk (or any later one) exists
+        const bool full = (col0 + 32 <= p.N);
+        bool pf_res = want_res && full, pf_aux = want_aux && full;
+        __syncwarp();  // tcgen05.ld is .sync.aligned
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + ch * 32), v);
+        if (pre_tma) {
+          mbar_wait(ld_bar, ld_phase);
+          ld_phase ^= 1;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rpre[g] = *reinterpret_cast<const uint4*>(ld_buf + lane * 64 + ((g ^ sw) << 4));
+          __syncwarp();                               // every lane has read the slot: the next box may land in it
+          if (chi + 1 < CH_PER_WARP) issue_loads(chi + 1, npre);
+          // out-of-range rows / columns of the box are zero-filled: use the staged values whenever they are requested
+          pf_aux = (p.tma_pre == 2);
+          pf_res = (p.tma_pre == 1) && first_split;
+        } else if (chi + 1 < CH_PER_WARP) {
+          issue_loads(chi + 1, npre);
+        }
         tmem_ld_wait();
-        if (!row_ok || col0 >= p.N) continue;
+        if (row_ok || p.tma_c || p.tma_x) {   // TMA stores are warp-collective: rows >= M are clipped by the tensor map
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
-        const bool full = (col0 + 32 <= p.N);
         {
-          const float* sb = &s_bias[acc][ch * 32];
+          const float* sb = &s_bias[ch * 32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] += sb[j];
         }
@@ -322,7 +420,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + j < p.N) ax[j] = x[j];
           } else {
             __nv_bfloat16* ax = reinterpret_cast<__nv_bfloat16*>(p.aux) + a_off;
-            if (full && ((p.ldaux & 7) == 0)) {
+            if (p.tma_x) {
+              tma_store_row(&tmap_x, x, col0);
+            } else if (full && ((p.ldaux & 7) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 uint4 o;
@@ -342,10 +442,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         if (do_gelu) {
+          if (p.flags & PB_GEMM_AUX_DGELU) {
+            float dg[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+            for (int j = 0; j < 32; ++j) gelu_fwd_grad(x[j], x[j], dg[j]);
+            __nv_bfloat16* ax = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col0;
+            if (p.tma_x) {
+              tma_store_row(&tmap_x, dg, col0);
+            } else if (full && ((p.ldaux & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(dg[j + 2 * t], dg[j + 2 * t + 1]);
+                *reinterpret_cast<uint4*>(ax + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) ax[j] = __float2bfloat16(dg[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float dummy;
+              gelu_fwd_grad(x[j], x[j], dummy);
+            }
+          }
         }
-        if (p.flags & PB_GEMM_MUL_DGELU) {
+        if (p.flags & PB_GEMM_MUL_AUX) {
+          const __nv_bfloat16* ax = aux_row + col0;
+          if (pf_aux) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rpre[j >> 3]);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(r2[t]);
+                x[j + 2 * t] *= f.x;
+                x[j + 2 * t + 1] *= f.y;
+              }
+            }
+          } else if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) x[j] *= __bfloat162float(ax[j]);
+          }
+        }
+        if ((p.flags & PB_GEMM_MUL_DGELU) && (row_ok || pf_aux)) {
           const long long a_off = (long long)row * p.ldaux + col0;
           if (out_f32) {
             const float* ax = reinterpret_cast<const float*>(p.aux) + a_off;
@@ -354,10 +499,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + j < p.N) x[j] *= dgelu_erf(ax[j]);
           } else {
             const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(p.aux) + a_off;
-            if (full && ((p.ldaux & 7) == 0)) {
+            if (pf_aux || (full && ((p.ldaux & 7) == 0))) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 rv = pf_aux ? raux[j >> 3] : *reinterpret_cast<const uint4*>(ax + j);
+                const uint4 rv = pf_aux ? rpre[j >> 3] : *reinterpret_cast<const uint4*>(ax + j);
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -379,7 +524,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = pbdrop::keep(key, base + j, p.drop.thresh) ? x[j] * p.drop.scale : 0.f;
         }
-        if (p.residual != nullptr && first_split) {
+        if (p.residual != nullptr && first_split && (row_ok || pf_res)) {
           if (res_f32) {
             const float* r = reinterpret_cast<const float*>(p.residual) + r_off + col0;
 #pragma unroll
@@ -387,10 +532,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + j < p.N) x[j] += r[j];
           } else {
             const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col0;
-            if (full && ((p.ldr & 7) == 0)) {
+            if (pf_res || (full && ((p.ldr & 7) == 0))) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 rv = pf_res ? rres[j >> 3] : *reinterpret_cast<const uint4*>(r + j);
+                const uint4 rv = pf_res ? rpre[j >> 3] : *reinterpret_cast<const uint4*>(r + j);
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -429,7 +574,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         } else {
           __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + col0;
-          if (full && ((p.ldc & 7) == 0)) {
+          if (p.tma_c) {
+            tma_store_row(&tmap_c, x, col0);
+          } else if (!row_ok) {
+            // (only reached when the aux output alone goes through TMA)
+          } else if (full && ((p.ldc & 7) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 o;
@@ -444,6 +593,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + j < p.N) c[j] = __float2bfloat16(x[j]);
           }
         }
+        }  // row_ok
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rpre[g] = npre[g];
       }
       tc_fence_before();
       __syncwarp();
@@ -454,6 +606,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait_all();   // outstanding TMA stores read this CTA's shared memory
   }
 
   tc_fence_before();
@@ -486,6 +639,7 @@ struct TmapKey {
   uint64_t d[4];
   uint64_t s[3];
   uint32_t b0, b1;
+  uint32_t swizzle, pad;
   bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -504,6 +658,12 @@ static std::mutex g_tmap_mutex;
 // inner = contiguous dimension (elements); rows = second dimension; ld = row stride (elements)
 int pb_make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, long long ld, int nh,
                      long long stride_h, int nb, long long stride_b, uint32_t box_inner, uint32_t box_rows) {
+  return pb_make_tmap_bf16_sw(out, base, inner, rows, ld, nh, stride_h, nb, stride_b, box_inner, box_rows, 128);
+}
+
+int pb_make_tmap_bf16_sw(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, long long ld, int nh,
+                        long long stride_h, int nb, long long stride_b, uint32_t box_inner, uint32_t box_rows,
+                        int swizzle_bytes) {
   using namespace pb;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return pb_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -516,6 +676,7 @@ int pb_make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   key.s[1] = nh > 1 ? (uint64_t)stride_h * 2ull : full;
   key.s[2] = nb > 1 ? (uint64_t)stride_b * 2ull : full * (uint64_t)(nh > 1 ? 1 : 1);
   key.b0 = box_inner; key.b1 = box_rows;
+  key.swizzle = (uint32_t)swizzle_bytes;
   {
     std::lock_guard<std::mutex> lk(g_tmap_mutex);
     auto it = g_tmap_cache.find(key);
@@ -529,7 +690,9 @@ int pb_make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   cuuint32_t box[4] = {box_inner, box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[160];
@@ -550,7 +713,8 @@ static inline int make_tmap(CUtensorMap* out, const void* base, uint64_t inner, 
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool CG2>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
+                  const CUtensorMap& tx, const GemmKParams& kp, cudaStream_t stream) {
   using Cfg = SmemCfg<BLOCK_N, CG2>;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CG2>;
@@ -561,7 +725,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParam
   }
   if constexpr (!CG2) {
     long long grid = kp.total_units < (long long)pb_num_sms() ? kp.total_units : (long long)pb_num_sms();
-    kern<<<(unsigned)grid, NUM_THREADS, Cfg::DYN_BYTES, stream>>>(ta, tb, kp);
+    kern<<<(unsigned)grid, NUM_THREADS, Cfg::DYN_BYTES, stream>>>(ta, tb, tc, tp, tx, kp);
   } else {
     // one CTA pair (cluster of 2 = one TPC) per scheduling unit slot
     const long long pairs_max = pb_num_sms() / 2;
@@ -577,7 +741,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParam
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, kp);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tp, tx, kp);
     if (e != cudaSuccess) return pb_set_cuda_error("cudaLaunchKernelEx(gemm_tc cta_group::2)", e);
   }
   return pb_check_launch("gemm_tc_kernel");
@@ -623,8 +787,13 @@ extern "C" int pb_gemm_bf16(const pb_gemm_desc* d, void* stream_) {
   kp.r_row_mod = d->r_row_mod;
   kp.drop.seed = d->drop_seed; kp.drop.op = d->drop_op; kp.drop.thresh = d->drop_thresh; kp.drop.scale = d->drop_scale;
   if (d->drop_seed != nullptr && (nh * nb != 1 || kp.split_k > 1)) return pb_set_error("pb_gemm_bf16: dropout needs no batching / split_k");
-  if ((d->flags & (PB_GEMM_AUX_PREACT | PB_GEMM_MUL_DGELU)) && (d->aux == nullptr || nh * nb != 1 || kp.split_k > 1))
+  constexpr int AUX_FLAGS = PB_GEMM_AUX_PREACT | PB_GEMM_MUL_DGELU | PB_GEMM_AUX_DGELU | PB_GEMM_MUL_AUX;
+  if ((d->flags & AUX_FLAGS) && (d->aux == nullptr || nh * nb != 1 || kp.split_k > 1))
     return pb_set_error("pb_gemm_bf16: aux epilogues need aux != NULL, no batching, no split_k");
+  if ((d->flags & (PB_GEMM_AUX_DGELU | PB_GEMM_MUL_AUX)) && (d->flags & PB_GEMM_OUT_F32))
+    return pb_set_error("pb_gemm_bf16: AUX_DGELU / MUL_AUX are bf16-output epilogues");
+  if ((d->flags & PB_GEMM_AUX_DGELU) && !(d->flags & PB_GEMM_GELU))
+    return pb_set_error("pb_gemm_bf16: AUX_DGELU needs GELU");
   if (kp.causal && kp.split_k > 1) return pb_set_error("pb_gemm_bf16: causal with split_k");
 
   CUtensorMap ta, tb;
@@ -644,27 +813,59 @@ extern "C" int pb_gemm_bf16(const pb_gemm_desc* d, void* stream_) {
                    BLOCK_K);
   if (rc) return rc;
 
+  // Epilogue tensor maps ([32 x 32] bf16 boxes, 64-byte swizzle) wherever the operand is bf16, 16-byte aligned and
+  // addressed by the plain (row, column, h, b) index: C, the residual or aux input, the aux output.
+  CUtensorMap tc = ta, tp = ta, tx = ta;
+  static const int tma_epi_env = getenv("PIANOBART_B200_TMA_EPI") ? atoi(getenv("PIANOBART_B200_TMA_EPI")) : 1;
+  auto epi_ok = [&](const void* ptr, long long ld, long long sh, long long sb) {
+    if (!tma_epi_env || ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld & 7) != 0 || ld < d->N) return false;
+    if (nh > 1 && ((sh & 7) != 0 || sh <= 0)) return false;
+    if (nb > 1 && ((sb & 7) != 0 || sb <= 0)) return false;
+    return true;
+  };
+  const bool out_bf16 = !(d->flags & PB_GEMM_OUT_F32);
+  kp.tma_c = kp.tma_pre = kp.tma_x = 0;
+  if (out_bf16 && epi_ok(d->c, d->ldc, d->c_stride_h, d->c_stride_b)) {
+    if (pb_make_tmap_bf16_sw(&tc, d->c, (uint64_t)d->N, (uint64_t)d->M, d->ldc, nh, d->c_stride_h, nb, d->c_stride_b, 32, 32, 64))
+      return -1;
+    kp.tma_c = 1;
+  }
+  if (out_bf16 && (d->flags & (PB_GEMM_MUL_AUX | PB_GEMM_MUL_DGELU)) && epi_ok(d->aux, d->ldaux, 0, 0)) {
+    if (pb_make_tmap_bf16_sw(&tp, d->aux, (uint64_t)d->N, (uint64_t)d->M, d->ldaux, 1, 0, 1, 0, 32, 32, 64)) return -1;
+    kp.tma_pre = 2;
+  } else if (out_bf16 && d->residual != nullptr && !(d->flags & PB_GEMM_RES_F32) && d->r_row_mod <= 0 && kp.split_k == 1 &&
+             epi_ok(d->residual, d->ldr, d->r_stride_h, d->r_stride_b)) {
+    if (pb_make_tmap_bf16_sw(&tp, d->residual, (uint64_t)d->N, (uint64_t)d->M, d->ldr, nh, d->r_stride_h, nb, d->r_stride_b,
+                             32, 32, 64))
+      return -1;
+    kp.tma_pre = 1;
+  }
+  if (out_bf16 && (d->flags & (PB_GEMM_AUX_PREACT | PB_GEMM_AUX_DGELU)) && epi_ok(d->aux, d->ldaux, 0, 0)) {
+    if (pb_make_tmap_bf16_sw(&tx, d->aux, (uint64_t)d->N, (uint64_t)d->M, d->ldaux, 1, 0, 1, 0, 32, 32, 64)) return -1;
+    kp.tma_x = 1;
+  }
+
   const int variant = (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
   if (cg2) {
     switch (variant) {
-      case 0: return launch<256, false, false, true>(ta, tb, kp, stream);
-      case 1: return launch<256, false, true, true>(ta, tb, kp, stream);
-      case 2: return launch<256, true, false, true>(ta, tb, kp, stream);
-      default: return launch<256, true, true, true>(ta, tb, kp, stream);
+      case 0: return launch<256, false, false, true>(ta, tb, tc, tp, tx, kp, stream);
+      case 1: return launch<256, false, true, true>(ta, tb, tc, tp, tx, kp, stream);
+      case 2: return launch<256, true, false, true>(ta, tb, tc, tp, tx, kp, stream);
+      default: return launch<256, true, true, true>(ta, tb, tc, tp, tx, kp, stream);
     }
   } else if (block_n == 256) {
     switch (variant) {
-      case 0: return launch<256, false, false, false>(ta, tb, kp, stream);
-      case 1: return launch<256, false, true, false>(ta, tb, kp, stream);
-      case 2: return launch<256, true, false, false>(ta, tb, kp, stream);
-      default: return launch<256, true, true, false>(ta, tb, kp, stream);
+      case 0: return launch<256, false, false, false>(ta, tb, tc, tp, tx, kp, stream);
+      case 1: return launch<256, false, true, false>(ta, tb, tc, tp, tx, kp, stream);
+      case 2: return launch<256, true, false, false>(ta, tb, tc, tp, tx, kp, stream);
+      default: return launch<256, true, true, false>(ta, tb, tc, tp, tx, kp, stream);
     }
   } else {
     switch (variant) {
-      case 0: return launch<128, false, false, false>(ta, tb, kp, stream);
-      case 1: return launch<128, false, true, false>(ta, tb, kp, stream);
-      case 2: return launch<128, true, false, false>(ta, tb, kp, stream);
-      default: return launch<128, true, true, false>(ta, tb, kp, stream);
+      case 0: return launch<128, false, false, false>(ta, tb, tc, tp, tx, kp, stream);
+      case 1: return launch<128, false, true, false>(ta, tb, tc, tp, tx, kp, stream);
+      case 2: return launch<128, true, false, false>(ta, tb, tc, tp, tx, kp, stream);
+      default: return launch<128, true, true, false>(ta, tb, tc, tp, tx, kp, stream);
     }
   }
 }

@@ -502,7 +502,7 @@ class BackboneGraph:
             Hn = self.buf(ln('Hn'), M, d)
             st2 = self.buf(ln('st2'), 2, M, dtype=torch.float32)
             f.gemm(_ptr(h_mid), self.W(lp + '.fc1.weight'), _ptr(Gt), M, F, d, d, d, F, bias=self.Pf(lp + '.fc1.bias'),
-                   flags=L.PB_GEMM_GELU | L.PB_GEMM_AUX_PREACT, aux=_ptr(Z), ldaux=F, name=ln('fc1'))
+                   flags=L.PB_GEMM_GELU | L.PB_GEMM_AUX_DGELU, aux=_ptr(Z), ldaux=F, name=ln('fc1'))
             f.gemm(_ptr(Gt), self.W(lp + '.fc2.weight'), _ptr(A2), M, d, F, F, F, d, bias=self.Pf(lp + '.fc2.bias'),
                    residual=_ptr(h_mid), ldr=d, drop=self.site(side, l, 3), name=ln('fc2'))
             f.ln_fwd(_ptr(A2), self.Pf(lp + '.final_layer_norm.weight'), self.Pf(lp + '.final_layer_norm.bias'),
@@ -537,7 +537,7 @@ class BackboneGraph:
                           dx_drop=_ptr(dAd), out_drop=self.site(side, l, 3))
                 bw.wgrad(_ptr(dAd), _ptr(r['G']), self.G(lp + '.fc2.weight'), d, F, M, d, F, name=ln('dW_fc2'))
                 bw.gemm(_ptr(dAd), self.W(lp + '.fc2.weight'), _ptr(dZ), M, F, d, d, F, F, b_mn=1,
-                        flags=L.PB_GEMM_MUL_DGELU, aux=_ptr(r['Z']), ldaux=F, name=ln('dZ'))
+                        flags=L.PB_GEMM_MUL_AUX, aux=_ptr(r['Z']), ldaux=F, name=ln('dZ'))
                 bw.colsum(_ptr(dZ), self.G(lp + '.fc1.bias'), M, F, F)
                 bw.wgrad(_ptr(dZ), _ptr(r['h_mid']), self.G(lp + '.fc1.weight'), F, d, M, F, d, name=ln('dW_fc1'))
                 bw.gemm(_ptr(dZ), self.W(lp + '.fc1.weight'), _ptr(dH1), M, d, F, F, d, d, b_mn=1, residual=_ptr(dA),

@@ -75,6 +75,24 @@ def test_gemm_tc_epilogues_and_splitk():
     ref = torch.nn.functional.gelu(z.bfloat16().float()) + res.float()
     assert _rel(aux.float().cpu(), z.cpu()) < 1e-2
     assert _rel(out.float().cpu(), ref.cpu()) < 1e-2
+    # fc1 as the training plan runs it: GELU and gelu'(pre-activation) from one evaluation, then dZ = (dY W) * gelu'
+    d.flags = L.PB_GEMM_GELU | L.PB_GEMM_AUX_DGELU
+    L.check(lib.pb_gemm_bf16(C.byref(d), L.stream_ptr()), 'gemm')
+    torch.cuda.synchronize()
+    zz = z.clone().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    assert _rel(aux.float().cpu(), zz.grad.cpu()) < 1e-2
+    assert _rel(out.float().cpu(), (torch.nn.functional.gelu(z) + res.float()).cpu()) < 1e-2
+    assert (aux.float() - zz.grad).abs().max().item() < 8e-3      # bf16 rounding of values in [-0.13, 1.13]
+    dY = (torch.randn(M, K, device=dev) * 0.3).bfloat16()
+    dZ = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    d3 = L.GemmDesc()
+    d3.a, d3.b, d3.c, d3.aux = dY.data_ptr(), W.data_ptr(), dZ.data_ptr(), aux.data_ptr()
+    d3.M, d3.N, d3.K, d3.lda, d3.ldb, d3.ldc, d3.ldaux = M, N, K, K, K, N, N
+    d3.alpha, d3.flags, d3.split_k = 1.0, L.PB_GEMM_MUL_AUX, 1
+    L.check(lib.pb_gemm_bf16(C.byref(d3), L.stream_ptr()), 'gemm')
+    torch.cuda.synchronize()
+    assert _rel(dZ.float().cpu(), ((dY.float() @ W.float().t()) * aux.float()).cpu()) < 1e-2
     # split-K, fp32 atomic accumulate on top of existing content (dW accumulation)
     X = (torch.randn(K, M, device=dev) * 0.3).bfloat16()   # stored [K][M]: MN-major operands
     Y = (torch.randn(K, N, device=dev) * 0.3).bfloat16()

@@ -87,8 +87,10 @@ for side, ids, keep, S, nl in (('encoder', enc, em, gr.Se, pb.layout.enc_layers)
             cmp(L + 'Hc', buf(L + 'Hc', M, d), ln(buf(L + 'Ac', M, d), sd[lp + '.encoder_attn_layer_norm.weight'], sd[lp + '.encoder_attn_layer_norm.bias']))
             hm = buf(L + 'Hc', M, d)
         Z = hm @ sd[lp + '.fc1.weight'].t() + sd[lp + '.fc1.bias']
-        cmp(L + 'Z', buf(L + 'Z', M, F), Z)
-        cmp(L + 'G', buf(L + 'G', M, F), torch.nn.functional.gelu(buf(L + 'Z', M, F)))
+        Zg = Z.detach().clone().requires_grad_(True)
+        torch.nn.functional.gelu(Zg).sum().backward()
+        cmp(L + 'Z (gelu\')', buf(L + 'Z', M, F), Zg.grad)      # the fc1 epilogue stores gelu'(pre-activation)
+        cmp(L + 'G', buf(L + 'G', M, F), torch.nn.functional.gelu(Z))
         A2 = buf(L + 'G', M, F) @ sd[lp + '.fc2.weight'].t() + sd[lp + '.fc2.bias'] + hm
         cmp(L + 'A2', buf(L + 'A2', M, d), A2)
         cmp(L + 'Hn', buf(L + 'Hn', M, d), ln(buf(L + 'A2', M, d), sd[lp + '.final_layer_norm.weight'], sd[lp + '.final_layer_norm.bias']))
