@@ -234,22 +234,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = tS0 + (j & 1) * 128;
-      float t[64];
+      float t[64];                     // raw scores (masked entries = -inf); the scale is folded into the exp2 FFMA
       float bm = -INFINITY;
       {
         uint32_t v0[32], v1[32];
         tmem_ld32(tS + lane_addr + hf * 64, v0);
         tmem_ld32(tS + lane_addr + hf * 64 + 32, v1);
         tmem_ld_wait();
+        if ((msk[0] & msk[1]) == 0xffffffffu) {     // nothing masked in this thread's 64 columns (the common case)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x0 = ((msk[0] >> i) & 1u) ? __uint_as_float(v0[i]) * sl2 : -INFINITY;
-          const float x1 = ((msk[1] >> i) & 1u) ? __uint_as_float(v1[i]) * sl2 : -INFINITY;
-          t[i] = x0;
-          t[32 + i] = x1;
-          bm = fmaxf(bm, fmaxf(x0, x1));
+          for (int i = 0; i < 32; ++i) {
+            t[i] = __uint_as_float(v0[i]);
+            t[32 + i] = __uint_as_float(v1[i]);
+            bm = fmaxf(bm, fmaxf(t[i], t[32 + i]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x0 = ((msk[0] >> i) & 1u) ? __uint_as_float(v0[i]) : -INFINITY;
+            const float x1 = ((msk[1] >> i) & 1u) ? __uint_as_float(v1[i]) : -INFINITY;
+            t[i] = x0;
+            t[32 + i] = x1;
+            bm = fmaxf(bm, fmaxf(x0, x1));
+          }
         }
       }
+      bm *= sl2;                       // sl2 > 0: max of the scaled scores (log2 domain)
       s_red[hf][r] = bm;
       publish_keep_bits(s_bits2[(j + 1) & 1], kp_next, tid);
       kp_next = load_keep(p, b, (j + 2) * AT + tid, tid);
@@ -282,22 +292,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         tmem_st_wait();
         l *= f;
       }
-      const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
-      float rs = 0.f;
-      float x[2][32];
+      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+      float rs0 = 0.f, rs1 = 0.f;
+      uint32_t pk[32];                 // P row chunk as packed bf16 pairs
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          // masked entries are -inf -> ex2 gives 0; the row sum uses the bf16-rounded value the tensor core sees
-          x[c][i] = __bfloat162float(__float2bfloat16(ex2(t[c * 32 + i] - m_safe)));
-          rs += x[c][i];
-        }
+      for (int i = 0; i < 32; ++i) {
+        // masked entries are -inf -> ex2 gives 0; the row sum uses the bf16-rounded values the tensor core sees
+        // (packed conversion + integer unpack: the scalar F2F conversion shares the MUFU pipe with ex2)
+        const float e0 = ex2(fmaf(t[2 * i], sl2, neg_m)), e1 = ex2(fmaf(t[2 * i + 1], sl2, neg_m));
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(&h2);
+        pk[i] = u;
+        rs0 += __uint_as_float(u << 16);
+        rs1 += __uint_as_float(u & 0xffff0000u);
       }
-      l += rs;
+      l += rs0 + rs1;
       if (j > 0 && !waited_pv) mbar_wait(&pv_done, (j - 1) & 1);   // P buffer is free once P V (j-1) retired
+      {
+        // this thread's 64 columns = one 128-byte row of the tile half hf: 16-byte chunks XOR-swizzled by (r & 7)
+        uint8_t* rowp = sm.t[5] + hf * HALF_BYTES + r * 128;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) store_chunk(sm.t[5], r, hf * 64 + c * 32, x[c]);
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(rowp + ((g ^ (r & 7)) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full);
@@ -466,8 +483,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     if (kkeep && p.key_keep) kkeep = p.key_keep[(long long)b * p.Sk + kg] != 0;
     const long long rbase = ((long long)b * p.H + h) * p.Sq;
     // per-query statistics (LSE, D) of block it+1 are staged in shared memory while block it is processed
-    auto load_L = [&](int q) { return (tid < QB && q < p.Sq) ? p.lse[rbase + q] : INFINITY; };
-    auto load_D = [&](int q) { return (tid < QB && q < p.Sq) ? p.dvec[rbase + q] : 0.f; };
+    // staged as -LSE and -D * scale so that P = exp2(fma(S, scale*log2e, -LSE)) and dS = P * fma(dP, scale, -D*scale)
+    auto load_L = [&](int q) { return (tid < QB && q < p.Sq) ? -p.lse[rbase + q] : -INFINITY; };
+    auto load_D = [&](int q) { return (tid < QB && q < p.Sq) ? -p.dvec[rbase + q] * p.scale : 0.f; };
     float L_next = 0.f, D_next = 0.f;
     if (tid < QB) {
       s_L[0][tid] = load_L(qb0 * QB + tid); s_D[0][tid] = load_D(qb0 * QB + tid);
@@ -504,9 +522,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int i = g * 4 + t;
-          const float pv = ((msk >> i) & 1u) ? ex2(__uint_as_float(sv[i]) * sl2 - lv[t]) : 0.f;
+          float pv = ex2(fmaf(__uint_as_float(sv[i]), sl2, lv[t]));
+          if (msk != 0xffffffffu) pv = ((msk >> i) & 1u) ? pv : 0.f;
           pr[i] = pv;
-          ds[i] = pv * (__uint_as_float(dv[i]) - dd[t]) * p.scale;
+          ds[i] = pv * fmaf(__uint_as_float(dv[i]), p.scale, dd[t]);
         }
       }
       if (it >= 2) mbar_wait(&pds_done[st], (uint32_t)((it - 2) >> 1) & 1);   // MMAs of block it-2 released this buffer
@@ -690,8 +709,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const int qg = q0 + r;
     const bool qok = qg < p.Sq;
     const long long ridx = ((long long)b * p.H + h) * p.Sq + qg;
-    const float L = qok ? p.lse[ridx] : INFINITY;
-    const float Dv = qok ? p.dvec[ridx] : 0.f;
+    const float negL = qok ? -p.lse[ridx] : -INFINITY;
+    const float nDs = qok ? -p.dvec[ridx] * p.scale : 0.f;
     auto keep_of = [&](int kc) {
       bool kp = kc < p.Sk;
       if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc] != 0;
@@ -719,8 +738,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       float ds[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float pv = ((msk >> i) & 1u) ? ex2(__uint_as_float(sv[i]) * sl2 - L) : 0.f;
-        ds[i] = pv * (__uint_as_float(dv[i]) - Dv) * p.scale;
+        float pv = ex2(fmaf(__uint_as_float(sv[i]), sl2, negL));
+        if (msk != 0xffffffffu) pv = ((msk >> i) & 1u) ? pv : 0.f;
+        ds[i] = pv * fmaf(__uint_as_float(dv[i]), p.scale, nDs);
       }
       if (j >= 2) mbar_wait(&dq_done[st], (uint32_t)((j - 2) >> 1) & 1);   // dQ MMA of block j-2 released this buffer
       {
