@@ -35,7 +35,7 @@ def _compile(src, force, hm):
     path = os.path.join(CSRC, src)
     if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hm):
         return obj, False
-    cmd = [NVCC] + FLAGS + ["-c", path, "-o", obj]
+    cmd = [NVCC] + FLAGS + os.environ.get("PIANOBART_B200_NVCC_EXTRA", "").split() + ["-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -27,6 +27,16 @@ constexpr int TILE_BYTES = AT * AT * 2;  // 32 KB
 constexpr int HALF_BYTES = TILE_BYTES / 2;
 constexpr float LOG2E = 1.4426950408889634f;
 
+// Developer-only phase trace (build with PIANOBART_B200_NVCC_EXTRA=-DPB_TRACE): clock64 stamps of one CTA's MMA warp
+// and two softmax warps per block, read back with pb_debug_trace().
+#ifdef PB_TRACE
+__device__ long long pb_trace_buf[3 * 64 * 8];
+#define PB_TRACE_ON (blockIdx.x == 3 && blockIdx.y == 3 && blockIdx.z == 8)
+#define PB_TR(role, j, k) do { if (PB_TRACE_ON && (j) < 64) pb_trace_buf[((role) * 64 + (j)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define PB_TR(role, j, k) do { } while (0)
+#endif
+
 struct AttnParams {
   int B, H, Sq, Sk;
   int causal;
@@ -596,7 +606,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 constexpr int KB = 64;                          // keys per block in this kernel
 constexpr int KV_TILE_BYTES = KB * AT * 2;      // 16 KB: [64 keys x 128 head dims] as two 64-column halves of 8 KB
 constexpr int DS_TILE_BYTES = AT * KB * 2;      // 16 KB: [128 queries x 64 keys], one 128-byte row per query
-constexpr int NKV = 3;                          // K/V ring depth: a slot is released by the dQ MMA of block j and must
+constexpr int NKV = 4;                          // K/V ring depth: a slot is released by the dQ MMA of block j and must
                                                 // be refilled before S/dP of block j+NKV-1 is issued -> 3 gives a full block of slack
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -661,12 +671,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const uint32_t kt = aK + ks * KV_TILE_BYTES, vt = aV + ks * KV_TILE_BYTES;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {   // contraction over head_dim: 16 columns per step, halves 16 KB (Q/dO) / 8 KB (K/V) apart
+          // the S and dP chains are interleaved: back-to-back MMAs into the same accumulator serialise on it
           const uint64_t qd = make_smem_desc_sw128(aQ + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
           const uint64_t kd = make_smem_desc_sw128(kt + (kk >> 2) * (KV_TILE_BYTES / 2) + (kk & 3) * 32, 16, 1024);
           umma_bf16(tS0 + st * KB, qd, kd, idesc_s, kk > 0 ? 1u : 0u);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
           const uint64_t od = make_smem_desc_sw128(adO + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
           const uint64_t vd = make_smem_desc_sw128(vt + (kk >> 2) * (KV_TILE_BYTES / 2) + (kk & 3) * 32, 16, 1024);
           umma_bf16(tdP0 + st * KB, od, vd, idesc_s, kk > 0 ? 1u : 0u);
@@ -682,10 +690,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         if (j + 1 < nkb) {
           mbar_wait(&kv_full[(j + 1) % NKV], (uint32_t)((j + 1) / NKV) & 1);
           tc_fence_after();
+          PB_TR(0, j, 0);
           issue_sdp(j + 1);              // its TMEM buffers were drained before ds_full(j-1) fired
+          PB_TR(0, j, 1);
         }
         mbar_wait(&ds_full[st], (uint32_t)(j >> 1) & 1);
         tc_fence_after();
+        PB_TR(0, j, 2);
         const uint32_t dst = adS + st * DS_TILE_BYTES, kt = aK + (j % NKV) * KV_TILE_BYTES;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {   // contraction over the 64 keys of the block
@@ -695,6 +706,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         }
         umma_commit(&dq_done[st]);       // dS buffer st reusable
         umma_commit(&kv_empty[j % NKV]); // K/V ring slot reusable
+        PB_TR(0, j, 3);
       }
       umma_commit(&acc_full);
     }
@@ -727,14 +739,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     for (int j = 0; j < nkb; ++j) {
       const int kg0 = j * KB, st = j & 1;
       compute_bar_sync();                    // publishes bits(j); orders reuse of the other bitmap buffer
+      const int trole = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 1 : 2) : -1;
+      if (trole > 0) PB_TR(trole, j, 0);
       const uint32_t msk = qok ? chunk_mask(s_bits2[st][hf], p.causal != 0, qg, kg0 + hf * 32) : 0u;
       if (tid < KB) { publish(s_bits2[st ^ 1], kp_next); kp_next = keep_of((j + 2) * KB + tid); }
       mbar_wait(&sdp_full[st], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
+      if (trole > 0) PB_TR(trole, j, 1);
       uint32_t sv[32], dv[32];
       tmem_ld32(tS0 + st * KB + lane_addr + hf * 32, sv);
       tmem_ld32(tdP0 + st * KB + lane_addr + hf * 32, dv);
       tmem_ld_wait();
+      if (trole > 0) PB_TR(trole, j, 2);
       float ds[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -742,7 +758,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         if (msk != 0xffffffffu) pv = ((msk >> i) & 1u) ? pv : 0.f;
         ds[i] = pv * fmaf(__uint_as_float(dv[i]), p.scale, nDs);
       }
+      if (trole > 0) PB_TR(trole, j, 3);
       if (j >= 2) mbar_wait(&dq_done[st], (uint32_t)((j - 2) >> 1) & 1);   // dQ MMA of block j-2 released this buffer
+      if (trole > 0) PB_TR(trole, j, 4);
       {
         // row r of the [128 x 64] dS tile: 128 bytes, 16-byte chunks XOR-swizzled by (r & 7)
         uint8_t* rowp = gdS + st * DS_TILE_BYTES + r * 128;
@@ -758,6 +776,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&ds_full[st]);
+      if (trole > 0) PB_TR(trole, j, 5);
     }
     mbar_wait(&acc_full, 0);
     tc_fence_after();
@@ -898,3 +917,10 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
   attn_bwd_dq_kernel<<<g2, NTHREADS, smem2, stream>>>(tq, tk64, tv64, tdo, p);
   return pb_check_launch("attn_bwd_dq_kernel");
 }
+
+#ifdef PB_TRACE
+extern "C" int pb_debug_trace(long long* out, int n) {
+  if (n > 3 * 64 * 8) n = 3 * 64 * 8;
+  return cudaMemcpyFromSymbol(out, pb::pb_trace_buf, sizeof(long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -521,8 +521,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (p.drop.seed != nullptr) {
           const uint32_t key = pbdrop::site_key(*p.drop.seed, p.drop.op);
           const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col0;
+          if ((base & 31ull) == 0) {
+            const uint32_t bits = pbdrop::keep_bits<32>(key, base, p.drop.thresh);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = pbdrop::keep(key, base + j, p.drop.thresh) ? x[j] * p.drop.scale : 0.f;
+            for (int j = 0; j < 32; ++j) x[j] = ((bits >> j) & 1u) ? x[j] * p.drop.scale : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = pbdrop::keep(key, base + j, p.drop.thresh) ? x[j] * p.drop.scale : 0.f;
+          }
         }
         if (p.residual != nullptr && first_split && (row_ok || pf_res)) {
           if (res_f32) {

@@ -108,29 +108,59 @@ __global__ void __launch_bounds__(256) octuple_embed_bwd_kernel(const I* __restr
 
 // ------------------------------------------------------------------ LayerNorm (one warp per row)
 // MAXP = 16-byte packs per lane (d <= MAXP * 32 * pack width); the row lives in registers.
+template <typename T> struct RawPack;
+template <> struct RawPack<float> { typedef float4 type; };
+template <> struct RawPack<bf16> { typedef uint4 type; };
+__device__ __forceinline__ void unpack_raw(const float4& r, float (&f)[4]) { f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w; }
+__device__ __forceinline__ void unpack_raw(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+// gamma / beta live in registers for the whole kernel and the 16-byte loads of the warp's next row are in flight while
+// the current row is reduced; the optional output dropout site costs one hash per two elements (dropout.cuh).
 template <typename T, int MAXP>
 __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, T* __restrict__ y,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                             long long M, int d, float eps, pbdrop::Site drop) {
   constexpr int N = Pack<T>::N;
+  typedef typename RawPack<T>::type Raw;
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const uint32_t dkey = drop.seed ? pbdrop::site_key(*drop.seed, drop.op) : 0u;
-  for (long long row = warp_global; row < M; row += nwarps) {
-    const T* xr = x + row * d;
+  float ga[MAXP][N], be[MAXP][N];
+#pragma unroll
+  for (int k = 0; k < MAXP; ++k) {
+    const int c = (k * 32 + lane) * N;
+#pragma unroll
+    for (int j = 0; j < N; ++j) { ga[k][j] = c < d ? __ldg(gamma + c + j) : 0.f; be[k][j] = c < d ? __ldg(beta + c + j) : 0.f; }
+  }
+  Raw nx[MAXP];
+  auto fetch = [&](long long row) {
+#pragma unroll
+    for (int k = 0; k < MAXP; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < d) nx[k] = *reinterpret_cast<const Raw*>(x + row * d + c);
+    }
+  };
+  long long row = warp_global;
+  if (row < M) fetch(row);
+  for (; row < M; row += nwarps) {
     float v[MAXP][N];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
-        load_pack(xr + c, v[k]);
+        unpack_raw(nx[k], v[k]);
 #pragma unroll
         for (int j = 0; j < N; ++j) s += v[k][j];
       }
     }
+    if (row + nwarps < M) fetch(row + nwarps);
     const float mean = warp_sum(s) / d;
     float q = 0.f;
 #pragma unroll
@@ -153,11 +183,11 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
       if (c < d) {
         float o[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) o[j] = (v[k][j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
+        for (int j = 0; j < N; ++j) o[j] = (v[k][j] - mean) * rstd * ga[k][j] + be[k][j];
         if (drop.seed) {
+          const uint32_t bits = pbdrop::keep_bits<N>(dkey, (unsigned long long)row * d + c, drop.thresh);
 #pragma unroll
-          for (int j = 0; j < N; ++j)
-            o[j] = pbdrop::keep(dkey, (unsigned long long)row * d + c + j, drop.thresh) ? o[j] * drop.scale : 0.f;
+          for (int j = 0; j < N; ++j) o[j] = ((bits >> j) & 1u) ? o[j] * drop.scale : 0.f;
         }
         store_pack(yr + c, o);
       }
@@ -168,18 +198,10 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += dy*xhat, dbeta += dy,
 // dbias (optional) += dx  - the bias gradient of the Linear whose output (+ residual) fed this LayerNorm.
 constexpr int LNB_WARPS = 8;
-template <typename T> struct RawPack;
-template <> struct RawPack<float> { typedef float4 type; };
-template <> struct RawPack<bf16> { typedef uint4 type; };
-__device__ __forceinline__ void unpack_raw(const float4& r, float (&f)[4]) { f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w; }
-__device__ __forceinline__ void unpack_raw(const uint4& r, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-}
 
 // One warp per row, rows software-pipelined: the 16-byte loads of row r+1 are in flight while row r is reduced
-// (the kernel is latency-bound otherwise: 8 warps per SM because of the per-column accumulators in registers).
+// (8 warps per SM because of the per-column accumulators in registers).  gamma is staged in shared memory; the keep
+// bits of the input dropout site are generated once per row and reused by both passes.
 template <typename T, int MAXP>
 __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma,
@@ -190,13 +212,15 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
                                                             long long M, int d, pbdrop::Site din, pbdrop::Site dout) {
   constexpr int N = Pack<T>::N;
   typedef typename RawPack<T>::type Raw;
-  extern __shared__ float sh_red[];   // LNB_WARPS * d floats
+  extern __shared__ float sh_red[];   // LNB_WARPS * d floats (gamma occupies the first d until the final reduction)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t kin = din.seed ? pbdrop::site_key(*din.seed, din.op) : 0u;
   const uint32_t kout = dout.seed ? pbdrop::site_key(*dout.seed, dout.op) : 0u;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) sh_red[c] = gamma[c];
+  __syncthreads();
   float ag[MAXP][N], ab[MAXP][N], ax[MAXP][N];
 #pragma unroll
   for (int k = 0; k < MAXP; ++k)
@@ -219,55 +243,53 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
   long long row = warp_global;
   if (row < M) fetch(row);
   for (; row < M; row += nwarps) {
-    Raw cx[MAXP], cdy[MAXP];
-#pragma unroll
-    for (int k = 0; k < MAXP; ++k) { cx[k] = rx[k]; cdy[k] = rdy[k]; }
+    float xh[MAXP][N], g[MAXP][N];     // normalised input and dy * gamma of this lane's columns
     const float cm = mean, cr = rstd;
-    if (row + nwarps < M) fetch(row + nwarps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
-        float xv[N], dv[N];
-        unpack_raw(cx[k], xv);
-        unpack_raw(cdy[k], dv);
+        float dv[N], gm[N];
+        unpack_raw(rx[k], xh[k]);
+        unpack_raw(rdy[k], dv);
+#pragma unroll
+        for (int j = 0; j < N; j += 4) *reinterpret_cast<float4*>(&gm[j]) = *reinterpret_cast<const float4*>(&sh_red[c + j]);
+        if (din.seed) {
+          const uint32_t bits = pbdrop::keep_bits<N>(kin, (unsigned long long)row * d + c, din.thresh);
+#pragma unroll
+          for (int j = 0; j < N; ++j) dv[j] = ((bits >> j) & 1u) ? dv[j] * din.scale : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          if (din.seed) dv[j] = pbdrop::keep(kin, (unsigned long long)row * d + c + j, din.thresh) ? dv[j] * din.scale : 0.f;
-          const float xh = (xv[j] - cm) * cr;
-          const float g = dv[j] * __ldg(gamma + c + j);
-          s1 += g;
-          s2 += g * xh;
-          ag[k][j] += dv[j] * xh;
+          xh[k][j] = (xh[k][j] - cm) * cr;
+          g[k][j] = dv[j] * gm[j];
+          s1 += g[k][j];
+          s2 = fmaf(g[k][j], xh[k][j], s2);
+          ag[k][j] = fmaf(dv[j], xh[k][j], ag[k][j]);
           ab[k][j] += dv[j];
         }
       }
     }
+    if (row + nwarps < M) fetch(row + nwarps);
     s1 = warp_sum(s1) / d;
     s2 = warp_sum(s2) / d;
 #pragma unroll
     for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
-        float xv[N], dv[N], o[N];
-        unpack_raw(cx[k], xv);
-        unpack_raw(cdy[k], dv);
+        float o[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          if (din.seed) dv[j] = pbdrop::keep(kin, (unsigned long long)row * d + c + j, din.thresh) ? dv[j] * din.scale : 0.f;
-          const float xh = (xv[j] - cm) * cr;
-          o[j] = cr * (dv[j] * __ldg(gamma + c + j) - s1 - xh * s2);
-        }
+        for (int j = 0; j < N; ++j) o[j] = cr * (g[k][j] - s1 - xh[k][j] * s2);
         store_pack(dx + row * d + c, o);
         if (dout.seed) {  // gradient of the dropped-out Linear output that (plus the residual) fed this LayerNorm
+          const uint32_t bits = pbdrop::keep_bits<N>(kout, (unsigned long long)row * d + c, dout.thresh);
 #pragma unroll
-          for (int j = 0; j < N; ++j)
-            o[j] = pbdrop::keep(kout, (unsigned long long)row * d + c + j, dout.thresh) ? o[j] * dout.scale : 0.f;
+          for (int j = 0; j < N; ++j) o[j] = ((bits >> j) & 1u) ? o[j] * dout.scale : 0.f;
           store_pack(dx_drop + row * d + c, o);
         }
 #pragma unroll
-        for (int j = 0; j < N; ++j) ax[k][j] += o[j];
+        for (int j = 0; j < N; ++j) ax[k][j] += o[j];     // the Linear's bias sits inside the dropout: its gradient sums the dropped dx
       }
     }
   }

