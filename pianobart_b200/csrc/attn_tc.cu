@@ -210,16 +210,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
           mbar_wait(&k_full[st], (uint32_t)((j + 1) >> 1) & 1);
           tc_fence_after();
           // buffer st was last read by the softmax of block j-1, which finished before p_full(j-1) fired
+          PB_TR(0, j, 0);
           mma_tile<false, false>(tS0 + st * 128, sm.a[0], sm.a[1 + st], false);   // S(j+1), overlaps softmax(j)
           umma_commit(&s_full[st]);
           umma_commit(&k_empty[st]);
+          PB_TR(0, j, 1);
         }
         mbar_wait(&p_full, j & 1);
         mbar_wait(&v_full[j & 1], (uint32_t)(j >> 1) & 1);
         tc_fence_after();
+        PB_TR(0, j, 2);
         mma_tile<false, true>(tO, sm.a[5], sm.a[3 + (j & 1)], j > 0);        // O += P V   (V as MN-major B)
         umma_commit(&pv_done);
         umma_commit(&v_empty[j & 1]);
+        PB_TR(0, j, 3);
       }
     }
   } else {
@@ -241,8 +245,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       uint32_t msk[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) msk[c] = chunk_mask(s_bits2[j & 1][hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32);
+      const int trole = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 1 : 2) : -1;
+      if (trole > 0) PB_TR(trole, j, 0);
       mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
+      if (trole > 0) PB_TR(trole, j, 1);
       const uint32_t tS = tS0 + (j & 1) * 128;
       float t[64];                     // raw scores (masked entries = -inf); the scale is folded into the exp2 FFMA
       float bm = -INFINITY;
@@ -273,7 +280,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       s_red[hf][r] = bm;
       publish_keep_bits(s_bits2[(j + 1) & 1], kp_next, tid);
       kp_next = load_keep(p, b, (j + 2) * AT + tid, tid);
+      if (trole > 0) PB_TR(trole, j, 2);
       compute_bar_sync();
+      if (trole > 0) PB_TR(trole, j, 3);
       bm = fmaxf(s_red[0][r], s_red[1][r]);
       // lazy rescale: keep the old reference unless the maximum grew by more than 2^8
       float f = 1.0f;
@@ -317,7 +326,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         rs1 += __uint_as_float(u & 0xffff0000u);
       }
       l += rs0 + rs1;
+      if (trole > 0) PB_TR(trole, j, 4);
       if (j > 0 && !waited_pv) mbar_wait(&pv_done, (j - 1) & 1);   // P buffer is free once P V (j-1) retired
+      if (trole > 0) PB_TR(trole, j, 5);
       {
         // this thread's 64 columns = one 128-byte row of the tile half hf: 16-byte chunks XOR-swizzled by (r & 7)
         uint8_t* rowp = sm.t[5] + hf * HALF_BYTES + r * 128;
@@ -328,6 +339,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full);
+      if (trole > 0) PB_TR(trole, j, 6);
     }
     mbar_wait(&pv_done, (nkb - 1) & 1);
     tc_fence_after();
@@ -364,29 +376,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 
 // ===================================================================================== backward: dK, dV
 // Transposed formulation so that 64-query blocks keep every MMA at M = 128:  S^T = K Q^T and dP^T = V dO^T are
-// [128 keys x 64 queries] (TMEM lane = key), P^T / dS^T go to shared memory K-major and feed dV += P^T dO, dK += dS^T Q
-// with the 64-row Q / dO tiles as MN-major B operands.  Q/dO stream through a 3-deep ring, S^T/dP^T and P^T/dS^T are
-// double-buffered: TMA, the tensor pipe and the softmax warps overlap instead of taking turns (the v1 kernel spent 43%
-// of its samples waiting on the S/dP barrier, profiles/r1_summary.md).
+// [128 keys x 64 queries] (TMEM lane = key); P^T / dS^T are written back (bf16, packed) over the S^T / dP^T columns they
+// were derived from and feed dV += P^T dO, dK += dS^T Q as A operands from TMEM, with the 64-row Q / dO tiles as MN-major
+// B operands - no shared-memory round trip.  Q/dO stream through a 5-deep ring (a TMA refill takes > 1500 cycles under
+// load), S^T/dP^T are double-buffered: TMA, the tensor pipe and the softmax warps overlap instead of taking turns (the
+// v1 kernel spent 43% of its samples waiting on the S/dP barrier, profiles/r1_summary.md).
 constexpr int QB = 64;                          // queries per block in this kernel
 constexpr int QT_BYTES = QB * AT * 2;           // 16 KB: [64 queries x 128 head dims], two 64-column halves of 8 KB
-constexpr int PT_BYTES = AT * QB * 2;           // 16 KB: [128 keys x 64 queries], one 128-byte row per key
-constexpr int NQ = 3;                           // Q/dO ring depth
+constexpr int NQ = 5;                           // Q/dO ring depth
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                     const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t kv_full, qdo_full[NQ], qdo_empty[NQ], sdp_full[2], pds_full[2], pds_done[2], acc_full;
+  __shared__ __align__(8) uint64_t kv_full, qdo_full[NQ], qdo_empty[NQ], sdp_full[2], pds_full[2], acc_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_L[2][QB], s_D[2][QB];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  // layout: K 32K | V 32K | Q ring NQ x 16K | dO ring NQ x 16K | P^T[2] 16K each | dS^T[2] 16K each
-  const uint32_t aK = base, aV = base + TILE_BYTES, aQ = base + 2 * TILE_BYTES, adO = aQ + NQ * QT_BYTES,
-                 aP = adO + NQ * QT_BYTES, adS = aP + 2 * PT_BYTES;
+  // layout: K 32K | V 32K | Q ring NQ x 16K | dO ring NQ x 16K
+  const uint32_t aK = base, aV = base + TILE_BYTES, aQ = base + 2 * TILE_BYTES, adO = aQ + NQ * QT_BYTES;
   uint8_t* gK = gen; uint8_t* gV = gen + TILE_BYTES; uint8_t* gQ = gen + 2 * TILE_BYTES; uint8_t* gdO = gQ + NQ * QT_BYTES;
-  uint8_t* gP = gdO + NQ * QT_BYTES; uint8_t* gdS = gP + 2 * PT_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int k0 = kb * AT;
@@ -398,7 +408,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   if (warp == 1 && lane == 0) {
     mbar_init(&kv_full, 1); mbar_init(&acc_full, 1);
     for (int i = 0; i < NQ; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&pds_full[i], NCOMPUTE); mbar_init(&pds_done[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&pds_full[i], NCOMPUTE); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -457,25 +467,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         if (it + 1 < niter) {
           mbar_wait(&qdo_full[(it + 1) % NQ], (uint32_t)((it + 1) / NQ) & 1);
           tc_fence_after();
-          issue_sdp(it + 1);             // its TMEM buffers were drained before pds_full(it-1) fired
-        }
+          issue_sdp(it + 1);             // its TMEM buffers held P^T / dS^T of block it-1: read by the dV / dK MMAs
+        }                                // of block it-1, which precede these in the in-order tensor pipe
         mbar_wait(&pds_full[st], (uint32_t)(it >> 1) & 1);
         tc_fence_after();
-        const uint32_t pt = aP + st * PT_BYTES, dst = adS + st * PT_BYTES;
         const uint32_t qt = aQ + (it % NQ) * QT_BYTES, ot = adO + (it % NQ) * QT_BYTES;
+        // A operands from TMEM: query 16*kk.. of the block = packed columns (kk >> 1) * 32 + (kk & 1) * 8 of buffer st
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {   // contraction over the 64 queries of the block
-          const uint64_t ad = make_smem_desc_sw128(pt + kk * 32, 16, 1024);                 // P^T: K-major
-          const uint64_t bd = make_smem_desc_sw128(ot + kk * 2048, QT_BYTES / 2, 1024);     // dO: MN-major
-          umma_bf16(tdV, ad, bd, idesc_a, (it > 0 || kk > 0) ? 1u : 0u);
+          const uint32_t acol = (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8);
+          const uint64_t bo = make_smem_desc_sw128(ot + kk * 2048, QT_BYTES / 2, 1024);     // dO: MN-major
+          umma_bf16_ts(tdV, tS0 + st * QB + acol, bo, idesc_a, (it > 0 || kk > 0) ? 1u : 0u);
+          const uint64_t bq = make_smem_desc_sw128(qt + kk * 2048, QT_BYTES / 2, 1024);     // Q: MN-major
+          umma_bf16_ts(tdK, tdP0 + st * QB + acol, bq, idesc_a, (it > 0 || kk > 0) ? 1u : 0u);
         }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t ad = make_smem_desc_sw128(dst + kk * 32, 16, 1024);                // dS^T: K-major
-          const uint64_t bd = make_smem_desc_sw128(qt + kk * 2048, QT_BYTES / 2, 1024);     // Q: MN-major
-          umma_bf16(tdK, ad, bd, idesc_a, (it > 0 || kk > 0) ? 1u : 0u);
-        }
-        umma_commit(&pds_done[st]);          // P^T / dS^T buffer st reusable
         umma_commit(&qdo_empty[it % NQ]);    // Q / dO ring slot reusable
       }
       umma_commit(&acc_full);
@@ -538,27 +543,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           ds[i] = pv * fmaf(__uint_as_float(dv[i]), p.scale, dd[t]);
         }
       }
-      if (it >= 2) mbar_wait(&pds_done[st], (uint32_t)((it - 2) >> 1) & 1);   // MMAs of block it-2 released this buffer
       {
-        // row r of the [128 x 64] P^T / dS^T tiles: 128 bytes, 16-byte chunks XOR-swizzled by (r & 7)
-        uint8_t* prow = gP + st * PT_BYTES + r * 128;
-        uint8_t* drow = gdS + st * PT_BYTES + r * 128;
+        // P^T / dS^T of this thread's 32 queries: 16 packed columns over the S^T / dP^T columns it has just consumed
+        uint32_t pp[16], pd[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v4, w4;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v4);
-          __nv_bfloat162* g2 = reinterpret_cast<__nv_bfloat162*>(&w4);
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt) {
-            h2[tt] = __floats2bfloat162_rn(pr[g * 8 + 2 * tt], pr[g * 8 + 2 * tt + 1]);
-            g2[tt] = __floats2bfloat162_rn(ds[g * 8 + 2 * tt], ds[g * 8 + 2 * tt + 1]);
-          }
-          const int off = ((hf * 4 + g) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(prow + off) = v4;
-          *reinterpret_cast<uint4*>(drow + off) = w4;
+        for (int i = 0; i < 16; ++i) {
+          const __nv_bfloat162 a2 = __floats2bfloat162_rn(pr[2 * i], pr[2 * i + 1]);
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(ds[2 * i], ds[2 * i + 1]);
+          pp[i] = *reinterpret_cast<const uint32_t*>(&a2);
+          pd[i] = *reinterpret_cast<const uint32_t*>(&b2);
         }
+        tmem_st16(tS0 + st * QB + lane_addr + hf * 32, pp);
+        tmem_st16(tdP0 + st * QB + lane_addr + hf * 32, pd);
+        tmem_st_wait();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&pds_full[st]);
     }
@@ -601,39 +599,43 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 }
 
 // ===================================================================================== backward: dQ
-// 64-key blocks, K/V tiles and the S / dP accumulators double-buffered: the MMA warp computes S, dP of block j+1 while
-// the softmax warps turn block j into dS, and TMA streams block j+2 - the three engines overlap instead of taking turns.
-constexpr int KB = 64;                          // keys per block in this kernel
-constexpr int KV_TILE_BYTES = KB * AT * 2;      // 16 KB: [64 keys x 128 head dims] as two 64-column halves of 8 KB
-constexpr int DS_TILE_BYTES = AT * KB * 2;      // 16 KB: [128 queries x 64 keys], one 128-byte row per query
-constexpr int NKV = 4;                          // K/V ring depth: a slot is released by the dQ MMA of block j and must
-                                                // be refilled before S/dP of block j+NKV-1 is issued -> 3 gives a full block of slack
-
+// Every tcgen05.mma (M = 128, K = 16) occupies the tensor pipe for max(~72, N/2) cycles (tools/micro/mma_bench.cu), so
+// all products use N = 128: 128-key blocks, 24 MMAs per block.  S is double-buffered in TMEM, dP single-buffered but
+// released as soon as the softmax warps hold it in registers, and dS never touches shared memory: it is written (bf16,
+// packed) over the S buffer it was derived from and feeds dQ += dS K as the A operand from TMEM:
+//   tensor pipe :  S(j+1)  dP(j+1)  dQ(j)   S(j+2) ...          softmax warps :  block j -> dS(j)   block j+1 ...
+// K streams through a three-deep ring (a slot is held from S(j) to dQ(j), and a TMA refill takes ~1500 cycles), V through a
+// two-deep ring (released after dP).
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t qdo_full, kv_full[NKV], kv_empty[NKV], sdp_full[2], ds_full[2], dq_done[2], acc_full;
+  __shared__ __align__(8) uint64_t qdo_full, k_full[3], k_empty[3], v_full[2], v_empty[2], s_full[2], dp_full, dp_free, ds_full,
+      acc_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t s_bits2[2][2];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  // layout: Q 32K | dO 32K | K ring NKV x 16K | V ring NKV x 16K | dS0 16K | dS1 16K
-  const uint32_t aQ = base, adO = base + TILE_BYTES, aK = base + 2 * TILE_BYTES, aV = aK + NKV * KV_TILE_BYTES,
-                 adS = aV + NKV * KV_TILE_BYTES;
-  uint8_t* gQ = gen; uint8_t* gdO = gen + TILE_BYTES; uint8_t* gK = gen + 2 * TILE_BYTES; uint8_t* gV = gK + NKV * KV_TILE_BYTES;
-  uint8_t* gdS = gV + NKV * KV_TILE_BYTES;
+  __shared__ uint32_t s_bits2[2][4];
+  Smem4 sm;
+  {
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    for (int i = 0; i < 6; ++i) { sm.t[i] = gen + i * TILE_BYTES; sm.a[i] = base + i * TILE_BYTES; }
+  }
+  // tiles: 0 Q, 1 dO, 2-4 K ring, 5-6 V ring
+  constexpr int NK = 3;
+  uint8_t* gV = sm.t[5];
+  const uint32_t aV = sm.a[5];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * AT;
-  int nkb = (p.Sk + KB - 1) / KB;
-  if (p.causal) nkb = min(nkb, (q0 + AT + KB - 1) / KB);   // key blocks that intersect keys <= last query of the tile
+  int nkb = (p.Sk + AT - 1) / AT;
+  if (p.causal) nkb = min(nkb, qb + 1);
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); }
   if (warp == 1 && lane == 0) {
-    mbar_init(&qdo_full, 1); mbar_init(&acc_full, 1);
-    for (int i = 0; i < NKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&ds_full[i], NCOMPUTE); mbar_init(&dq_done[i], 1); }
+    mbar_init(&qdo_full, 1); mbar_init(&acc_full, 1); mbar_init(&dp_full, 1);
+    mbar_init(&dp_free, NCOMPUTE); mbar_init(&ds_full, NCOMPUTE);
+    for (int i = 0; i < NK; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); mbar_init(&s_full[i], 1); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -641,71 +643,66 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
-  // TMEM columns: S[2] at 0/64, dP[2] at 128/192, dQ at 256
-  const uint32_t tS0 = tmem, tdP0 = tmem + 128, tdQ = tmem + 256;
+  const uint32_t tS0 = tmem, tdP = tmem + 256, tdQ = tmem + 384;   // S buffers at columns 0 / 128
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(&qdo_full, 2 * TILE_BYTES);
-      load_tile(gQ, &tq, &qdo_full, q0, h, b);
-      load_tile(gdO, &tdo, &qdo_full, q0, h, b);
+      load_tile(sm.t[0], &tq, &qdo_full, q0, h, b);
+      load_tile(sm.t[1], &tdo, &qdo_full, q0, h, b);
       for (int j = 0; j < nkb; ++j) {
-        const int st = j % NKV;
-        mbar_wait(&kv_empty[st], ((uint32_t)(j / NKV) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * KV_TILE_BYTES);
-        // the K/V tensor maps use 128-row boxes; a 64-key block is loaded as two (64 col x 64 row) halves per tensor:
-        // rows beyond the block are simply not requested (box rows fixed at 128 would over-read) -> use the kv64 maps
-        tma_load_4d(gK + st * KV_TILE_BYTES, &tk, &kv_full[st], 0, j * KB, h, b);
-        tma_load_4d(gK + st * KV_TILE_BYTES + KV_TILE_BYTES / 2, &tk, &kv_full[st], 64, j * KB, h, b);
-        tma_load_4d(gV + st * KV_TILE_BYTES, &tv, &kv_full[st], 0, j * KB, h, b);
-        tma_load_4d(gV + st * KV_TILE_BYTES + KV_TILE_BYTES / 2, &tv, &kv_full[st], 64, j * KB, h, b);
+        const int ks = j % NK, vs = j & 1;
+        mbar_wait(&k_empty[ks], ((uint32_t)(j / NK) & 1) ^ 1);
+        mbar_expect_tx(&k_full[ks], TILE_BYTES);
+        load_tile(sm.t[2 + ks], &tk, &k_full[ks], j * AT, h, b);
+        mbar_wait(&v_empty[vs], ((uint32_t)(j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&v_full[vs], TILE_BYTES);
+        load_tile(gV + vs * TILE_BYTES, &tv, &v_full[vs], j * AT, h, b);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(AT, KB, 0, 0);     // [128 q x 64 keys], both operands K-major
-      constexpr uint32_t idesc_q = make_idesc_bf16(AT, AT, 0, 1);     // dQ [128 q x 128 hd], B = K tile MN-major
-      auto issue_sdp = [&](int j) {
-        const int st = j & 1;                       // TMEM buffer
-        const int ks = j % NKV;                     // K/V ring slot
-        const uint32_t kt = aK + ks * KV_TILE_BYTES, vt = aV + ks * KV_TILE_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {   // contraction over head_dim: 16 columns per step, halves 16 KB (Q/dO) / 8 KB (K/V) apart
-          // the S and dP chains are interleaved: back-to-back MMAs into the same accumulator serialise on it
-          const uint64_t qd = make_smem_desc_sw128(aQ + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
-          const uint64_t kd = make_smem_desc_sw128(kt + (kk >> 2) * (KV_TILE_BYTES / 2) + (kk & 3) * 32, 16, 1024);
-          umma_bf16(tS0 + st * KB, qd, kd, idesc_s, kk > 0 ? 1u : 0u);
-          const uint64_t od = make_smem_desc_sw128(adO + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
-          const uint64_t vd = make_smem_desc_sw128(vt + (kk >> 2) * (KV_TILE_BYTES / 2) + (kk & 3) * 32, 16, 1024);
-          umma_bf16(tdP0 + st * KB, od, vd, idesc_s, kk > 0 ? 1u : 0u);
-        }
-        umma_commit(&sdp_full[st]);
-      };
       mbar_wait(&qdo_full, 0);
-      mbar_wait(&kv_full[0], 0);
+      mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_sdp(0);
+      mma_tile<false, false>(tS0, sm.a[0], sm.a[2], false);                 // S(0) = Q K(0)^T
+      umma_commit(&s_full[0]);
+      mbar_wait(&v_full[0], 0);
+      tc_fence_after();
+      mma_tile<false, false>(tdP, sm.a[1], aV, false);                      // dP(0) = dO V(0)^T
+      umma_commit(&dp_full);
+      umma_commit(&v_empty[0]);
       for (int j = 0; j < nkb; ++j) {
-        const int st = j & 1;
+        const int st = j & 1, nx = st ^ 1;
+        const uint32_t ph = (uint32_t)j & 1;
         if (j + 1 < nkb) {
-          mbar_wait(&kv_full[(j + 1) % NKV], (uint32_t)((j + 1) / NKV) & 1);
+          mbar_wait(&k_full[(j + 1) % NK], (uint32_t)((j + 1) / NK) & 1);
           tc_fence_after();
           PB_TR(0, j, 0);
-          issue_sdp(j + 1);              // its TMEM buffers were drained before ds_full(j-1) fired
+          // S buffer nx held S(j-1) / dS(j-1): read by dQ(j-1), which precedes this MMA in the in-order tensor pipe
+          mma_tile<false, false>(tS0 + nx * AT, sm.a[0], sm.a[2 + (j + 1) % NK], false);   // S(j+1)
+          umma_commit(&s_full[nx]);
+          mbar_wait(&dp_free, ph);                                            // softmax(j) holds dP(j) in registers
+          mbar_wait(&v_full[nx], (uint32_t)((j + 1) >> 1) & 1);
+          tc_fence_after();
           PB_TR(0, j, 1);
+          mma_tile<false, false>(tdP, sm.a[1], aV + nx * TILE_BYTES, false);  // dP(j+1)
+          umma_commit(&dp_full);
+          umma_commit(&v_empty[nx]);
         }
-        mbar_wait(&ds_full[st], (uint32_t)(j >> 1) & 1);
+        mbar_wait(&ds_full, ph);
         tc_fence_after();
         PB_TR(0, j, 2);
-        const uint32_t dst = adS + st * DS_TILE_BYTES, kt = aK + (j % NKV) * KV_TILE_BYTES;
+        {
+          // dQ += dS K: A = dS from TMEM (packed bf16 over S buffer st: key half 0 at columns 0-31, half 1 at 64-95),
+          // B = K tile as MN-major operand
+          constexpr uint32_t idesc = make_idesc_bf16(AT, AT, 0, 1);
+          const uint32_t kt = sm.a[2 + j % NK];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {   // contraction over the 64 keys of the block
-          const uint64_t ad = make_smem_desc_sw128(dst + kk * 32, 16, 1024);                          // dS: K-major
-          const uint64_t bd = make_smem_desc_sw128(kt + kk * 2048, KV_TILE_BYTES / 2, 1024);          // K: MN-major
-          umma_bf16(tdQ, ad, bd, idesc_q, (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ts(tdQ, tS0 + st * AT + (kk >> 2) * 64 + (kk & 3) * 8, desc_mnmajor(kt, kk), idesc, (j > 0 || kk > 0) ? 1u : 0u);
         }
-        umma_commit(&dq_done[st]);       // dS buffer st reusable
-        umma_commit(&kv_empty[j % NKV]); // K/V ring slot reusable
+        umma_commit(&k_empty[j % NK]);                                        // K ring slot reusable
         PB_TR(0, j, 3);
       }
       umma_commit(&acc_full);
@@ -713,7 +710,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   } else {
     const int cw = warp - 2;
     const int quad = warp & 3;
-    const int hf = cw >> 2;                  // 32-column half of the 64-key block
+    const int hf = cw >> 2;                  // 64-column half of the key block handled by this thread
     const int r = quad * 32 + lane;
     const int tid = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -723,69 +720,63 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const long long ridx = ((long long)b * p.H + h) * p.Sq + qg;
     const float negL = qok ? -p.lse[ridx] : -INFINITY;
     const float nDs = qok ? -p.dvec[ridx] * p.scale : 0.f;
-    auto keep_of = [&](int kc) {
-      bool kp = kc < p.Sk;
-      if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc] != 0;
-      return kp;
-    };
-    auto publish = [&](uint32_t* dst, bool kp) {
-      if (tid < KB) {
-        const uint32_t w = __ballot_sync(0xffffffffu, kp);
-        if ((tid & 31) == 0) dst[tid >> 5] = w;
-      }
-    };
-    bool kp_next = false;
-    if (tid < KB) { publish(s_bits2[0], keep_of(tid)); kp_next = keep_of(KB + tid); }
+    publish_keep_bits(s_bits2[0], load_keep(p, b, tid, tid), tid);
+    bool kp_next = load_keep(p, b, AT + tid, tid);
     for (int j = 0; j < nkb; ++j) {
-      const int kg0 = j * KB, st = j & 1;
+      const int kg0 = j * AT, st = j & 1;
+      const uint32_t ph = (uint32_t)j & 1;
       compute_bar_sync();                    // publishes bits(j); orders reuse of the other bitmap buffer
       const int trole = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 1 : 2) : -1;
       if (trole > 0) PB_TR(trole, j, 0);
-      const uint32_t msk = qok ? chunk_mask(s_bits2[st][hf], p.causal != 0, qg, kg0 + hf * 32) : 0u;
-      if (tid < KB) { publish(s_bits2[st ^ 1], kp_next); kp_next = keep_of((j + 2) * KB + tid); }
-      mbar_wait(&sdp_full[st], (uint32_t)(j >> 1) & 1);
+      uint32_t msk[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) msk[c] = qok ? chunk_mask(s_bits2[st][hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32) : 0u;
+      publish_keep_bits(s_bits2[st ^ 1], kp_next, tid);
+      kp_next = load_keep(p, b, (j + 2) * AT + tid, tid);
+      mbar_wait(&s_full[st], (uint32_t)(j >> 1) & 1);
+      mbar_wait(&dp_full, ph);
       tc_fence_after();
       if (trole > 0) PB_TR(trole, j, 1);
-      uint32_t sv[32], dv[32];
-      tmem_ld32(tS0 + st * KB + lane_addr + hf * 32, sv);
-      tmem_ld32(tdP0 + st * KB + lane_addr + hf * 32, dv);
+      uint32_t dv[2][32];
+      tmem_ld32(tdP + lane_addr + hf * 64, dv[0]);
+      tmem_ld32(tdP + lane_addr + hf * 64 + 32, dv[1]);
       tmem_ld_wait();
-      if (trole > 0) PB_TR(trole, j, 2);
-      float ds[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float pv = ex2(fmaf(__uint_as_float(sv[i]), sl2, negL));
-        if (msk != 0xffffffffu) pv = ((msk >> i) & 1u) ? pv : 0.f;
-        ds[i] = pv * fmaf(__uint_as_float(dv[i]), p.scale, nDs);
-      }
-      if (trole > 0) PB_TR(trole, j, 3);
-      if (j >= 2) mbar_wait(&dq_done[st], (uint32_t)((j - 2) >> 1) & 1);   // dQ MMA of block j-2 released this buffer
-      if (trole > 0) PB_TR(trole, j, 4);
-      {
-        // row r of the [128 x 64] dS tile: 128 bytes, 16-byte chunks XOR-swizzled by (r & 7)
-        uint8_t* rowp = gdS + st * DS_TILE_BYTES + r * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v4;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v4);
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt) h2[tt] = __floats2bfloat162_rn(ds[g * 8 + 2 * tt], ds[g * 8 + 2 * tt + 1]);
-          *reinterpret_cast<uint4*>(rowp + (((hf * 4 + g) ^ (r & 7)) << 4)) = v4;
-        }
-      }
-      fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&ds_full[st]);
+      mbar_arrive(&dp_free);                 // dP(j) is in registers: the tensor pipe may overwrite it with dP(j+1)
+      if (trole > 0) PB_TR(trole, j, 2);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32];
+        tmem_ld32(tS0 + st * AT + lane_addr + hf * 64 + c * 32, sv);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, negL)), p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, negL));
+          if (msk[c] != 0xffffffffu) {
+            p0 = ((msk[c] >> (2 * i)) & 1u) ? p0 : 0.f;
+            p1 = ((msk[c] >> (2 * i + 1)) & 1u) ? p1 : 0.f;
+          }
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0 * fmaf(__uint_as_float(dv[c][2 * i]), p.scale, nDs),
+                                                          p1 * fmaf(__uint_as_float(dv[c][2 * i + 1]), p.scale, nDs));
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        if (c == 0 && trole > 0) PB_TR(trole, j, 3);
+        // dS chunk (32 keys = 16 packed columns) over the S columns this thread has already consumed
+        tmem_st16(tS0 + st * AT + lane_addr + hf * 64 + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&ds_full);
       if (trole > 0) PB_TR(trole, j, 5);
     }
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    const int hq = cw >> 2;                  // 64-column half of head_dim written by this thread
-    __nv_bfloat16* dst = p.dq + (long long)b * p.dq_sb + (long long)qg * p.lddq + h * AT + hq * 64;
+    __nv_bfloat16* dst = p.dq + (long long)b * p.dq_sb + (long long)qg * p.lddq + h * AT + hf * 64;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(tdQ + lane_addr + hq * 64 + c * 32, v);
+      tmem_ld32(tdQ + lane_addr + hf * 64 + c * 32, v);
       tmem_ld_wait();
       if (qok) {
 #pragma unroll
@@ -901,7 +892,7 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
     if (pb_check_launch("attn_bwd_prep_kernel")) return -1;
   }
   static bool attr1 = false, attr2 = false;
-  const int smem1 = 2 * TILE_BYTES + 2 * NQ * QT_BYTES + 4 * PT_BYTES + 1024, smem2 = 2 * TILE_BYTES + 2 * NKV * KV_TILE_BYTES + 2 * DS_TILE_BYTES + 1024;
+  const int smem1 = 2 * TILE_BYTES + 2 * NQ * QT_BYTES + 1024, smem2 = 7 * TILE_BYTES + 1024;
   if (set_smem(attn_bwd_dkv_kernel, smem1, attr1)) return -1;
   if (set_smem(attn_bwd_dq_kernel, smem2, attr2)) return -1;
   CUtensorMap tq64, tdo64;   // 64-query boxes for the dK/dV kernel
@@ -910,11 +901,8 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
   dim3 g1((d->Sk + AT - 1) / AT, d->H, d->B);
   attn_bwd_dkv_kernel<<<g1, NTHREADS, smem1, stream>>>(tq64, tk, tv, tdo64, p);
   if (pb_check_launch("attn_bwd_dkv_kernel")) return -1;
-  CUtensorMap tk64, tv64;   // 64-key boxes for the dQ kernel
-  if (attn_tmap(&tk64, d->k, d->Sk, d->ldk, d->H, d->B, (long long)d->Sk * d->ldk, KB)) return -1;
-  if (attn_tmap(&tv64, d->v, d->Sk, d->ldv, d->H, d->B, (long long)d->Sk * d->ldv, KB)) return -1;
   dim3 g2((d->Sq + AT - 1) / AT, d->H, d->B);
-  attn_bwd_dq_kernel<<<g2, NTHREADS, smem2, stream>>>(tq, tk64, tv64, tdo, p);
+  attn_bwd_dq_kernel<<<g2, NTHREADS, smem2, stream>>>(tq, tk, tv, tdo, p);
   return pb_check_launch("attn_bwd_dq_kernel");
 }
 
