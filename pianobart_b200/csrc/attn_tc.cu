@@ -142,22 +142,27 @@ __device__ __forceinline__ void carve(uint8_t* raw, Smem4& s, int n) {
 }
 
 // ===================================================================================== forward
-// Software-pipelined: the MMA warp issues S(j+1) = Q K(j+1)^T (second TMEM buffer, double-buffered K/V tiles) while
-// the softmax warps work on S(j); the output accumulates in TMEM across key blocks (O += P V) and is only rescaled
-// when the running row maximum grows by more than 2^8 ("lazy rescale"), so the per-block critical path of the softmax
-// warps is  ld S -> max -> exp2 -> P to smem -> arrive  with no accumulator round trip.
+// The tensor pipe runs S = Q K^T two key blocks ahead of the softmax (three S buffers in TMEM, three-deep K ring), so
+// that while the softmax warps exponentiate block j - a MUFU-bound stretch - the same instruction stream also takes
+// the masked row maximum of block j+1 straight out of TMEM.  P(j) is written back (bf16, packed) over the S(j) columns
+// it was computed from and feeds O += P V as the A operand from TMEM: no shared-memory tile, no proxy fence, no wait
+// for the previous P V.  O accumulates in TMEM across key blocks and is only rescaled when the running row maximum
+// grows by more than 2^8 ("lazy rescale").  Per block the softmax warps' critical path is
+//   exchange max (one named barrier) -> [ld S(j), S(j+1) -> exp2 / max -> st P(j)] x 2 chunks -> arrive.
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 domain: probabilities stay <= 256 between rescales
+constexpr int NSBUF = 3;                    // S buffers in TMEM / K ring depth
+constexpr int FWD_MAX_SK = 8192;            // keys per sequence supported by the in-kernel key-padding bitmap
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                 const __grid_constant__ CUtensorMap tv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, k_full[2], v_full[2], k_empty[2], v_empty[2], s_full[2], p_full, pv_done;
+  __shared__ __align__(8) uint64_t q_full, k_full[NSBUF], k_empty[NSBUF], v_full[2], v_empty[2], s_full[NSBUF], p_full, pv_done;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t s_bits2[2][4];
-  __shared__ float s_red[2][AT];
+  __shared__ uint32_t s_keep[FWD_MAX_SK / 32];   // key-padding bitmap of the whole key sequence (built once)
+  __shared__ float s_red[2][2][AT];
   Smem4 sm;
-  carve(smem_raw, sm, 6);  // 0 Q, 1-2 K ring, 3-4 V ring, 5 P
+  carve(smem_raw, sm, 6);  // 0 Q, 1-3 K ring, 4-5 V ring
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * AT;
@@ -167,10 +172,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); }
   if (warp == 1 && lane == 0) {
     mbar_init(&q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-    }
+    for (int i = 0; i < NSBUF; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&s_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     mbar_init(&p_full, NCOMPUTE); mbar_init(&pv_done, 1);
     fence_mbar_init();
   }
@@ -179,48 +182,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
-  const uint32_t tS0 = tmem, tO = tmem + 256;   // S buffers at columns 0 and 128, O at 256
+  const uint32_t tS0 = tmem, tO = tmem + NSBUF * AT;   // S buffers at columns 0 / 128 / 256, O at 384
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(&q_full, TILE_BYTES);
       load_tile(sm.t[0], &tq, &q_full, q0, h, b);
-      for (int j = 0; j < nkb; ++j) {
-        const int st = j & 1;
-        const uint32_t n = (uint32_t)(j >> 1);
-        mbar_wait(&k_empty[st], (n & 1) ^ 1);
-        mbar_expect_tx(&k_full[st], TILE_BYTES);
-        load_tile(sm.t[1 + st], &tk, &k_full[st], j * AT, h, b);
-        mbar_wait(&v_empty[st], (n & 1) ^ 1);
-        mbar_expect_tx(&v_full[st], TILE_BYTES);
-        load_tile(sm.t[3 + st], &tv, &v_full[st], j * AT, h, b);
+      // K runs two blocks ahead of V: S(j+2) is issued while block j is in the softmax, and a V slot is only released by
+      // P V(j-2) - one producer thread must not let the K loads queue behind a V slot wait
+      for (int i = 0; i < nkb + 2; ++i) {
+        if (i < nkb) {
+          const int ks = i % NSBUF;
+          mbar_wait(&k_empty[ks], ((uint32_t)(i / NSBUF) & 1) ^ 1);
+          mbar_expect_tx(&k_full[ks], TILE_BYTES);
+          load_tile(sm.t[1 + ks], &tk, &k_full[ks], i * AT, h, b);
+        }
+        if (i >= 2) {
+          const int j = i - 2, vs = j & 1;
+          mbar_wait(&v_empty[vs], ((uint32_t)(j >> 1) & 1) ^ 1);
+          mbar_expect_tx(&v_full[vs], TILE_BYTES);
+          load_tile(sm.t[4 + vs], &tv, &v_full[vs], j * AT, h, b);
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
+      auto issue_s = [&](int i) {
+        const int sb = i % NSBUF;
+        mbar_wait(&k_full[sb], (uint32_t)(i / NSBUF) & 1);
+        tc_fence_after();
+        // buffer sb held S(i-3) / P(i-3): read by P V(i-3), which precedes this MMA in the in-order tensor pipe
+        mma_tile<false, false>(tS0 + sb * AT, sm.a[0], sm.a[1 + sb], false);
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[sb]);
+      };
       mbar_wait(&q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      mma_tile<false, false>(tS0, sm.a[0], sm.a[1], false);                  // S(0) = Q K(0)^T
-      umma_commit(&s_full[0]);
-      umma_commit(&k_empty[0]);
+      for (int i = 0; i < 2 && i < nkb; ++i) issue_s(i);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(AT, AT, 0, 1);
       for (int j = 0; j < nkb; ++j) {
-        if (j + 1 < nkb) {
-          const int st = (j + 1) & 1;
-          mbar_wait(&k_full[st], (uint32_t)((j + 1) >> 1) & 1);
-          tc_fence_after();
-          // buffer st was last read by the softmax of block j-1, which finished before p_full(j-1) fired
-          PB_TR(0, j, 0);
-          mma_tile<false, false>(tS0 + st * 128, sm.a[0], sm.a[1 + st], false);   // S(j+1), overlaps softmax(j)
-          umma_commit(&s_full[st]);
-          umma_commit(&k_empty[st]);
-          PB_TR(0, j, 1);
-        }
+        if (j + 2 < nkb) { PB_TR(0, j, 0); issue_s(j + 2); PB_TR(0, j, 1); }
         mbar_wait(&p_full, j & 1);
         mbar_wait(&v_full[j & 1], (uint32_t)(j >> 1) & 1);
         tc_fence_after();
         PB_TR(0, j, 2);
-        mma_tile<false, true>(tO, sm.a[5], sm.a[3 + (j & 1)], j > 0);        // O += P V   (V as MN-major B)
+        // O += P V: A = P from TMEM (packed bf16 over S buffer j%3: key half 0 at columns 0-31, half 1 at 64-95),
+        // B = V tile as MN-major operand
+        const uint32_t tP = tS0 + (j % NSBUF) * AT, vt = sm.a[4 + (j & 1)];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ts(tO, tP + (kk >> 2) * 64 + (kk & 3) * 8, desc_mnmajor(vt, kk), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&pv_done);
         umma_commit(&v_empty[j & 1]);
         PB_TR(0, j, 3);
@@ -235,69 +245,57 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     const int qg = q0 + r;                   // global query index
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float sl2 = p.scale * LOG2E;
+    const bool causal = p.causal != 0;
     float m_used = -INFINITY, l = 0.f;       // scaling reference of the accumulator / partial row sum of this half
-    // key-padding bitmaps are published one block ahead: bits of block j+1 ride on the barrier of block j
-    publish_keep_bits(s_bits2[0], load_keep(p, b, tid, tid), tid);
-    bool kp_next = load_keep(p, b, AT + tid, tid);
+    const int trole = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 1 : 2) : -1;
+    // key-padding bitmap of all key blocks this CTA visits: one ballot per 32 keys, one barrier for the whole kernel
+    for (int k0 = 0; k0 < nkb * AT; k0 += NCOMPUTE) {
+      const int kc = k0 + tid;
+      bool kp = kc < p.Sk;
+      if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc] != 0;
+      const uint32_t w = __ballot_sync(0xffffffffu, kp);
+      if (lane == 0) s_keep[kc >> 5] = w;
+    }
     compute_bar_sync();
-    for (int j = 0; j < nkb; ++j) {
-      const int kg0 = j * AT;
-      uint32_t msk[2];
+    // the two warps that share a row quadrant (column halves 0 / 1) exchange their row maxima through a 64-thread barrier
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); };
+    uint32_t msk_cur[2], msk_next[2] = {0u, 0u};
 #pragma unroll
-      for (int c = 0; c < 2; ++c) msk[c] = chunk_mask(s_bits2[j & 1][hf * 2 + c], p.causal != 0, qg, kg0 + hf * 64 + c * 32);
-      const int trole = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 1 : 2) : -1;
-      if (trole > 0) PB_TR(trole, j, 0);
-      mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1);
+    for (int c = 0; c < 2; ++c) msk_cur[c] = chunk_mask(s_keep[hf * 2 + c], causal, qg, hf * 64 + c * 32);
+    // row maximum of block 0
+    float m_blk;
+    {
+      mbar_wait(&s_full[0], 0);
       tc_fence_after();
-      if (trole > 0) PB_TR(trole, j, 1);
-      const uint32_t tS = tS0 + (j & 1) * 128;
-      float t[64];                     // raw scores (masked entries = -inf); the scale is folded into the exp2 FFMA
       float bm = -INFINITY;
-      {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tS + lane_addr + hf * 64, v0);
-        tmem_ld32(tS + lane_addr + hf * 64 + 32, v1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS0 + lane_addr + hf * 64 + c * 32, v);
         tmem_ld_wait();
-        if ((msk[0] & msk[1]) == 0xffffffffu) {     // nothing masked in this thread's 64 columns (the common case)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            t[i] = __uint_as_float(v0[i]);
-            t[32 + i] = __uint_as_float(v1[i]);
-            bm = fmaxf(bm, fmaxf(t[i], t[32 + i]));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x0 = ((msk[0] >> i) & 1u) ? __uint_as_float(v0[i]) : -INFINITY;
-            const float x1 = ((msk[1] >> i) & 1u) ? __uint_as_float(v1[i]) : -INFINITY;
-            t[i] = x0;
-            t[32 + i] = x1;
-            bm = fmaxf(bm, fmaxf(x0, x1));
-          }
-        }
+        for (int i = 0; i < 32; ++i) bm = fmaxf(bm, ((msk_cur[c] >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
       }
-      bm *= sl2;                       // sl2 > 0: max of the scaled scores (log2 domain)
-      s_red[hf][r] = bm;
-      publish_keep_bits(s_bits2[(j + 1) & 1], kp_next, tid);
-      kp_next = load_keep(p, b, (j + 2) * AT + tid, tid);
-      if (trole > 0) PB_TR(trole, j, 2);
-      compute_bar_sync();
-      if (trole > 0) PB_TR(trole, j, 3);
-      bm = fmaxf(s_red[0][r], s_red[1][r]);
+      s_red[0][hf][r] = bm * sl2;
+      pair_sync();
+      m_blk = fmaxf(s_red[0][0][r], s_red[0][1][r]);
+    }
+    for (int j = 0; j < nkb; ++j) {
+      if (trole > 0) PB_TR(trole, j, 0);
+      const bool has_next = j + 1 < nkb;
+      const uint32_t tS = tS0 + (j % NSBUF) * AT, tSn = tS0 + ((j + 1) % NSBUF) * AT;
       // lazy rescale: keep the old reference unless the maximum grew by more than 2^8
       float f = 1.0f;
       bool need = false;
       if (m_used == -INFINITY) {
-        m_used = bm;                                      // nothing non-zero accumulated so far
-      } else if (bm > m_used + RESCALE_THRESHOLD) {
-        f = ex2(m_used - bm);
-        m_used = bm;
+        m_used = m_blk;                                   // nothing non-zero accumulated so far
+      } else if (m_blk > m_used + RESCALE_THRESHOLD) {
+        f = ex2(m_used - m_blk);
+        m_used = m_blk;
         need = true;
       }
-      bool waited_pv = false;
       if (__any_sync(0xffffffffu, need)) {
         mbar_wait(&pv_done, (j - 1) & 1);                 // j > 0 here: the previous P V must have landed in O
-        waited_pv = true;
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -312,41 +310,68 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         l *= f;
       }
       const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
-      float rs0 = 0.f, rs1 = 0.f;
-      uint32_t pk[32];                 // P row chunk as packed bf16 pairs
+      if (has_next) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        // masked entries are -inf -> ex2 gives 0; the row sum uses the bf16-rounded values the tensor core sees
-        // (packed conversion + integer unpack: the scalar F2F conversion shares the MUFU pipe with ex2)
-        const float e0 = ex2(fmaf(t[2 * i], sl2, neg_m)), e1 = ex2(fmaf(t[2 * i + 1], sl2, neg_m));
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
-        const uint32_t u = *reinterpret_cast<const uint32_t*>(&h2);
-        pk[i] = u;
-        rs0 += __uint_as_float(u << 16);
-        rs1 += __uint_as_float(u & 0xffff0000u);
+        for (int c = 0; c < 2; ++c)
+          msk_next[c] = chunk_mask(s_keep[(j + 1) * 4 + hf * 2 + c], causal, qg, (j + 1) * AT + hf * 64 + c * 32);
+        mbar_wait(&s_full[(j + 1) % NSBUF], (uint32_t)((j + 1) / NSBUF) & 1);
+        tc_fence_after();
+      }
+      if (trole > 0) PB_TR(trole, j, 1);
+      float rs0 = 0.f, rs1 = 0.f, bmn = -INFINITY;   // (row sums of the unrounded probabilities: two accumulators for ILP)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], nv[32];
+        tmem_ld32(tS + lane_addr + hf * 64 + c * 32, sv);
+        if (has_next) tmem_ld32(tSn + lane_addr + hf * 64 + c * 32, nv);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        const bool all_cur = msk_cur[c] == 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          // masked entries are -inf -> ex2 gives 0
+          float x0 = __uint_as_float(sv[2 * i]), x1 = __uint_as_float(sv[2 * i + 1]);
+          if (!all_cur) {
+            x0 = ((msk_cur[c] >> (2 * i)) & 1u) ? x0 : -INFINITY;
+            x1 = ((msk_cur[c] >> (2 * i + 1)) & 1u) ? x1 : -INFINITY;
+          }
+          const float e0 = ex2(fmaf(x0, sl2, neg_m)), e1 = ex2(fmaf(x1, sl2, neg_m));
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          rs0 += e0;
+          rs1 += e1;
+        }
+        if (has_next) {                      // row maximum of the next block, hidden under the exponentials
+          if (msk_next[c] == 0xffffffffu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bmn = fmaxf(bmn, __uint_as_float(nv[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bmn = fmaxf(bmn, ((msk_next[c] >> i) & 1u) ? __uint_as_float(nv[i]) : -INFINITY);
+          }
+        }
+        // P chunk (32 keys = 16 packed columns) over S columns this thread has already consumed
+        tmem_st16(tS + lane_addr + hf * 64 + c * 16, pk);
       }
       l += rs0 + rs1;
-      if (trole > 0) PB_TR(trole, j, 4);
-      if (j > 0 && !waited_pv) mbar_wait(&pv_done, (j - 1) & 1);   // P buffer is free once P V (j-1) retired
-      if (trole > 0) PB_TR(trole, j, 5);
-      {
-        // this thread's 64 columns = one 128-byte row of the tile half hf: 16-byte chunks XOR-swizzled by (r & 7)
-        uint8_t* rowp = sm.t[5] + hf * HALF_BYTES + r * 128;
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<uint4*>(rowp + ((g ^ (r & 7)) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-      }
-      fence_proxy_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full);
-      if (trole > 0) PB_TR(trole, j, 6);
+      if (trole > 0) PB_TR(trole, j, 2);
+      if (has_next) {
+        s_red[(j + 1) & 1][hf][r] = bmn * sl2;
+        pair_sync();
+        m_blk = fmaxf(s_red[(j + 1) & 1][0][r], s_red[(j + 1) & 1][1][r]);
+        msk_cur[0] = msk_next[0]; msk_cur[1] = msk_next[1];
+      }
+      if (trole > 0) PB_TR(trole, j, 3);
     }
     mbar_wait(&pv_done, (nkb - 1) & 1);
     tc_fence_after();
     compute_bar_sync();
-    s_red[hf][r] = l;
+    s_red[0][hf][r] = l;
     compute_bar_sync();
-    l = s_red[0][r] + s_red[1][r];
+    l = s_red[0][0][r] + s_red[0][1][r];
     const float inv = l > 0.f ? 1.f / l : 0.f;
     __nv_bfloat16* orow = p.o + (long long)b * p.o_sb + (long long)qg * p.ldo + h * AT + hf * 64;
 #pragma unroll
@@ -676,19 +701,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const int st = j & 1, nx = st ^ 1;
         const uint32_t ph = (uint32_t)j & 1;
         if (j + 1 < nkb) {
-          mbar_wait(&k_full[(j + 1) % NK], (uint32_t)((j + 1) / NK) & 1);
-          tc_fence_after();
-          PB_TR(0, j, 0);
-          // S buffer nx held S(j-1) / dS(j-1): read by dQ(j-1), which precedes this MMA in the in-order tensor pipe
-          mma_tile<false, false>(tS0 + nx * AT, sm.a[0], sm.a[2 + (j + 1) % NK], false);   // S(j+1)
-          umma_commit(&s_full[nx]);
+          // dP first: its inputs (V ring, dP buffer released at the very start of softmax(j)) are ready long before K(j+1),
+          // whose ring slot was only released by dQ(j-2) - issuing S(j+1) second gives that TMA refill half a block more
           mbar_wait(&dp_free, ph);                                            // softmax(j) holds dP(j) in registers
           mbar_wait(&v_full[nx], (uint32_t)((j + 1) >> 1) & 1);
           tc_fence_after();
-          PB_TR(0, j, 1);
+          PB_TR(0, j, 0);
           mma_tile<false, false>(tdP, sm.a[1], aV + nx * TILE_BYTES, false);  // dP(j+1)
           umma_commit(&dp_full);
           umma_commit(&v_empty[nx]);
+          mbar_wait(&k_full[(j + 1) % NK], (uint32_t)((j + 1) / NK) & 1);
+          tc_fence_after();
+          PB_TR(0, j, 1);
+          // S buffer nx held S(j-1) / dS(j-1): read by dQ(j-1), which precedes this MMA in the in-order tensor pipe
+          mma_tile<false, false>(tS0 + nx * AT, sm.a[0], sm.a[2 + (j + 1) % NK], false);   // S(j+1)
+          umma_commit(&s_full[nx]);
+#ifdef PB_TRACE_EXEC
+          PB_TR(0, j, 4);
+          mbar_wait_spin(&s_full[nx], (uint32_t)((j + 1) >> 1) & 1);
+          PB_TR(0, j, 5);
+#endif
         }
         mbar_wait(&ds_full, ph);
         tc_fence_after();
@@ -859,6 +891,7 @@ static void fill_params(AttnParams& p, const pb_attn_desc* d) {
 
 extern "C" int pb_attn_fwd(const pb_attn_desc* d, void* stream_) {
   if (attn_check(d)) return -1;
+  if (d->Sk > FWD_MAX_SK) return pb_set_error("pb_attn_fwd: Sk > 8192 not supported (in-kernel key-padding bitmap)");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CUtensorMap tq, tk, tv;
   if (attn_tmap(&tq, d->q, d->Sq, d->ldq, d->H, d->B, (long long)d->Sq * d->ldq)) return -1;

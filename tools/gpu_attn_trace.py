@@ -14,7 +14,7 @@ t0 = t[t > 0].min()
 nb = 8
 print('MMA warp: [k_full(j+1) ok, S(j+1) issued + dp_free(j) + v_full ok, ds_full(j) ok, dQ(j) issued]')
 for j in range(nb):
-    print(j, [int(x - t0) if x > 0 else -1 for x in t[0, j, :4]])
+    print(j, [int(x - t0) if x > 0 else -1 for x in t[0, j, :6]])
 for role in (1, 2):
     print('softmax warp %d: [bar, s/dp_full ok, dP read (2nd chunk), chunk0 math done, dq_done ok, arrived]' % role)
     for j in range(nb):
