@@ -33,6 +33,10 @@ int pb_version(void);
 /* number of kernels launched by this library since the last reset (bench: gpu_launches) */
 long long pb_launch_count(void);
 void pb_reset_launch_count(void);
+/* Programmatic dependent launch: when on (default; PIANOBART_B200_PDL=0 turns it off) consecutive kernels of a stream
+ * overlap their prologue with the previous kernel's tail (every kernel waits for its predecessor with
+ * griddepcontrol.wait before touching global memory).  Returns the previous setting.                              */
+int pb_set_pdl(int on);
 
 /* ------------------------------------------------------------------ GEMM
  * C[b,h][m,n] = epi(alpha * sum_k A[b,h][m,k] * B[b,h][n,k])

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -36,4 +37,19 @@ int pb_num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
+}
+
+static std::atomic<int> g_pdl{-1};
+bool pb_pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    v = (getenv("PIANOBART_B200_PDL") && atoi(getenv("PIANOBART_B200_PDL")) == 0) ? 0 : 1;
+    g_pdl.store(v);
+  }
+  return v != 0;
+}
+extern "C" int pb_set_pdl(int on) {
+  const int prev = pb_pdl_enabled() ? 1 : 0;
+  g_pdl.store(on ? 1 : 0);
+  return prev;
 }

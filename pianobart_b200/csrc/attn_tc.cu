@@ -178,9 +178,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // global memory of the preceding kernel is visible from here on
   const uint32_t tmem = tmem_base_smem;
   const uint32_t tS0 = tmem, tO = tmem + NSBUF * AT;   // S buffers at columns 0 / 128 / 256, O at 384
 
@@ -437,9 +439,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // global memory of the preceding kernel is visible from here on
   const uint32_t tmem = tmem_base_smem;
   // TMEM columns: S^T[2] at 0/64, dP^T[2] at 128/192, dV at 256, dK at 384
   const uint32_t tS0 = tmem, tdP0 = tmem + 128, tdV = tmem + 256, tdK = tmem + 384;
@@ -664,9 +668,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // global memory of the preceding kernel is visible from here on
   const uint32_t tmem = tmem_base_smem;
   const uint32_t tS0 = tmem, tdP = tmem + 256, tdQ = tmem + 384;   // S buffers at columns 0 / 128
 
@@ -833,6 +839,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                                             float* __restrict__ dvec, int B, int H, int Sq, long long ldo,
                                                             long long o_sb, long long lddo, long long do_sb) {
+  pdl_entry();
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = (long long)B * Sq * H;
@@ -903,7 +910,7 @@ extern "C" int pb_attn_fwd(const pb_attn_desc* d, void* stream_) {
   const int smem = 6 * TILE_BYTES + 1024;
   if (set_smem(attn_fwd_kernel, smem, attr)) return -1;
   dim3 grid((d->Sq + AT - 1) / AT, d->H, d->B);
-  attn_fwd_kernel<<<grid, NTHREADS, smem, stream>>>(tq, tk, tv, p);
+  PB_LAUNCH(attn_fwd_kernel, grid, NTHREADS, smem, stream, tq, tk, tv, p);
   return pb_check_launch("attn_fwd_kernel");
 }
 
@@ -920,8 +927,8 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
   {
     const long long rows = (long long)d->B * d->Sq * d->H;
     const int grid = (int)((rows * 32 + 255) / 256);
-    attn_bwd_prep_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)d->o, (const __nv_bfloat16*)d->dout, d->dvec, d->B, d->H,
-                                                   d->Sq, d->ldo, (long long)d->Sq * d->ldo, d->lddo, (long long)d->Sq * d->lddo);
+    PB_LAUNCH(attn_bwd_prep_kernel, grid, 256, 0, stream, (const __nv_bfloat16*)d->o, (const __nv_bfloat16*)d->dout, d->dvec, d->B, d->H,
+              d->Sq, d->ldo, (long long)d->Sq * d->ldo, d->lddo, (long long)d->Sq * d->lddo);
     if (pb_check_launch("attn_bwd_prep_kernel")) return -1;
   }
   static bool attr1 = false, attr2 = false;
@@ -932,10 +939,10 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
   if (attn_tmap(&tq64, d->q, d->Sq, d->ldq, d->H, d->B, (long long)d->Sq * d->ldq, QB)) return -1;
   if (attn_tmap(&tdo64, d->dout, d->Sq, d->lddo, d->H, d->B, (long long)d->Sq * d->lddo, QB)) return -1;
   dim3 g1((d->Sk + AT - 1) / AT, d->H, d->B);
-  attn_bwd_dkv_kernel<<<g1, NTHREADS, smem1, stream>>>(tq64, tk, tv, tdo64, p);
+  PB_LAUNCH(attn_bwd_dkv_kernel, g1, NTHREADS, smem1, stream, tq64, tk, tv, tdo64, p);
   if (pb_check_launch("attn_bwd_dkv_kernel")) return -1;
   dim3 g2((d->Sq + AT - 1) / AT, d->H, d->B);
-  attn_bwd_dq_kernel<<<g2, NTHREADS, smem2, stream>>>(tq, tk, tv, tdo, p);
+  PB_LAUNCH(attn_bwd_dq_kernel, g2, NTHREADS, smem2, stream, tq, tk, tv, tdo, p);
   return pb_check_launch("attn_bwd_dq_kernel");
 }
 

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) decode_finalize_kernel(float* __restrict_
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               bf16* __restrict__ out, float* __restrict__ out_f32, int N,
                                                               int gelu, float eps) {
+  pdl_entry();
   extern __shared__ float row[];  // N floats
   __shared__ float red[8];
   const int b = blockIdx.x;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const bf16* __restrict
                                                           int out_ld, int hd, float scale, int max_keys,
                                                           float* __restrict__ ws, int* __restrict__ tickets,
                                                           float* __restrict__ out_f32) {
+  pdl_entry();
   __shared__ float qs[128];
   __shared__ float pr[DK];
   __shared__ float red[8];
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(256) decode_gemv_kernel(const float* __restric
                                                           const float* __restrict__ residual, const bf16* __restrict__ pos_table,
                                                           const int* __restrict__ t_dev, float* __restrict__ y_f32,
                                                           bf16* __restrict__ y_bf16, int N, int K, int gelu, float eps) {
+  pdl_entry();
   extern __shared__ float xs[];  // B * K
   __shared__ float red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(256) decode_sample_kernel(const float* __restr
                                                             const int* __restrict__ forced, const int* __restrict__ t_dev,
                                                             int* __restrict__ cur_tok, int* __restrict__ sampled, int S,
                                                             SampleMeta meta) {
+  pdl_entry();
   __shared__ float p[512];
   __shared__ float sp[512];
   __shared__ int si[512];
@@ -394,6 +398,7 @@ struct PadMeta { int pad[8]; };
 // one thread per batch row: model.py:59-65
 __global__ void decode_advance_kernel(const int* __restrict__ cur_tok, int* __restrict__ result, int* __restrict__ done,
                                       int* __restrict__ t_dev, int* __restrict__ n_written, int B, int S, PadMeta pm) {
+  pdl_entry();
   const int b = threadIdx.x;
   const int t = *t_dev;
   if (b < B && t < S && !done[b]) {
@@ -417,7 +422,7 @@ extern "C" int pb_decode_finalize(float* acc, const float* bias, const void* res
                                   const float* gamma, const float* beta, void* out, float* out_f32, int B, int N, int gelu,
                                   void* stream) {
   if (N * 4 > 48 * 1024) return pb_set_error("decode_finalize: row too wide");
-  decode_finalize_kernel<<<B, 256, N * sizeof(float), PB_STREAM(stream)>>>(acc, bias, (const bf16*)residual, (const bf16*)pos_table,
+  PB_LAUNCH((decode_finalize_kernel), B, 256, N * sizeof(float), PB_STREAM(stream), acc, bias, (const bf16*)residual, (const bf16*)pos_table,
                                                                           t_dev, gamma, beta, (bf16*)out, out_f32, N, gelu, 1e-5f);
   return pb_check_launch("decode_finalize");
 }
@@ -435,7 +440,7 @@ static void gemv_launch(const float* x_raw, const float* gamma, const float* bet
   int grid = (N + 7) / 8;                       // 8 warps per CTA, one weight row per warp per pass
   const int cap = pb_num_sms() * 4;
   if (grid > cap) grid = cap;
-  decode_gemv_kernel<B><<<grid, 256, smem, st>>>(x_raw, gamma, beta, x_norm_out, (const bf16*)W, bias, residual,
+  PB_LAUNCH((decode_gemv_kernel<B>), grid, 256, smem, st, x_raw, gamma, beta, x_norm_out, (const bf16*)W, bias, residual,
                                                  (const bf16*)pos_table, t_dev, y_f32, (bf16*)y_bf16, N, K, gelu, 1e-5f);
 }
 
@@ -466,7 +471,7 @@ extern "C" int pb_decode_attn(const void* q, int q_ld, const void* k_new, const 
   if ((q_ld % 4) != 0 || (kv_ld % 4) != 0) return pb_set_error("decode_attn: row strides must be multiples of 4 elements");
   const int NS = (max_keys + DK - 1) / DK;
   dim3 grid(H, B, NS);
-  decode_attn_kernel<<<grid, 128, 0, PB_STREAM(stream)>>>(
+  PB_LAUNCH((decode_attn_kernel), grid, 128, 0, PB_STREAM(stream), 
       (const bf16*)q, q_ld, (const bf16*)k_new, (const bf16*)v_new, (bf16*)k_cache, (bf16*)v_cache, kv_batch_stride, kv_ld, key_keep,
       n_keys, t_dev, append, (bf16*)out, out_ld, hd, scale, max_keys, workspace, tickets, out_f32);
   return pb_check_launch("decode_attn");
@@ -483,7 +488,7 @@ extern "C" int pb_decode_sample(const float* logits, const double* uniforms, con
   }
   m.off[8] = off;
   dim3 grid(8, B);
-  decode_sample_kernel<<<grid, 256, 0, PB_STREAM(stream)>>>(logits, uniforms, forced, t_dev, cur_tok, sampled, S, m);
+  PB_LAUNCH((decode_sample_kernel), grid, 256, 0, PB_STREAM(stream), logits, uniforms, forced, t_dev, cur_tok, sampled, S, m);
   return pb_check_launch("decode_sample");
 }
 
@@ -492,6 +497,6 @@ extern "C" int pb_decode_advance(const int* cur_tok, int* result, int* done, int
   if (B > 1024) return pb_set_error("decode_advance: batch > 1024");
   PadMeta pm;
   for (int i = 0; i < 8; ++i) pm.pad[i] = pad_host[i];
-  decode_advance_kernel<<<1, ((B + 31) / 32) * 32, 0, PB_STREAM(stream)>>>(cur_tok, result, done, t_dev, n_written, B, S, pm);
+  PB_LAUNCH((decode_advance_kernel), 1, ((B + 31) / 32) * 32, 0, PB_STREAM(stream), cur_tok, result, done, t_dev, n_written, B, S, pm);
   return pb_check_launch("decode_advance");
 }

@@ -133,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   // 1024-byte aligned tile ring (required by the 128B swizzle atom = 8 rows x 128 B).
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -160,6 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  pdl_wait();   // on-chip state is set up; global memory of the preceding kernel is visible from here on
   const uint32_t tmem_base = tmem_base_smem;
 
   const long long units_per_batch = (long long)p.num_m_blocks * p.num_n_blocks * p.split_k;
@@ -731,7 +733,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   }
   if constexpr (!CG2) {
     long long grid = kp.total_units < (long long)pb_num_sms() ? kp.total_units : (long long)pb_num_sms();
-    kern<<<(unsigned)grid, NUM_THREADS, Cfg::DYN_BYTES, stream>>>(ta, tb, tc, tp, tx, kp);
+    PB_LAUNCH(kern, (unsigned)grid, NUM_THREADS, Cfg::DYN_BYTES, stream, ta, tb, tc, tp, tx, kp);
   } else {
     // one CTA pair (cluster of 2 = one TPC) per scheduling unit slot
     const long long pairs_max = pb_num_sms() / 2;
@@ -742,11 +744,13 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg::DYN_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pb_pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tp, tx, kp);
     if (e != cudaSuccess) return pb_set_cuda_error("cudaLaunchKernelEx(gemm_tc cta_group::2)", e);
   }

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256) noise_apply_kernel(const int16_t* __restr
                                                           int* __restrict__ dec_ids, int* __restrict__ targets,
                                                           float* __restrict__ loss_mask, uint8_t* __restrict__ enc_keep,
                                                           uint8_t* __restrict__ dec_keep, int B, int S, NoiseConst c) {
+  pdl_entry();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long row = t >> 3;
   const int a = (int)(t & 7);
@@ -63,7 +64,7 @@ extern "C" int pb_noise_apply(const int16_t* ori, const int* src, const int* ran
   for (int i = 0; i < 8; ++i) { c.pad[i] = pad_host[i]; c.mask[i] = mask_host[i]; c.sos[i] = sos_host[i]; }
   const long long threads = (long long)B * S * 8;
   const int grid = (int)((threads + 255) / 256);
-  noise_apply_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ori, src, rand_tok, loss_in, loss_mode,
+  PB_LAUNCH((noise_apply_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), ori, src, rand_tok, loss_in, loss_mode,
                                                                               enc_ids, dec_ids, targets, loss_mask,
                                                                               enc_keep, dec_keep, B, S, c);
   return pb_check_launch("noise_apply");

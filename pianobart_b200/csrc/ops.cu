@@ -69,6 +69,7 @@ template <typename T, typename I>
 __global__ void __launch_bounds__(256) octuple_embed_fwd_kernel(const I* __restrict__ ids, const T* __restrict__ table,
                                                                 T* __restrict__ out, long long M, EmbedMeta meta,
                                                                 int* __restrict__ err) {
+  pdl_entry();
   constexpr int N = Pack<T>::N;
   constexpr int PACKS = 2048 / N;
   for (long long m = blockIdx.x; m < M; m += gridDim.x) {
@@ -89,6 +90,7 @@ template <typename T, typename I>
 __global__ void __launch_bounds__(256) octuple_embed_bwd_kernel(const I* __restrict__ ids, const T* __restrict__ dx,
                                                                 float* __restrict__ dtable, long long M, EmbedMeta meta,
                                                                 float scale) {
+  pdl_entry();
   constexpr int N = Pack<T>::N;
   constexpr int PACKS = 2048 / N;
   for (long long m = blockIdx.x; m < M; m += gridDim.x) {
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
                                                             const float* __restrict__ beta, T* __restrict__ y,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                             long long M, int d, float eps, pbdrop::Site drop) {
+  pdl_entry();
   constexpr int N = Pack<T>::N;
   typedef typename RawPack<T>::type Raw;
   const int lane = threadIdx.x & 31;
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const T* 
                                                             T* __restrict__ dx_drop, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, float* __restrict__ dbias,
                                                             long long M, int d, pbdrop::Site din, pbdrop::Site dout) {
+  pdl_entry();
   constexpr int N = Pack<T>::N;
   typedef typename RawPack<T>::type Raw;
   extern __shared__ float sh_red[];   // LNB_WARPS * d floats (gamma occupies the first d until the final reduction)
@@ -325,6 +329,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) softmax_fwd_kernel(const float* __restrict__ s, T* __restrict__ p,
                                                           const uint8_t* __restrict__ key_keep, int B, int H, int Sq,
                                                           int Sk, int causal) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long rows = (long long)B * H * Sq;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -369,6 +374,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) softmax_bwd_kernel(const T* __restrict__ p, const float* __restrict__ dp,
                                                           T* __restrict__ ds, const uint8_t* __restrict__ key_keep,
                                                           int B, int H, int Sq, int Sk, int causal) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long rows = (long long)B * H * Sq;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -403,6 +409,7 @@ __global__ void __launch_bounds__(128) softmax_bwd_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long M, int N,
                                                      long long ld, int rows_per_block) {
+  pdl_entry();
   constexpr int PN = Pack<T>::N;
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + cx) * PN;
@@ -447,6 +454,7 @@ __global__ void __launch_bounds__(128) heads_ce_kernel(const float* __restrict__
                                                        float* __restrict__ loss_num, float* __restrict__ correct,
                                                        T* __restrict__ dlogits, int* __restrict__ argmax_out, long long M,
                                                        SegMeta meta, float sum_w, float grad_scale) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int V = meta.off[meta.nseg];
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -512,6 +520,7 @@ __global__ void __launch_bounds__(128) heads_ce_kernel(const float* __restrict__
 // den[s] = sum_m mask[m, s]
 __global__ void __launch_bounds__(256) mask_sums_kernel(const float* __restrict__ mask, float* __restrict__ den,
                                                         long long M, int nseg) {
+  pdl_entry();
   float acc = 0.f;
   const long long total = M * nseg;
   // thread handles a fixed segment: stride by a multiple of nseg
@@ -526,6 +535,7 @@ __global__ void __launch_bounds__(256) mask_sums_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------ optimizer
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  pdl_entry();
   float acc = 0.f;
   const long long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -556,6 +566,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
                                                     float lr, float beta1, float beta2, float eps, float wd,
                                                     float step_size, const float* __restrict__ gnorm_sq, float max_norm,
                                                     float grad_scale, float bf16_scale) {
+  pdl_entry();
   float coef = grad_scale;
   if (max_norm > 0.f) {
     const float norm = sqrtf(*gnorm_sq) * grad_scale;
@@ -576,6 +587,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
 template <typename T>
 __global__ void __launch_bounds__(256) add_rows_mod_kernel(const T* __restrict__ x, const T* __restrict__ table, T* __restrict__ y,
                                                            long long M, int d, int S) {
+  pdl_entry();
   constexpr int N = Pack<T>::N;
   const long long packs = M * (d / N);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < packs; i += (long long)gridDim.x * blockDim.x) {
@@ -593,11 +605,13 @@ __global__ void __launch_bounds__(256) add_rows_mod_kernel(const T* __restrict__
 template <typename TO>
 __global__ void __launch_bounds__(256) cast_scale_kernel(const float* __restrict__ src, TO* __restrict__ dst, long long n,
                                                          float scale) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f<TO>(src[i] * scale);
 }
 template <typename TI>
 __global__ void __launch_bounds__(256) to_f32_kernel(const TI* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = to_f(src[i]);
 }
@@ -618,11 +632,11 @@ extern "C" int pb_octuple_embed_fwd(const void* ids, int ids_int64, const void* 
   fill_embed_meta(meta, n_tokens_host);
   const int grid = grid_for(M, 1, 16);
   if (dtype == PB_DTYPE_BF16) {
-    if (ids_int64) octuple_embed_fwd_kernel<bf16, long long><<<grid, 256, 0, PB_STREAM(stream)>>>((const long long*)ids, (const bf16*)table, (bf16*)out, M, meta, err_flag);
-    else octuple_embed_fwd_kernel<bf16, int><<<grid, 256, 0, PB_STREAM(stream)>>>((const int*)ids, (const bf16*)table, (bf16*)out, M, meta, err_flag);
+    if (ids_int64) PB_LAUNCH((octuple_embed_fwd_kernel<bf16, long long>), grid, 256, 0, PB_STREAM(stream), (const long long*)ids, (const bf16*)table, (bf16*)out, M, meta, err_flag);
+    else PB_LAUNCH((octuple_embed_fwd_kernel<bf16, int>), grid, 256, 0, PB_STREAM(stream), (const int*)ids, (const bf16*)table, (bf16*)out, M, meta, err_flag);
   } else {
-    if (ids_int64) octuple_embed_fwd_kernel<float, long long><<<grid, 256, 0, PB_STREAM(stream)>>>((const long long*)ids, (const float*)table, (float*)out, M, meta, err_flag);
-    else octuple_embed_fwd_kernel<float, int><<<grid, 256, 0, PB_STREAM(stream)>>>((const int*)ids, (const float*)table, (float*)out, M, meta, err_flag);
+    if (ids_int64) PB_LAUNCH((octuple_embed_fwd_kernel<float, long long>), grid, 256, 0, PB_STREAM(stream), (const long long*)ids, (const float*)table, (float*)out, M, meta, err_flag);
+    else PB_LAUNCH((octuple_embed_fwd_kernel<float, int>), grid, 256, 0, PB_STREAM(stream), (const int*)ids, (const float*)table, (float*)out, M, meta, err_flag);
   }
   return pb_check_launch("octuple_embed_fwd");
 }
@@ -633,11 +647,11 @@ extern "C" int pb_octuple_embed_bwd(const void* ids, int ids_int64, const void* 
   fill_embed_meta(meta, n_tokens_host);
   const int grid = grid_for(M, 1, 16);
   if (dtype == PB_DTYPE_BF16) {
-    if (ids_int64) octuple_embed_bwd_kernel<bf16, long long><<<grid, 256, 0, PB_STREAM(stream)>>>((const long long*)ids, (const bf16*)dx, dtable, M, meta, scale);
-    else octuple_embed_bwd_kernel<bf16, int><<<grid, 256, 0, PB_STREAM(stream)>>>((const int*)ids, (const bf16*)dx, dtable, M, meta, scale);
+    if (ids_int64) PB_LAUNCH((octuple_embed_bwd_kernel<bf16, long long>), grid, 256, 0, PB_STREAM(stream), (const long long*)ids, (const bf16*)dx, dtable, M, meta, scale);
+    else PB_LAUNCH((octuple_embed_bwd_kernel<bf16, int>), grid, 256, 0, PB_STREAM(stream), (const int*)ids, (const bf16*)dx, dtable, M, meta, scale);
   } else {
-    if (ids_int64) octuple_embed_bwd_kernel<float, long long><<<grid, 256, 0, PB_STREAM(stream)>>>((const long long*)ids, (const float*)dx, dtable, M, meta, scale);
-    else octuple_embed_bwd_kernel<float, int><<<grid, 256, 0, PB_STREAM(stream)>>>((const int*)ids, (const float*)dx, dtable, M, meta, scale);
+    if (ids_int64) PB_LAUNCH((octuple_embed_bwd_kernel<float, long long>), grid, 256, 0, PB_STREAM(stream), (const long long*)ids, (const float*)dx, dtable, M, meta, scale);
+    else PB_LAUNCH((octuple_embed_bwd_kernel<float, int>), grid, 256, 0, PB_STREAM(stream), (const int*)ids, (const float*)dx, dtable, M, meta, scale);
   }
   return pb_check_launch("octuple_embed_bwd");
 }
@@ -656,7 +670,7 @@ template <typename T, int MAXP>
 static void ln_fwd_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                           long long M, int d, float eps, pbdrop::Site drop, cudaStream_t st) {
   const int grid = grid_for(M, 4, 16);
-  layernorm_fwd_kernel<T, MAXP><<<grid, 128, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, M, d, eps, drop);
+  PB_LAUNCH((layernorm_fwd_kernel<T, MAXP>), grid, 128, 0, st, (const T*)x, gamma, beta, (T*)y, mean, rstd, M, d, eps, drop);
 }
 template <typename T, int MAXP>
 static void ln_bwd_launch(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
@@ -667,7 +681,7 @@ static void ln_bwd_launch(const void* dy, const void* x, const float* gamma, con
   const int grid = grid_for(M, LNB_WARPS * 2, 1);
   const int smem = LNB_WARPS * d * (int)sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<T, MAXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  layernorm_bwd_kernel<T, MAXP><<<grid, LNB_WARPS * 32, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx,
+  PB_LAUNCH((layernorm_bwd_kernel<T, MAXP>), grid, LNB_WARPS * 32, smem, st, (const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx,
                                                                  (T*)dx_drop, dgamma, dbeta, dbias, M, d, din, dout);
 }
 
@@ -716,18 +730,20 @@ extern "C" int pb_layernorm_bwd(const void* dy, const void* x, const float* gamm
 }
 
 __global__ void dropout_mask_kernel(const unsigned long long* seed, uint32_t op, uint32_t thresh, unsigned char* mask, long long n) {
+  pdl_entry();
   const uint32_t key = pbdrop::site_key(*seed, op);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     mask[i] = pbdrop::keep(key, (unsigned long long)i, thresh) ? 1 : 0;
 }
 extern "C" int pb_dropout_mask(const unsigned long long* seed, unsigned int op, unsigned int thresh, unsigned char* mask,
                                long long n, void* stream) {
-  dropout_mask_kernel<<<grid_for(n, 256 * 8, 8), 256, 0, PB_STREAM(stream)>>>(seed, op, thresh, mask, n);
+  PB_LAUNCH((dropout_mask_kernel), grid_for(n, 256 * 8, 8), 256, 0, PB_STREAM(stream), seed, op, thresh, mask, n);
   return pb_check_launch("dropout_mask");
 }
-__global__ void add_u64_kernel(unsigned long long* p, unsigned long long inc) { *p += inc; }
+__global__ void add_u64_kernel(unsigned long long* p, unsigned long long inc) {
+  pdl_entry(); *p += inc; }
 extern "C" int pb_add_u64(unsigned long long* ptr, unsigned long long inc, void* stream) {
-  add_u64_kernel<<<1, 1, 0, PB_STREAM(stream)>>>(ptr, inc);
+  PB_LAUNCH((add_u64_kernel), 1, 1, 0, PB_STREAM(stream), ptr, inc);
   return pb_check_launch("add_u64");
 }
 
@@ -736,9 +752,9 @@ extern "C" int pb_softmax_fwd(const float* scores, void* probs, const uint8_t* k
   if (Sk > SM_MAX * 32) return pb_set_error("softmax: Sk > 1024 not supported");
   const int grid = grid_for((long long)B * H * Sq, 4, 16);
   if (dtype == PB_DTYPE_BF16)
-    softmax_fwd_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>(scores, (bf16*)probs, key_keep, B, H, Sq, Sk, causal);
+    PB_LAUNCH((softmax_fwd_kernel<bf16>), grid, 128, 0, PB_STREAM(stream), scores, (bf16*)probs, key_keep, B, H, Sq, Sk, causal);
   else
-    softmax_fwd_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>(scores, (float*)probs, key_keep, B, H, Sq, Sk, causal);
+    PB_LAUNCH((softmax_fwd_kernel<float>), grid, 128, 0, PB_STREAM(stream), scores, (float*)probs, key_keep, B, H, Sq, Sk, causal);
   return pb_check_launch("softmax_fwd");
 }
 
@@ -747,9 +763,9 @@ extern "C" int pb_softmax_bwd(const void* probs, const float* dprobs, void* dsco
   if (Sk > SM_MAX * 32) return pb_set_error("softmax: Sk > 1024 not supported");
   const int grid = grid_for((long long)B * H * Sq, 4, 16);
   if (dtype == PB_DTYPE_BF16)
-    softmax_bwd_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>((const bf16*)probs, dprobs, (bf16*)dscores, key_keep, B, H, Sq, Sk, causal);
+    PB_LAUNCH((softmax_bwd_kernel<bf16>), grid, 128, 0, PB_STREAM(stream), (const bf16*)probs, dprobs, (bf16*)dscores, key_keep, B, H, Sq, Sk, causal);
   else
-    softmax_bwd_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>((const float*)probs, dprobs, (float*)dscores, key_keep, B, H, Sq, Sk, causal);
+    PB_LAUNCH((softmax_bwd_kernel<float>), grid, 128, 0, PB_STREAM(stream), (const float*)probs, dprobs, (float*)dscores, key_keep, B, H, Sq, Sk, causal);
   return pb_check_launch("softmax_bwd");
 }
 
@@ -763,8 +779,8 @@ extern "C" int pb_colsum(const void* x, float* out, long long M, int N, long lon
   const long long gy = (M + rows_per_block - 1) / rows_per_block;
   if (gy > 65535) return pb_set_error("colsum: too many row blocks");
   dim3 grid(gx, (unsigned)gy);
-  if (dtype == PB_DTYPE_BF16) colsum_kernel<bf16><<<grid, 256, 0, PB_STREAM(stream)>>>((const bf16*)x, out, M, N, ld, rows_per_block);
-  else colsum_kernel<float><<<grid, 256, 0, PB_STREAM(stream)>>>((const float*)x, out, M, N, ld, rows_per_block);
+  if (dtype == PB_DTYPE_BF16) PB_LAUNCH((colsum_kernel<bf16>), grid, 256, 0, PB_STREAM(stream), (const bf16*)x, out, M, N, ld, rows_per_block);
+  else PB_LAUNCH((colsum_kernel<float>), grid, 256, 0, PB_STREAM(stream), (const float*)x, out, M, N, ld, rows_per_block);
   return pb_check_launch("colsum");
 }
 
@@ -781,20 +797,20 @@ extern "C" int pb_heads_ce(const float* logits, const int* targets, const float*
   meta.off[nseg] = off;
   const int grid = grid_for(M, 4 * 4, 8);
   if (dtype == PB_DTYPE_BF16)
-    heads_ce_kernel<bf16><<<grid, 128, 0, PB_STREAM(stream)>>>(logits, targets, mask, den, loss_num, correct, (bf16*)dlogits, argmax_out, M, meta, sw, grad_scale);
+    PB_LAUNCH((heads_ce_kernel<bf16>), grid, 128, 0, PB_STREAM(stream), logits, targets, mask, den, loss_num, correct, (bf16*)dlogits, argmax_out, M, meta, sw, grad_scale);
   else
-    heads_ce_kernel<float><<<grid, 128, 0, PB_STREAM(stream)>>>(logits, targets, mask, den, loss_num, correct, (float*)dlogits, argmax_out, M, meta, sw, grad_scale);
+    PB_LAUNCH((heads_ce_kernel<float>), grid, 128, 0, PB_STREAM(stream), logits, targets, mask, den, loss_num, correct, (float*)dlogits, argmax_out, M, meta, sw, grad_scale);
   return pb_check_launch("heads_ce");
 }
 
 extern "C" int pb_mask_sums(const float* mask, float* den, long long M, int nseg, void* stream) {
-  mask_sums_kernel<<<grid_for(M * nseg, 256 * 8, 4), 256, 0, PB_STREAM(stream)>>>(mask, den, M, nseg);
+  PB_LAUNCH((mask_sums_kernel), grid_for(M * nseg, 256 * 8, 4), 256, 0, PB_STREAM(stream), mask, den, M, nseg);
   return pb_check_launch("mask_sums");
 }
 
 extern "C" int pb_sumsq(const float* g, long long n, float* out, void* stream) {
   if ((reinterpret_cast<uintptr_t>(g) & 15) != 0) return pb_set_error("sumsq: pointer not 16-byte aligned");
-  sumsq_kernel<<<grid_for(n, 256 * 16, 8), 256, 0, PB_STREAM(stream)>>>(g, n, out);
+  PB_LAUNCH((sumsq_kernel), grid_for(n, 256 * 16, 8), 256, 0, PB_STREAM(stream), g, n, out);
   return pb_check_launch("sumsq");
 }
 
@@ -803,7 +819,7 @@ extern "C" int pb_adamw(float* p, float* m, float* v, const float* g, void* p_bf
                         float grad_scale, float bf16_scale, void* stream) {
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
-  adamw_kernel<<<grid_for(n, 256 * 8, 8), 256, 0, PB_STREAM(stream)>>>(p, m, v, g, (bf16*)p_bf16, n, lr, beta1, beta2, eps, wd, step_size, gnorm_sq, max_norm, grad_scale, bf16_scale);
+  PB_LAUNCH((adamw_kernel), grid_for(n, 256 * 8, 8), 256, 0, PB_STREAM(stream), p, m, v, g, (bf16*)p_bf16, n, lr, beta1, beta2, eps, wd, step_size, gnorm_sq, max_norm, grad_scale, bf16_scale);
   return pb_check_launch("adamw");
 }
 
@@ -811,21 +827,21 @@ extern "C" int pb_add_rows_mod(const void* x, const void* table, void* y, long l
   const int pn = dtype == PB_DTYPE_BF16 ? 8 : 4;
   if (d % pn != 0) return pb_set_error("add_rows_mod: d must be a multiple of the pack width");
   const int grid = grid_for(M * (d / pn), 256 * 4, 8);
-  if (dtype == PB_DTYPE_BF16) add_rows_mod_kernel<bf16><<<grid, 256, 0, PB_STREAM(stream)>>>((const bf16*)x, (const bf16*)table, (bf16*)y, M, d, S);
-  else add_rows_mod_kernel<float><<<grid, 256, 0, PB_STREAM(stream)>>>((const float*)x, (const float*)table, (float*)y, M, d, S);
+  if (dtype == PB_DTYPE_BF16) PB_LAUNCH((add_rows_mod_kernel<bf16>), grid, 256, 0, PB_STREAM(stream), (const bf16*)x, (const bf16*)table, (bf16*)y, M, d, S);
+  else PB_LAUNCH((add_rows_mod_kernel<float>), grid, 256, 0, PB_STREAM(stream), (const float*)x, (const float*)table, (float*)y, M, d, S);
   return pb_check_launch("add_rows_mod");
 }
 
 extern "C" int pb_cast_from_f32(const float* src, void* dst, long long n, float scale, int dtype, void* stream) {
   const int grid = grid_for(n, 256 * 8, 8);
-  if (dtype == PB_DTYPE_BF16) cast_scale_kernel<bf16><<<grid, 256, 0, PB_STREAM(stream)>>>(src, (bf16*)dst, n, scale);
-  else cast_scale_kernel<float><<<grid, 256, 0, PB_STREAM(stream)>>>(src, (float*)dst, n, scale);
+  if (dtype == PB_DTYPE_BF16) PB_LAUNCH((cast_scale_kernel<bf16>), grid, 256, 0, PB_STREAM(stream), src, (bf16*)dst, n, scale);
+  else PB_LAUNCH((cast_scale_kernel<float>), grid, 256, 0, PB_STREAM(stream), src, (float*)dst, n, scale);
   return pb_check_launch("cast_from_f32");
 }
 
 extern "C" int pb_cast_to_f32(const void* src, float* dst, long long n, int dtype, void* stream) {
   const int grid = grid_for(n, 256 * 8, 8);
-  if (dtype == PB_DTYPE_BF16) to_f32_kernel<bf16><<<grid, 256, 0, PB_STREAM(stream)>>>((const bf16*)src, dst, n);
-  else to_f32_kernel<float><<<grid, 256, 0, PB_STREAM(stream)>>>((const float*)src, dst, n);
+  if (dtype == PB_DTYPE_BF16) PB_LAUNCH((to_f32_kernel<bf16>), grid, 256, 0, PB_STREAM(stream), (const bf16*)src, dst, n);
+  else PB_LAUNCH((to_f32_kernel<float>), grid, 256, 0, PB_STREAM(stream), (const float*)src, dst, n);
   return pb_check_launch("cast_to_f32");
 }

@@ -11,6 +11,7 @@ One decode step = one CUDA-graph replay of ~120 launches; the step index, the sa
 stop flags live in device memory so the same graph is replayed for every position.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -275,9 +276,16 @@ class Generator:
             for c, s in zip(self.self_cache, caches):
                 c[:, :1].copy_(s)
             self.acc.zero_()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.step.run()
+            # the per-token kernels are a few microseconds each: programmatic dependent launch edges inside the graph
+            # measured slower than plain kernel-to-kernel edges (profiles/r1_summary.md), so the capture turns them off
+            lib = L.lib()
+            prev = lib.pb_set_pdl(1 if os.environ.get('PIANOBART_B200_DECODE_PDL', '0') == '1' else 0)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.step.run()
+            finally:
+                lib.pb_set_pdl(prev)
             self.graph = g
             # capture does not execute: state is unchanged
         for _ in range(n):

@@ -17,7 +17,7 @@ M = 16384
 seed = torch.tensor([12345], dtype=torch.int64, device=dev)
 
 
-def case(tag, N, K, bias=False, drop=False, res=False, flags=0, aux=False, b_mn=0):
+def case(tag, N, K, bias=False, drop=False, res=False, flags=0, aux=False, b_mn=0, block_n=0, cg=0):
     A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
     Bm = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     if b_mn:
@@ -35,6 +35,7 @@ def case(tag, N, K, bias=False, drop=False, res=False, flags=0, aux=False, b_mn=
     d.lda, d.ldb, d.ldc, d.ldr = K, (N if b_mn else K), N, N
     d.batch_h = d.batch_b = 1
     d.alpha, d.flags, d.split_k = 1.0, flags, 1
+    d.block_n, d.cta_group = block_n, cg
     if aux:
         d.aux, d.ldaux = aux_t.data_ptr(), N
     if drop:
@@ -64,3 +65,9 @@ case('dZ: mul aux', 4096, 1024, flags=L.PB_GEMM_MUL_AUX, aux=True, b_mn=1)
 case('fc2: bias+dropout+residual', 1024, 4096, bias=True, drop=True, res=True)
 case('plain N=4096', 4096, 1024)
 case('plain K=4096', 1024, 4096)
+case('out_proj bn=128 (no pairs)', 1024, 1024, bias=True, drop=True, res=True, block_n=128)
+case('plain bn=128 (no pairs)', 1024, 1024, block_n=128)
+case('out_proj bn=256 no pairs', 1024, 1024, bias=True, drop=True, res=True, block_n=256, cg=1)
+case('fc1 N=2048: bias+gelu+dgelu', 2048, 1024, bias=True, flags=L.PB_GEMM_GELU | L.PB_GEMM_AUX_DGELU, aux=True)
+case('fc2 K=2048: bias+dropout+residual', 1024, 2048, bias=True, drop=True, res=True)
+case('fc2 K=2048 bn=128', 1024, 2048, bias=True, drop=True, res=True, block_n=128)

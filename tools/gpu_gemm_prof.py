@@ -21,8 +21,8 @@ def main():
     S = 1024
     torch.manual_seed(0)
     e2w, w2e = build_octuple_vocab()
-    bc = BartConfig(max_position_embeddings=1024, d_model=1024, encoder_layers=8, decoder_layers=8, encoder_ffn_dim=4096,
-                    decoder_ffn_dim=4096, encoder_attention_heads=8, decoder_attention_heads=8)
+    bc = BartConfig(max_position_embeddings=1024, d_model=1024, encoder_layers=8, decoder_layers=8, encoder_ffn_dim=2048,
+                    decoder_ffn_dim=2048, encoder_attention_heads=8, decoder_attention_heads=8)
     dev = torch.device('cuda', 0)
     pb = PianoBart(bc, e2w, w2e, dtype='bf16')
     lm = PianoBartLM(pb).to(dev)
