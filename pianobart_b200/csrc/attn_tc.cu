@@ -164,7 +164,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   Smem4 sm;
   carve(smem_raw, sm, 6);  // 0 Q, 1-3 K ring, 4-5 V ring
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // causal: query blocks near the end of the sequence visit the most key blocks - schedule them first
+  const int qb = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * AT;
   int nkb = (p.Sk + AT - 1) / AT;
   if (p.causal) nkb = min(nkb, qb + 1);
@@ -654,7 +655,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   uint8_t* gV = sm.t[5];
   const uint32_t aV = sm.a[5];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // causal: query blocks near the end of the sequence visit the most key blocks - schedule them first
+  const int qb = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * AT;
   int nkb = (p.Sk + AT - 1) / AT;
   if (p.causal) nkb = min(nkb, qb + 1);
@@ -835,31 +837,52 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-// D[b,h,q] = sum_c dO[b,q,h,c] * O[b,q,h,c]      (one warp per (b,q,h) row of 128)
+// D[b,h,q] = sum_c dO[b,q,h,c] * O[b,q,h,c]      (16 lanes x 16 bytes per (b,q,h) row of 128, two rows in flight per thread)
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                                             float* __restrict__ dvec, int B, int H, int Sq, long long ldo,
                                                             long long o_sb, long long lddo, long long do_sb) {
   pdl_entry();
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int sub = threadIdx.x & 15;                                      // 16-byte piece of the row
   const long long total = (long long)B * Sq * H;
-  if (w >= total) return;
-  const int h = (int)(w % H);
-  const long long bq = w / H;
-  const int q = (int)(bq % Sq), b = (int)(bq / Sq);
-  const uint2 ov = *reinterpret_cast<const uint2*>(o + (long long)b * o_sb + (long long)q * ldo + h * AT + lane * 4);
-  const uint2 dv = *reinterpret_cast<const uint2*>(dout + (long long)b * do_sb + (long long)q * lddo + h * AT + lane * 4);
-  const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
-  const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
-  float s = 0.f;
+  const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;   // row group of this half-warp
+  const long long stride = ((long long)gridDim.x * blockDim.x) >> 4;
+  for (long long w0 = g0; w0 < total; w0 += 2 * stride) {
+    uint4 ov[2], dv[2];
+    bool ok[2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float2 a = __bfloat1622float2(o2[i]), c = __bfloat1622float2(d2[i]);
-    s += a.x * c.x + a.y * c.y;
+    for (int u = 0; u < 2; ++u) {
+      const long long w = w0 + u * stride;
+      ok[u] = w < total;
+      if (ok[u]) {
+        const int h = (int)(w % H);
+        const long long bq = w / H;
+        const int q = (int)(bq % Sq), b = (int)(bq / Sq);
+        ov[u] = *reinterpret_cast<const uint4*>(o + (long long)b * o_sb + (long long)q * ldo + h * AT + sub * 8);
+        dv[u] = *reinterpret_cast<const uint4*>(dout + (long long)b * do_sb + (long long)q * lddo + h * AT + sub * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float s = 0.f;
+      if (ok[u]) {
+        const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov[u]);
+        const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __bfloat1622float2(o2[i]), c = __bfloat1622float2(d2[i]);
+          s += a.x * c.x + a.y * c.y;
+        }
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      const long long w = w0 + u * stride;
+      if (ok[u] && sub == 0) {
+        const int h = (int)(w % H);
+        const long long bq = w / H;
+        dvec[((long long)(bq / Sq) * H + h) * Sq + (bq % Sq)] = s;
+      }
+    }
   }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) dvec[((long long)b * H + h) * Sq + q] = s;
 }
 
 template <typename K>
@@ -926,7 +949,9 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
   fill_params(p, d);
   {
     const long long rows = (long long)d->B * d->Sq * d->H;
-    const int grid = (int)((rows * 32 + 255) / 256);
+    long long blocks = (rows * 16 / 2 + 255) / 256;                       // two rows per thread
+    const long long cap = (long long)pb_num_sms() * 16;
+    const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
     PB_LAUNCH(attn_bwd_prep_kernel, grid, 256, 0, stream, (const __nv_bfloat16*)d->o, (const __nv_bfloat16*)d->dout, d->dvec, d->B, d->H,
               d->Sq, d->ldo, (long long)d->Sq * d->ldo, d->lddo, (long long)d->Sq * d->lddo);
     if (pb_check_launch("attn_bwd_prep_kernel")) return -1;

@@ -120,7 +120,7 @@ __device__ __forceinline__ void unpack_raw(const uint4& r, float (&f)[8]) {
   for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
-// gamma / beta live in registers for the whole kernel and the 16-byte loads of the warp's next row are in flight while
+// gamma / beta are staged in shared memory once per block and the 16-byte loads of the warp's next row are in flight while
 // the current row is reduced; the optional output dropout site costs one hash per two elements (dropout.cuh).
 template <typename T, int MAXP>
 __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
@@ -134,13 +134,12 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const uint32_t dkey = drop.seed ? pbdrop::site_key(*drop.seed, drop.op) : 0u;
-  float ga[MAXP][N], be[MAXP][N];
-#pragma unroll
-  for (int k = 0; k < MAXP; ++k) {
-    const int c = (k * 32 + lane) * N;
-#pragma unroll
-    for (int j = 0; j < N; ++j) { ga[k][j] = c < d ? __ldg(gamma + c + j) : 0.f; be[k][j] = c < d ? __ldg(beta + c + j) : 0.f; }
+  __shared__ __align__(16) float s_ga[MAXP * 32 * N], s_be[MAXP * 32 * N];   // gamma / beta (registers would halve the occupancy)
+  for (int c = threadIdx.x; c < MAXP * 32 * N; c += blockDim.x) {
+    s_ga[c] = c < d ? __ldg(gamma + c) : 0.f;
+    s_be[c] = c < d ? __ldg(beta + c) : 0.f;
   }
+  __syncthreads();
   Raw nx[MAXP];
   auto fetch = [&](long long row) {
 #pragma unroll
@@ -184,9 +183,14 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
     for (int k = 0; k < MAXP; ++k) {
       const int c = (k * 32 + lane) * N;
       if (c < d) {
-        float o[N];
+        float o[N], ga[N], be[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) o[j] = (v[k][j] - mean) * rstd * ga[k][j] + be[k][j];
+        for (int j = 0; j < N; j += 4) {
+          *reinterpret_cast<float4*>(&ga[j]) = *reinterpret_cast<const float4*>(&s_ga[c + j]);
+          *reinterpret_cast<float4*>(&be[j]) = *reinterpret_cast<const float4*>(&s_be[c + j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[j] = (v[k][j] - mean) * rstd * ga[j] + be[j];
         if (drop.seed) {
           const uint32_t bits = pbdrop::keep_bits<N>(dkey, (unsigned long long)row * d + c, drop.thresh);
 #pragma unroll
