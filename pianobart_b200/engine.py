@@ -123,6 +123,16 @@ class ParamLayout:
         return self.fused[name][0]
 
 
+_NUM_SMS = None
+
+
+def _num_sms():
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        _NUM_SMS = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count if torch.cuda.is_available() else 148
+    return _NUM_SMS
+
+
 class Plan:
     """A recorded list of (function, args) library calls; run() replays it on a stream."""
 
@@ -192,10 +202,20 @@ class Plan:
     def wgrad(self, dy, x, dw, n_out, n_in, M, ld_dy, ld_x, name='wgrad'):
         """dW[n_out, n_in] += dY[M, n_out]^T X[M, n_in]   (fp32 atomic accumulate, split-K)."""
         bn = int(os.environ.get('PIANOBART_B200_WGRAD_BN', '256'))
-        units = ((n_out + 127) // 128) * ((n_in + bn - 1) // bn)
+        # split-K from a wave model of the persistent kernel: cost(s) = ceil(tiles * s / slots) * (k-blocks / s + c), c = the
+        # per-unit fill + fp32-reduction epilogue in k-block units (fitted on tools/gpu_wgrad_split.py: 31 vs 39 us for
+        # 1024 x 1024, 55 vs 62 us for 2048 x 1024 against the earlier "two units per SM" rule)
+        pairs = n_out >= 1024 and bn == 256 and os.environ.get('PIANOBART_B200_CG2', '1') != '0'   # library's cta_group::2 rule
+        tiles = ((n_out + (255 if pairs else 127)) // (256 if pairs else 128)) * ((n_in + bn - 1) // bn)
+        slots = _num_sms() // 2 if pairs else _num_sms()
         kblocks = (M + 63) // 64
-        target = int(os.environ.get('PIANOBART_B200_WGRAD_UNITS', '296'))
-        split = max(1, min((target + units - 1) // units, max(1, kblocks // 4)))
+        split, best = 1, None
+        for sk in range(1, max(1, kblocks // 4) + 1):
+            cost = -(-tiles * sk // slots) * (kblocks / sk + 8.0)
+            if best is None or cost < best - 1e-9:
+                split, best = sk, cost
+            if sk >= 32:
+                break
         self.gemm(dy, x, dw, n_out, n_in, M, ld_dy, ld_x, n_in, a_mn=1, b_mn=1,
                   flags=L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC, split_k=split, block_n=bn, name=name)
 
