@@ -109,7 +109,10 @@ __device__ __forceinline__ void gelu_fwd_grad(float x, float& g, float& d) {
   d = fmaf(x * 0.3989422804014327f, e, phi);
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool CG2>
+// FAST: the epilogue is specialised for the training step's bf16 GEMMs - C, residual / aux input and aux output all go
+// through TMA, no fp32 / atomic / legacy pre-activation paths - which removes two thirds of the epilogue's code (the generic
+// epilogue spent 8-15 % of its issue slots waiting for instruction fetch, profiles/r1_summary.md).
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CG2, bool FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
@@ -289,10 +292,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int etid = threadIdx.x - 64;       // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool out_f32 = p.flags & PB_GEMM_OUT_F32;
-    const bool do_gelu = p.flags & PB_GEMM_GELU;
-    const bool atomic_acc = p.flags & PB_GEMM_ATOMIC_ACC;
-    const bool res_f32 = p.flags & PB_GEMM_RES_F32;
+    // (with FAST these are compile-time constants and the branches on them disappear)
+    const int flags = FAST ? (p.flags & (PB_GEMM_GELU | PB_GEMM_AUX_DGELU | PB_GEMM_MUL_AUX)) : p.flags;
+    const bool out_f32 = FAST ? false : bool(flags & PB_GEMM_OUT_F32);
+    const bool do_gelu = flags & PB_GEMM_GELU;
+    const bool atomic_acc = FAST ? false : bool(flags & PB_GEMM_ATOMIC_ACC);
+    const bool res_f32 = FAST ? false : bool(flags & PB_GEMM_RES_F32);
+    const bool tma_c = FAST ? true : (p.tma_c != 0);
+    const bool tma_x = FAST ? bool(flags & PB_GEMM_AUX_DGELU) : (p.tma_x != 0);
     // TMA epilogue: a thread owns one accumulator row, so direct global accesses touch 32 different rows per warp
     // instruction (32 L1 wavefronts per request, partial sectors) and the LSU - not the tensor pipe - bounded every GEMM
     // with a residual, aux operand or second output.  Instead each warp stages its [32 rows x 32 columns] bf16 box in
@@ -306,9 +313,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int st_slot = 0;
     const int sw = (lane >> 1) & 3;          // 64-byte swizzle: 16-byte chunk g of row `lane` lives at chunk g ^ sw
     if (lane == 0) {
-      if (p.tma_c) tma_prefetch_desc(&tmap_c);
+      if (tma_c) tma_prefetch_desc(&tmap_c);
       if (p.tma_pre) tma_prefetch_desc(&tmap_pre);
-      if (p.tma_x) tma_prefetch_desc(&tmap_x);
+      if (tma_x) tma_prefetch_desc(&tmap_x);
     }
     for (long long w = unit0; w < p.total_units; w += unit_stride) {
       int m_blk, n_blk, split, h, b, kb0, kb1;
@@ -334,8 +341,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // stores.  One prefetch stream: the aux operand when the epilogue multiplies by it, else the residual; by TMA
       // when the host could build a tensor map for it (p.tma_pre), else with per-thread vector loads.
       const bool pre_tma = p.tma_pre != 0 && row0w < p.M;
-      const bool want_aux = row_ok && !out_f32 && (p.flags & (PB_GEMM_MUL_DGELU | PB_GEMM_MUL_AUX)) && ((p.ldaux & 7) == 0);
-      const bool want_res = !want_aux && row_ok && !out_f32 && p.residual != nullptr && first_split && !res_f32 && ((p.ldr & 7) == 0);
+      const bool want_aux = FAST ? false : (row_ok && !out_f32 && (flags & (PB_GEMM_MUL_DGELU | PB_GEMM_MUL_AUX)) && ((p.ldaux & 7) == 0));
+      const bool want_res = FAST ? false : (!want_aux && row_ok && !out_f32 && p.residual != nullptr && first_split && !res_f32 && ((p.ldr & 7) == 0));
       const __nv_bfloat16* res_row = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off;
       const __nv_bfloat16* aux_row = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux;
       const __nv_bfloat16* pre_row = want_aux ? aux_row : res_row;
@@ -404,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           issue_loads(chi + 1, npre);
         }
         tmem_ld_wait();
-        if (row_ok || p.tma_c || p.tma_x) {   // TMA stores are warp-collective: rows >= M are clipped by the tensor map
+        if (row_ok || tma_c || tma_x) {   // TMA stores are warp-collective: rows >= M are clipped by the tensor map
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
@@ -413,7 +420,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] += sb[j];
         }
-        if (p.flags & PB_GEMM_AUX_PREACT) {
+        if (flags & PB_GEMM_AUX_PREACT) {
           const long long a_off = (long long)row * p.ldaux + col0;
           if (out_f32) {
             float* ax = reinterpret_cast<float*>(p.aux) + a_off;
@@ -422,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + j < p.N) ax[j] = x[j];
           } else {
             __nv_bfloat16* ax = reinterpret_cast<__nv_bfloat16*>(p.aux) + a_off;
-            if (p.tma_x) {
+            if (tma_x) {
               tma_store_row(&tmap_x, x, col0);
             } else if (full && ((p.ldaux & 7) == 0)) {
 #pragma unroll
@@ -444,12 +451,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         if (do_gelu) {
-          if (p.flags & PB_GEMM_AUX_DGELU) {
+          if (flags & PB_GEMM_AUX_DGELU) {
             float dg[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) gelu_fwd_grad(x[j], x[j], dg[j]);
             __nv_bfloat16* ax = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col0;
-            if (p.tma_x) {
+            if (tma_x) {
               tma_store_row(&tmap_x, dg, col0);
             } else if (full && ((p.ldaux & 7) == 0)) {
 #pragma unroll
@@ -473,7 +480,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
-        if (p.flags & PB_GEMM_MUL_AUX) {
+        if (flags & PB_GEMM_MUL_AUX) {
           const __nv_bfloat16* ax = aux_row + col0;
           if (pf_aux) {
 #pragma unroll
@@ -486,13 +493,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 x[j + 2 * t + 1] *= f.y;
               }
             }
-          } else if (row_ok) {
+          } else if (!FAST && row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) x[j] *= __bfloat162float(ax[j]);
           }
         }
-        if ((p.flags & PB_GEMM_MUL_DGELU) && (row_ok || pf_aux)) {
+        if ((flags & PB_GEMM_MUL_DGELU) && (row_ok || pf_aux)) {
           const long long a_off = (long long)row * p.ldaux + col0;
           if (out_f32) {
             const float* ax = reinterpret_cast<const float*>(p.aux) + a_off;
@@ -523,7 +530,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (p.drop.seed != nullptr) {
           const uint32_t key = pbdrop::site_key(*p.drop.seed, p.drop.op);
           const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col0;
-          if ((base & 31ull) == 0) {
+          if (FAST || (base & 31ull) == 0) {
             const uint32_t bits = pbdrop::keep_bits<32>(key, base, p.drop.thresh);
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = ((bits >> j) & 1u) ? x[j] * p.drop.scale : 0.f;
@@ -532,7 +539,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = 0; j < 32; ++j) x[j] = pbdrop::keep(key, base + j, p.drop.thresh) ? x[j] * p.drop.scale : 0.f;
           }
         }
-        if (p.residual != nullptr && first_split && (row_ok || pf_res)) {
+        if (p.residual != nullptr && first_split && (FAST ? pf_res : (row_ok || pf_res))) {
           if (res_f32) {
             const float* r = reinterpret_cast<const float*>(p.residual) + r_off + col0;
 #pragma unroll
@@ -540,10 +547,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + j < p.N) x[j] += r[j];
           } else {
             const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off + col0;
-            if (pf_res || (full && ((p.ldr & 7) == 0))) {
+            if (FAST || pf_res || (full && ((p.ldr & 7) == 0))) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 rv = pf_res ? rpre[j >> 3] : *reinterpret_cast<const uint4*>(r + j);
+                const uint4 rv = (FAST || pf_res) ? rpre[j >> 3] : *reinterpret_cast<const uint4*>(r + j);
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -582,7 +589,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         } else {
           __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + col0;
-          if (p.tma_c) {
+          if (tma_c) {
             tma_store_row(&tmap_c, x, col0);
           } else if (!row_ok) {
             // (only reached when the aux output alone goes through TMA)
@@ -720,12 +727,12 @@ static inline int make_tmap(CUtensorMap* out, const void* base, uint64_t inner, 
   return pb_make_tmap_bf16(out, base, inner, rows, ld, nh, stride_h, nb, stride_b, box_inner, box_rows);
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool CG2>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CG2, bool FAST>
+static int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                   const CUtensorMap& tx, const GemmKParams& kp, cudaStream_t stream) {
   using Cfg = SmemCfg<BLOCK_N, CG2>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CG2>;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CG2, FAST>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::DYN_BYTES);
     if (e != cudaSuccess) return pb_set_cuda_error("cudaFuncSetAttribute(gemm_tc)", e);
@@ -755,6 +762,13 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     if (e != cudaSuccess) return pb_set_cuda_error("cudaLaunchKernelEx(gemm_tc cta_group::2)", e);
   }
   return pb_check_launch("gemm_tc_kernel");
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CG2>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
+                  const CUtensorMap& tx, const GemmKParams& kp, cudaStream_t stream, bool fast) {
+  return fast ? launch_impl<BLOCK_N, A_MN, B_MN, CG2, true>(ta, tb, tc, tp, tx, kp, stream)
+              : launch_impl<BLOCK_N, A_MN, B_MN, CG2, false>(ta, tb, tc, tp, tx, kp, stream);
 }
 
 }  // namespace pb
@@ -855,27 +869,34 @@ extern "C" int pb_gemm_bf16(const pb_gemm_desc* d, void* stream_) {
     kp.tma_x = 1;
   }
 
+  // specialised epilogue: everything the epilogue touches goes through TMA and none of the fp32 / legacy paths is needed
+  static const int fast_env = getenv("PIANOBART_B200_FAST_EPI") ? atoi(getenv("PIANOBART_B200_FAST_EPI")) : 1;
+  const bool fast = fast_env && kp.tma_c && kp.split_k == 1 && (d->N % 32) == 0 &&
+                    !(d->flags & (PB_GEMM_OUT_F32 | PB_GEMM_ATOMIC_ACC | PB_GEMM_RES_F32 | PB_GEMM_AUX_PREACT | PB_GEMM_MUL_DGELU)) &&
+                    (d->residual == nullptr || kp.tma_pre == 1) && (!(d->flags & PB_GEMM_MUL_AUX) || kp.tma_pre == 2) &&
+                    (!(d->flags & PB_GEMM_AUX_DGELU) || kp.tma_x) && d->r_row_mod <= 0;
+
   const int variant = (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
   if (cg2) {
     switch (variant) {
-      case 0: return launch<256, false, false, true>(ta, tb, tc, tp, tx, kp, stream);
-      case 1: return launch<256, false, true, true>(ta, tb, tc, tp, tx, kp, stream);
-      case 2: return launch<256, true, false, true>(ta, tb, tc, tp, tx, kp, stream);
-      default: return launch<256, true, true, true>(ta, tb, tc, tp, tx, kp, stream);
+      case 0: return launch<256, false, false, true>(ta, tb, tc, tp, tx, kp, stream, fast);
+      case 1: return launch<256, false, true, true>(ta, tb, tc, tp, tx, kp, stream, fast);
+      case 2: return launch<256, true, false, true>(ta, tb, tc, tp, tx, kp, stream, fast);
+      default: return launch<256, true, true, true>(ta, tb, tc, tp, tx, kp, stream, fast);
     }
   } else if (block_n == 256) {
     switch (variant) {
-      case 0: return launch<256, false, false, false>(ta, tb, tc, tp, tx, kp, stream);
-      case 1: return launch<256, false, true, false>(ta, tb, tc, tp, tx, kp, stream);
-      case 2: return launch<256, true, false, false>(ta, tb, tc, tp, tx, kp, stream);
-      default: return launch<256, true, true, false>(ta, tb, tc, tp, tx, kp, stream);
+      case 0: return launch<256, false, false, false>(ta, tb, tc, tp, tx, kp, stream, fast);
+      case 1: return launch<256, false, true, false>(ta, tb, tc, tp, tx, kp, stream, fast);
+      case 2: return launch<256, true, false, false>(ta, tb, tc, tp, tx, kp, stream, fast);
+      default: return launch<256, true, true, false>(ta, tb, tc, tp, tx, kp, stream, fast);
     }
   } else {
     switch (variant) {
-      case 0: return launch<128, false, false, false>(ta, tb, tc, tp, tx, kp, stream);
-      case 1: return launch<128, false, true, false>(ta, tb, tc, tp, tx, kp, stream);
-      case 2: return launch<128, true, false, false>(ta, tb, tc, tp, tx, kp, stream);
-      default: return launch<128, true, true, false>(ta, tb, tc, tp, tx, kp, stream);
+      case 0: return launch<128, false, false, false>(ta, tb, tc, tp, tx, kp, stream, fast);
+      case 1: return launch<128, false, true, false>(ta, tb, tc, tp, tx, kp, stream, fast);
+      case 2: return launch<128, true, false, false>(ta, tb, tc, tp, tx, kp, stream, fast);
+      default: return launch<128, true, true, false>(ta, tb, tc, tp, tx, kp, stream, fast);
     }
   }
 }
