@@ -92,6 +92,28 @@ __device__ __forceinline__ void store_chunk(uint8_t* tile, int r, int c0, const 
     *reinterpret_cast<uint4*>(half + (((cbase + g) ^ (r & 7)) << 4)) = v;
   }
 }
+// Output epilogue: accumulator rows are staged (bf16) in a shared-memory tile that is free by then, in the same two-half
+// 128-byte-swizzled layout the operand tiles use, and written with two bulk tensor stores - a thread owns one row, so direct
+// global stores would cost 32 L1 wavefronts per warp instruction (3200 cycles per CTA in the forward kernel, profiles/).
+// Rows beyond the sequence are clipped by the tensor map.
+__device__ __forceinline__ void stage_row_chunk(uint8_t* tile, int r, int hf, int c, const uint32_t (&v)[32], float scale) {
+  uint8_t* rowp = tile + hf * HALF_BYTES + r * 128;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 o;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int tt = 0; tt < 4; ++tt)
+      h2[tt] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * tt]) * scale, __uint_as_float(v[g * 8 + 2 * tt + 1]) * scale);
+    *reinterpret_cast<uint4*>(rowp + (((c * 4 + g) ^ (r & 7)) << 4)) = o;
+  }
+}
+__device__ __forceinline__ void store_tile_tma(const CUtensorMap* m, const uint8_t* tile, int row0, int h, int b) {
+  tma_store_4d(m, tile, 0, row0, h, b);
+  tma_store_4d(m, tile + HALF_BYTES, 64, row0, h, b);
+  bulk_commit();
+}
+
 constexpr int NCOMPUTE = 256;             // 8 softmax / epilogue warps: (TMEM lane quadrant) x (column half)
 constexpr int NTHREADS = 64 + NCOMPUTE;
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -155,8 +177,9 @@ constexpr int FWD_MAX_SK = 8192;            // keys per sequence supported by th
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
-                const __grid_constant__ CUtensorMap tv, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 64) PB_TR(0, 63, 0);
   __shared__ __align__(8) uint64_t q_full, k_full[NSBUF], k_empty[NSBUF], v_full[2], v_empty[2], s_full[NSBUF], p_full, pv_done;
   __shared__ uint32_t tmem_base_smem;
   __shared__ uint32_t s_keep[FWD_MAX_SK / 32];   // key-padding bitmap of the whole key sequence (built once)
@@ -184,6 +207,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   pdl_wait();   // global memory of the preceding kernel is visible from here on
+  if (threadIdx.x == 64) PB_TR(0, 63, 1);
   const uint32_t tmem = tmem_base_smem;
   const uint32_t tS0 = tmem, tO = tmem + NSBUF * AT;   // S buffers at columns 0 / 128 / 256, O at 384
 
@@ -371,35 +395,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     }
     mbar_wait(&pv_done, (nkb - 1) & 1);
     tc_fence_after();
+    if (threadIdx.x == 64) PB_TR(0, 63, 2);
     compute_bar_sync();
     s_red[0][hf][r] = l;
     compute_bar_sync();
     l = s_red[0][0][r] + s_red[0][1][r];
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat16* orow = p.o + (long long)b * p.o_sb + (long long)qg * p.ldo + h * AT + hf * 64;
+    // O rows -> the Q tile (every S MMA has retired) -> two bulk tensor stores
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
       tmem_ld32(tO + lane_addr + hf * 64 + c * 32, v);
       tmem_ld_wait();
-      if (qg < p.Sq) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o4;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o4);
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt)
-            h2[tt] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * tt]) * inv, __uint_as_float(v[g * 8 + 2 * tt + 1]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o4;
-        }
-      }
+      stage_row_chunk(sm.t[0], r, hf, c, v, inv);
     }
+    fence_proxy_async_smem();
+    compute_bar_sync();
+    if (tid == 0) { store_tile_tma(&to, sm.t[0], q0, h, b); bulk_wait_read<0>(); }
     if (qg < p.Sq && hf == 0) p.lse[((long long)b * p.H + h) * p.Sq + qg] = (l > 0.f) ? (m_used + log2f(l)) : INFINITY;
+    if (threadIdx.x == 64) PB_TR(0, 63, 3);
     tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
+  if (threadIdx.x == 64) PB_TR(0, 63, 4);
 }
 
 // ===================================================================================== backward: dK, dV
@@ -415,7 +435,8 @@ constexpr int NQ = 5;                           // Q/dO ring depth
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
-                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, const AttnParams p) {
+                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                    const __grid_constant__ CUtensorMap tdk, const __grid_constant__ CUtensorMap tdv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t kv_full, qdo_full[NQ], qdo_empty[NQ], sdp_full[2], pds_full[2], acc_full;
   __shared__ uint32_t tmem_base_smem;
@@ -593,11 +614,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     // epilogue: thread = (key row, 64-column half of head_dim)
     mbar_wait(&acc_full, 0);
     tc_fence_after();
+    // dV rows -> the V tile, dK rows -> the K tile (all S^T / dP^T MMAs have retired) -> bulk tensor stores
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t tacc = which == 0 ? tdV : tdK;
-      __nv_bfloat16* dst = which == 0 ? (p.dv + (long long)b * p.dv_sb + (long long)kg * p.lddv + h * AT)
-                                      : (p.dk + (long long)b * p.dk_sb + (long long)kg * p.lddk + h * AT);
+      uint8_t* tile = which == 0 ? gV : gK;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
@@ -608,19 +629,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        if (kg < p.Sk) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 o;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int tt = 0; tt < 4; ++tt)
-              h2[tt] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * tt]), __uint_as_float(v[g * 8 + 2 * tt + 1]));
-            *reinterpret_cast<uint4*>(dst + hf * 64 + c * 32 + g * 8) = o;
-          }
-        }
+        stage_row_chunk(tile, r, hf, c, v, 1.0f);
       }
     }
+    fence_proxy_async_smem();
+    compute_bar_sync();
+    if (tid == 0) { store_tile_tma(&tdv, gV, k0, h, b); store_tile_tma(&tdk, gK, k0, h, b); bulk_wait_read<0>(); }
     tc_fence_before();
   }
   tc_fence_before();
@@ -638,7 +652,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 // two-deep ring (released after dP).
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
-                   const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, const AttnParams p) {
+                   const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                   const __grid_constant__ CUtensorMap tdq, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t qdo_full, k_full[3], k_empty[3], v_full[2], v_empty[2], s_full[2], dp_full, dp_free, ds_full,
       acc_full;
@@ -812,24 +827,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     }
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    __nv_bfloat16* dst = p.dq + (long long)b * p.dq_sb + (long long)qg * p.lddq + h * AT + hf * 64;
+    // dQ rows -> the Q tile (every S MMA has retired) -> two bulk tensor stores
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
       tmem_ld32(tdQ + lane_addr + hf * 64 + c * 32, v);
       tmem_ld_wait();
-      if (qok) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt)
-            h2[tt] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * tt]), __uint_as_float(v[g * 8 + 2 * tt + 1]));
-          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
-        }
-      }
+      stage_row_chunk(sm.t[0], r, hf, c, v, 1.0f);
     }
+    fence_proxy_async_smem();
+    compute_bar_sync();
+    if (tid == 0) { store_tile_tma(&tdq, sm.t[0], q0, h, b); bulk_wait_read<0>(); }
     tc_fence_before();
   }
   tc_fence_before();
@@ -923,17 +931,18 @@ extern "C" int pb_attn_fwd(const pb_attn_desc* d, void* stream_) {
   if (attn_check(d)) return -1;
   if (d->Sk > FWD_MAX_SK) return pb_set_error("pb_attn_fwd: Sk > 8192 not supported (in-kernel key-padding bitmap)");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, to;
   if (attn_tmap(&tq, d->q, d->Sq, d->ldq, d->H, d->B, (long long)d->Sq * d->ldq)) return -1;
   if (attn_tmap(&tk, d->k, d->Sk, d->ldk, d->H, d->B, (long long)d->Sk * d->ldk)) return -1;
   if (attn_tmap(&tv, d->v, d->Sk, d->ldv, d->H, d->B, (long long)d->Sk * d->ldv)) return -1;
+  if (attn_tmap(&to, d->o, d->Sq, d->ldo, d->H, d->B, (long long)d->Sq * d->ldo)) return -1;
   AttnParams p;
   fill_params(p, d);
   static bool attr = false;
   const int smem = 6 * TILE_BYTES + 1024;
   if (set_smem(attn_fwd_kernel, smem, attr)) return -1;
   dim3 grid((d->Sq + AT - 1) / AT, d->H, d->B);
-  PB_LAUNCH(attn_fwd_kernel, grid, NTHREADS, smem, stream, tq, tk, tv, p);
+  PB_LAUNCH(attn_fwd_kernel, grid, NTHREADS, smem, stream, tq, tk, tv, to, p);
   return pb_check_launch("attn_fwd_kernel");
 }
 
@@ -960,14 +969,18 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
   const int smem1 = 2 * TILE_BYTES + 2 * NQ * QT_BYTES + 1024, smem2 = 7 * TILE_BYTES + 1024;
   if (set_smem(attn_bwd_dkv_kernel, smem1, attr1)) return -1;
   if (set_smem(attn_bwd_dq_kernel, smem2, attr2)) return -1;
+  CUtensorMap tdq, tdk, tdv;   // output maps (TMA-store epilogues)
+  if (attn_tmap(&tdq, d->dq, d->Sq, d->lddq, d->H, d->B, (long long)d->Sq * d->lddq)) return -1;
+  if (attn_tmap(&tdk, d->dk, d->Sk, d->lddk, d->H, d->B, (long long)d->Sk * d->lddk)) return -1;
+  if (attn_tmap(&tdv, d->dv, d->Sk, d->lddv, d->H, d->B, (long long)d->Sk * d->lddv)) return -1;
   CUtensorMap tq64, tdo64;   // 64-query boxes for the dK/dV kernel
   if (attn_tmap(&tq64, d->q, d->Sq, d->ldq, d->H, d->B, (long long)d->Sq * d->ldq, QB)) return -1;
   if (attn_tmap(&tdo64, d->dout, d->Sq, d->lddo, d->H, d->B, (long long)d->Sq * d->lddo, QB)) return -1;
   dim3 g1((d->Sk + AT - 1) / AT, d->H, d->B);
-  PB_LAUNCH(attn_bwd_dkv_kernel, g1, NTHREADS, smem1, stream, tq64, tk, tv, tdo64, p);
+  PB_LAUNCH(attn_bwd_dkv_kernel, g1, NTHREADS, smem1, stream, tq64, tk, tv, tdo64, tdk, tdv, p);
   if (pb_check_launch("attn_bwd_dkv_kernel")) return -1;
   dim3 g2((d->Sq + AT - 1) / AT, d->H, d->B);
-  PB_LAUNCH(attn_bwd_dq_kernel, g2, NTHREADS, smem2, stream, tq, tk, tv, tdo, p);
+  PB_LAUNCH(attn_bwd_dq_kernel, g2, NTHREADS, smem2, stream, tq, tk, tv, tdo, tdq, p);
   return pb_check_launch("attn_bwd_dq_kernel");
 }
 

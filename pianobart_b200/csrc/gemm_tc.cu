@@ -621,7 +621,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (lane == 0) bulk_wait_all();   // outstanding TMA stores read this CTA's shared memory
+    if (lane == 0) bulk_wait_read<0>();   // outstanding TMA stores still read this CTA's shared memory
   }
 
   tc_fence_before();

@@ -19,3 +19,4 @@ for role in (1, 2):
     print('softmax warp %d: [bar, s/dp_full ok, dP read (2nd chunk), chunk0 math done, dq_done ok, arrived]' % role)
     for j in range(nb):
         print(j, [int(x - t0) if x > 0 else -1 for x in t[role, j, :7]])
+print('CTA life (thread 64): [entry, prologue done, last PV done, O stored, after dealloc]', [int(x - t0) if x > 0 else -1 for x in t[0, 63, :5]])
