@@ -98,7 +98,9 @@ int pb_gemm_f32(const pb_gemm_desc* d, void* stream);
  * autograd without materialising scores: encoder self-attention (key padding), decoder self-attention
  * (causal and key padding), decoder cross-attention (encoder key padding).  All tensors bf16, laid out
  * [B, S, H*hd] with row stride ld* (elements) so that slices of the fused QKV activation are used in place.
- * lse fp32 [B,H,Sq] (log2 domain) is written by forward and read by backward; dvec fp32 [B,H,Sq] is scratch. */
+ * lse fp32 [B,H,Sq] (log2 domain) is written by forward and read by backward; dvec fp32 [B,H,Sq] is scratch.
+ * Outputs (o, dq, dk, dv) are written with bulk tensor stores: pointers 16-byte aligned, row strides multiples of 8
+ * elements.  Forward supports Sk <= 8192 (the key-padding bitmap of a sequence is kept in shared memory). */
 typedef struct pb_attn_desc {
   const void* q; const void* k; const void* v;
   void* o;            /* forward output / backward input */

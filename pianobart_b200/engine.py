@@ -133,6 +133,23 @@ def _num_sms():
     return _NUM_SMS
 
 
+def choose_split_k(n_out, n_in, M, bn, pairs, num_sms):
+    """Split-K factor of a weight-gradient GEMM dW[n_out, n_in] = dY[M, n_out]^T X[M, n_in] from a wave model of the
+    persistent kernel: cost(s) = ceil(tiles * s / slots) * (k-blocks / s + c), c = the per-unit pipeline fill + fp32-reduction
+    epilogue in k-block units (fitted on tools/gpu_wgrad_split.py: 31 vs 39 us for 1024 x 1024, 55 vs 62 us for 2048 x 1024
+    against the earlier "two units per SM" rule).  pairs: the library will run cta_group::2 tiles (256 rows, one per SM pair)."""
+    tile_m = 256 if pairs else 128
+    tiles = ((n_out + tile_m - 1) // tile_m) * ((n_in + bn - 1) // bn)
+    slots = max(1, num_sms // 2 if pairs else num_sms)
+    kblocks = (M + 63) // 64
+    split, best = 1, None
+    for sk in range(1, min(32, max(1, kblocks // 4)) + 1):
+        cost = -(-tiles * sk // slots) * (kblocks / sk + 8.0)
+        if best is None or cost < best - 1e-9:
+            split, best = sk, cost
+    return split
+
+
 class Plan:
     """A recorded list of (function, args) library calls; run() replays it on a stream."""
 
@@ -211,20 +228,8 @@ class Plan:
     def wgrad(self, dy, x, dw, n_out, n_in, M, ld_dy, ld_x, name='wgrad'):
         """dW[n_out, n_in] += dY[M, n_out]^T X[M, n_in]   (fp32 atomic accumulate, split-K)."""
         bn = int(os.environ.get('PIANOBART_B200_WGRAD_BN', '256'))
-        # split-K from a wave model of the persistent kernel: cost(s) = ceil(tiles * s / slots) * (k-blocks / s + c), c = the
-        # per-unit fill + fp32-reduction epilogue in k-block units (fitted on tools/gpu_wgrad_split.py: 31 vs 39 us for
-        # 1024 x 1024, 55 vs 62 us for 2048 x 1024 against the earlier "two units per SM" rule)
         pairs = n_out >= 1024 and bn == 256 and os.environ.get('PIANOBART_B200_CG2', '1') != '0'   # library's cta_group::2 rule
-        tiles = ((n_out + (255 if pairs else 127)) // (256 if pairs else 128)) * ((n_in + bn - 1) // bn)
-        slots = _num_sms() // 2 if pairs else _num_sms()
-        kblocks = (M + 63) // 64
-        split, best = 1, None
-        for sk in range(1, max(1, kblocks // 4) + 1):
-            cost = -(-tiles * sk // slots) * (kblocks / sk + 8.0)
-            if best is None or cost < best - 1e-9:
-                split, best = sk, cost
-            if sk >= 32:
-                break
+        split = choose_split_k(n_out, n_in, M, bn, pairs, _num_sms())
         self.gemm(dy, x, dw, n_out, n_in, M, ld_dy, ld_x, n_in, a_mn=1, b_mn=1,
                   flags=L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC, split_k=split, block_n=bn, name=name)
 

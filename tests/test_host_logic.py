@@ -106,3 +106,14 @@ def test_param_layout_fused_groups_are_contiguous():
     assert los[0][0] == 0 and los[-1][1] == lay.size
     for (a, b), (c, d) in zip(los[:-1], los[1:]):
         assert b == c
+
+
+def test_wgrad_split_k_wave_model():
+    """engine.choose_split_k picks the split measured fastest on a 148-SM B200 (tools/gpu_wgrad_split.py) and never
+    exceeds a quarter of the k-blocks."""
+    from pianobart_b200.engine import choose_split_k
+    M = 16 * 1024
+    for (n_out, n_in), want in {(1024, 1024): 4, (3072, 1024): 3, (2048, 1024): 2, (1024, 2048): 2, (1280, 1024): 7}.items():
+        assert choose_split_k(n_out, n_in, M, 256, True, 148) == want
+    assert choose_split_k(64, 64, 128, 256, False, 148) == 1          # 2 k-blocks: no split
+    assert 1 <= choose_split_k(256, 256, 4096, 128, False, 148) <= 16
