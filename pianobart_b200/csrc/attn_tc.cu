@@ -6,17 +6,22 @@
 //
 // Three kernels share one tile convention: every operand tile is [128 rows x 128 cols] bf16 stored as two
 // 64-column halves of [128 x 128 B] with the 128-byte swizzle.  The same physical tile can be consumed
-//   * K-major  : rows = M/N index, columns = contraction index  (Q, K for S=QK^T; dO, V for dP=dO V^T; P, dS as A)
-//   * MN-major : rows = contraction index, columns = M/N index  (V for O=PV; P^T, dS^T, dO, Q, K in backward)
-// so P / dS are written to shared memory once and feed both dQ = dS K and dK = dS^T Q.
+//   * K-major  : rows = M/N index, columns = contraction index  (Q, K for S=QK^T; dO, V for dP=dO V^T)
+//   * MN-major : rows = contraction index, columns = M/N index  (V for O=PV; K for dQ=dS K; dO, Q for dV, dK)
+// P, dS (and their transposes) never touch shared memory: the softmax warps write them back (bf16, packed) over the
+// TMEM columns of the S / dP values they were derived from, and the next MMA reads them as its A operand from TMEM.
 //
-//   attn_fwd     CTA = (b, h, 128 queries)  loop over key blocks:  S=QK^T -> online softmax -> O += P V ; LSE out
-//   attn_bwd_dkv CTA = (b, h, 128 keys)     loop over query blocks: S, dP -> P, dS -> dV += P^T dO, dK += dS^T Q
-//   attn_bwd_dq  CTA = (b, h, 128 queries)  loop over key blocks:  S, dP -> dS -> dQ += dS K
+//   attn_fwd     CTA = (b, h, 128 queries)  loop over 128-key blocks:  S=QK^T -> online softmax -> O += P V ; LSE out
+//   attn_bwd_dkv CTA = (b, h, 128 keys)     loop over 64-query blocks: S^T, dP^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q
+//   attn_bwd_dq  CTA = (b, h, 128 queries)  loop over 128-key blocks:  S, dP -> dS -> dQ += dS K
 //   attn_bwd_prep                           D = rowsum(dO * O)
 // Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax / epilogue:
 // thread <-> (TMEM lane = tile row, 64-column half), two warps per scheduler so that the dependent ALU chains of
 // one warp hide behind the other (a single warp per scheduler left the kernel latency-bound, profiles/).
+// Measured facts the pipelines are built around (tools/micro/mma_bench.cu, -DPB_TRACE phase traces): one tcgen05.mma
+// (M=128, K=16) holds the tensor pipe for max(~72, N/2) cycles whatever the operand source; a TMA tile refill takes
+// 1500-2300 cycles under load; the MUFU pipe (ex2) is what bounds the softmax.  Outputs leave through bulk tensor
+// stores from an operand tile that is free by then.
 #include "ptx.cuh"
 #include "pb_internal.h"
 

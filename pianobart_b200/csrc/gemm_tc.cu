@@ -12,9 +12,14 @@
 //   * persistent grid, one CTA per SM, 320 threads = 10 warps with fixed roles:
 //       warp 0   TMA producer   (cp.async.bulk.tensor 4D, 128B swizzle, mbarrier complete_tx)
 //       warp 1   MMA issuer     (one elected thread issues tcgen05.mma, commits to mbarriers)
-//       warp 2-9 epilogue       (tcgen05.ld TMEM->registers, bias/GELU/residual/dropout, global stores;
-//                                8 warps = lane quadrant x column half so two warps share a scheduler and
-//                                hide each other's load latency; bias staged in smem once per tile)
+//       warp 2-9 epilogue       (tcgen05.ld TMEM->registers, bias / GELU + gelu' / dropout / residual; a thread owns
+//                                one accumulator row, so C, the residual / aux input and the aux output move as
+//                                [32 x 32] boxes staged in shared memory by bulk tensor copies instead of row-per-
+//                                thread global accesses; 8 warps = lane quadrant x column half so two warps share
+//                                a scheduler; bias staged in smem once per tile; a specialised instantiation (FAST)
+//                                carries only the bf16 TMA path the training step uses)
+//   * cta_group::2: for M >= 1024 a CTA pair (cluster of 2) computes a 256 x 256 tile, each CTA staging its 128 rows
+//     of A and half of B.
 //   * CTA tile 128 x BLOCK_N (128 or 256), BLOCK_K = 64 bf16 = one 128-byte swizzle row,
 //     multi-stage smem ring (full/empty mbarriers), two TMEM accumulators (2 x BLOCK_N columns)
 //     so the epilogue of tile i overlaps the main loop of tile i+1.
