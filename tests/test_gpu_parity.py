@@ -108,6 +108,98 @@ def test_gemm_tc_epilogues_and_splitk():
     assert _rel(acc.cpu(), ref2.cpu()) < 1e-5
 
 
+
+# --------------------------------------------------------------------------- fused attention vs torch fp32
+@pytest.mark.parametrize('B,H,Sq,Sk,causal,pad,fused', [
+    (1, 1, 128, 128, 0, 0, True),      # single tile
+    (2, 2, 384, 384, 0, 1, True),      # encoder self-attention with key padding
+    (2, 2, 384, 384, 1, 1, True),      # decoder self-attention: causal and padding
+    (2, 2, 256, 384, 0, 1, False),     # cross-attention (separate Q and fused K|V activations)
+    (1, 2, 200, 200, 1, 1, True),      # tails: S % 128 != 0
+    (1, 1, 96, 320, 0, 1, False),      # cross tails, Sq < one tile
+])
+def test_flash_attention_fwd_bwd_vs_torch(B, H, Sq, Sk, causal, pad, fused):
+    """pb_attn_fwd / pb_attn_bwd (tcgen05 kernels, TMEM-resident P / dS, TMA-store outputs) against the fp32 definition
+    softmax(Q K^T hd^-0.5 + mask) V and its autograd; bf16 operands: max-norm relative error <= 3e-2."""
+    L, lib = _lib()
+    dev = 'cuda:0'
+    torch.manual_seed(11)
+    hd = 128; d = H * hd
+    if fused:
+        qkv = (torch.randn(B, Sq, 3 * d, device=dev) * 0.7).bfloat16()
+        q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        ldq = ldk = ldv = 3 * d
+        dqkv = torch.zeros_like(qkv); dq, dk, dv = dqkv[..., :d], dqkv[..., d:2 * d], dqkv[..., 2 * d:]
+    else:
+        q = (torch.randn(B, Sq, d, device=dev) * 0.7).bfloat16()
+        kv = (torch.randn(B, Sk, 2 * d, device=dev) * 0.7).bfloat16()
+        k, v = kv[..., :d], kv[..., d:]
+        ldq, ldk, ldv = d, 2 * d, 2 * d
+        dq = torch.zeros_like(q); dkv = torch.zeros_like(kv); dk, dv = dkv[..., :d], dkv[..., d:]
+    keep = torch.ones(B, Sk, device=dev, dtype=torch.uint8)
+    if pad:
+        keep = (torch.rand(B, Sk, device=dev) > 0.3).to(torch.uint8); keep[:, 0] = 1
+    o = torch.zeros(B, Sq, d, device=dev, dtype=torch.bfloat16)
+    do = (torch.randn(B, Sq, d, device=dev) * 0.5).bfloat16()
+    lse = torch.zeros(B, H, Sq, device=dev); dvec = torch.zeros(B, H, Sq, device=dev)
+    a = L.AttnDesc()
+    a.q, a.k, a.v, a.o, a.dout = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr()
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.ldq, a.ldk, a.ldv, a.ldo, a.lddo = ldq, ldk, ldv, d, d
+    a.lddq, a.lddk, a.lddv = ldq, ldk, ldv
+    a.lse, a.dvec, a.key_keep = lse.data_ptr(), dvec.data_ptr(), keep.data_ptr()
+    a.B, a.H, a.Sq, a.Sk, a.hd, a.causal, a.scale = B, H, Sq, Sk, hd, causal, hd ** -0.5
+    L.check(lib.pb_attn_fwd(C.byref(a), L.stream_ptr()), 'attn_fwd')
+    L.check(lib.pb_attn_bwd(C.byref(a), L.stream_ptr()), 'attn_bwd')
+    torch.cuda.synchronize()
+    qf = q.float().view(B, Sq, H, hd).transpose(1, 2).detach().requires_grad_(True)
+    kf = k.float().view(B, Sk, H, hd).transpose(1, 2).detach().requires_grad_(True)
+    vf = v.float().view(B, Sk, H, hd).transpose(1, 2).detach().requires_grad_(True)
+    sc = (qf @ kf.transpose(-1, -2)) * hd ** -0.5
+    allow = (keep != 0)[:, None, None, :].expand(B, H, Sq, Sk)
+    if causal:
+        allow = allow & torch.ones(Sq, Sk, dtype=torch.bool, device=dev).tril()
+    pr = torch.softmax(sc.masked_fill(~allow, float('-inf')), -1)
+    ref = (pr @ vf).transpose(1, 2).reshape(B, Sq, d)
+    ref.backward(do.float())
+    gq = qf.grad.transpose(1, 2).reshape(B, Sq, d)
+    gk = kf.grad.transpose(1, 2).reshape(B, Sk, d)
+    gv = vf.grad.transpose(1, 2).reshape(B, Sk, d)
+    for name, got, want in (('o', o, ref.detach()), ('dq', dq, gq), ('dk', dk, gk), ('dv', dv, gv)):
+        err = ((got.float() - want).abs().max() / want.abs().max()).item()
+        assert err < 3e-2, (name, err)
+    # log-sum-exp rows (log2 domain) of the visible queries
+    lse_ref = torch.logsumexp(sc.masked_fill(~allow, float('-inf')), -1) * 1.4426950408889634
+    assert torch.allclose(lse[:, :, :Sq], lse_ref.detach(), atol=2e-2, rtol=1e-3)
+
+
+def test_octuple_embed_bwd_vs_index_add():
+    """pb_octuple_embed_bwd (shared-memory accumulators per 32-column table slice) against torch index_add, skewed ids."""
+    from pianobart_b200.vocab import build_octuple_vocab
+    L, lib = _lib()
+    dev = 'cuda:0'
+    e2w, _ = build_octuple_vocab()
+    ntok = [len(e2w[k]) for k in e2w]
+    off = [0]
+    for n in ntok[:-1]:
+        off.append(off[-1] + n)
+    torch.manual_seed(5)
+    for M in (1000, 16384):
+        ids = torch.stack([torch.randint(0, n, (M,), device=dev) for n in ntok], 1).int().contiguous()
+        ids[:, 0] = (torch.arange(M, device=dev) // 64 % ntok[0]).int()
+        dx = torch.randn(M, 2048, device=dev).bfloat16()
+        tab = torch.zeros(sum(ntok), 256, device=dev)
+        arr = (C.c_int * 8)(*ntok)
+        P = C.c_void_p
+        L.check(lib.pb_octuple_embed_bwd(P(ids.data_ptr()), 0, P(dx.data_ptr()), P(tab.data_ptr()), C.c_longlong(M), arr,
+                                         C.c_float(16.0), 1, L.stream_ptr()), 'embed_bwd')
+        ref = torch.zeros_like(tab)
+        for a in range(8):
+            ref.index_add_(0, ids[:, a].long() + off[a], dx[:, a * 256:(a + 1) * 256].float() * 16.0)
+        torch.cuda.synchronize()
+        assert (tab - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
 # --------------------------------------------------------------------------- single kernels vs torch fp32
 @pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
 def test_layernorm_fwd_bwd(dtype):
