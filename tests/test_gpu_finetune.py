@@ -84,6 +84,37 @@ def test_generation_finetune_loss_matches_oracle():
     assert np.allclose(losses, [l.item() * e for l, e in zip(ref_losses, O.GEN_EXTRA_W)], rtol=1e-5)
 
 
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_generation_trainer_matches_executed_reference(dtype):
+    """Row A16 pinned to the REAL reference: tests/golden/genft_tiny.npz was recorded by running
+    GenerationTrainer.iteration of /root/reference/finetune_generation.py:140-258 (valid and train mode, dropout 0, lr 0;
+    tools/make_golden.py golden_genft).  Loss, per-head losses, pre-clip gradient norm and gradients must agree."""
+    from pianobart_b200.finetune_generation import GenerationTrainer
+    g = load_golden('genft_tiny')
+    pb, lm = build_cuda_model(g['cfg'], int(g['seed']), dtype, dropout=0.0)
+    tr = GenerationTrainer(pb, None, None, None, 0.0, None, False, [0], model=lm, verbose=False)
+    x = torch.from_numpy(g['x'].astype(np.int64))
+    y = torch.from_numpy(g['y'].astype(np.int64))
+    tol = 1e-5 if dtype == 'fp32' else 1e-2
+    lm.eval()
+    loss, losses, accs = tr.step(x, y, train=False)
+    extra = np.array([1, 1, 0.3, 1.5, 1, 1, 0.3, 0.3])
+    assert abs(loss - float(g['valid_total'])) / float(g['valid_total']) < tol
+    assert np.allclose(losses, g['valid_losses'] * extra, rtol=tol * 10)
+    if dtype == 'fp32':
+        assert np.allclose(accs, g['valid_acc_rounded'], atol=1e-4)
+    lm.train()
+    loss, losses, accs = tr.step(x, y, train=True)
+    torch.cuda.synchronize()
+    assert abs(loss - float(g['train_total'])) / float(g['train_total']) < tol
+    gt = tol * 10 if dtype == 'fp32' else 5e-2
+    for k in g.files:
+        if k.startswith('grad:'):
+            assert _rel(pb.flat_grad(k[5:]).cpu().numpy(), g[k]) < gt, k
+    gn = float(torch.sqrt((pb._grad.double() ** 2).sum()).item())
+    assert abs(gn - float(g['grad_norm_preclip'])) / float(g['grad_norm_preclip']) < (1e-4 if dtype == 'fp32' else 2e-2)
+
+
 @pytest.mark.parametrize('seq', [True, False])
 def test_finetune_trainer_steps_reduce_loss(seq):
     """FinetuneTrainer mirror (finetune.py:152-256): a few optimisation steps on a fixed batch reduce the loss; the

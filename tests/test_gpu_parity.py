@@ -117,6 +117,14 @@ def test_gemm_tc_epilogues_and_splitk():
     (2, 2, 256, 384, 0, 1, False),     # cross-attention (separate Q and fused K|V activations)
     (1, 2, 200, 200, 1, 1, True),      # tails: S % 128 != 0
     (1, 1, 96, 320, 0, 1, False),      # cross tails, Sq < one tile
+    # BASELINE sequence length (S = 1024, H = 8): 8 key blocks / 16 query blocks -> the 3-deep K ring, the 3-deep dQ K/V ring
+    # and the 5-deep dK/dV Q/dO ring wrap 2-3 times with mbarrier parity flips
+    (2, 8, 1024, 1024, 0, 1, True),    # encoder self-attention + key padding
+    (2, 8, 1024, 1024, 1, 1, True),    # decoder self-attention: causal + padding
+    (2, 8, 1024, 768, 0, 1, False),    # cross-attention, Sq != Sk
+    (2, 8, 768, 1024, 0, 1, False),    # cross-attention, Sq < Sk
+    (1, 8, 1000, 1000, 1, 1, True),    # S = 1000 tail, causal
+    (1, 8, 1000, 1000, 0, 0, True),    # S = 1000 tail, no padding
 ])
 def test_flash_attention_fwd_bwd_vs_torch(B, H, Sq, Sk, causal, pad, fused):
     """pb_attn_fwd / pb_attn_bwd (tcgen05 kernels, TMEM-resident P / dS, TMA-store outputs) against the fp32 definition
@@ -329,24 +337,53 @@ def test_forward_loss_grads_vs_reference(name, dtype):
 
 
 @pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
-def test_default_model_loss_vs_reference(dtype):
-    """BASELINE.json configs[0] scale: default pretrain.py model (d=1024, 8+8 layers, S=1024), batch 1."""
+def test_default_model_loss_and_gradients_vs_reference(dtype):
+    """BASELINE.json configs[0] scale: default pretrain.py model (d=1024, 8+8 layers, S=1024), batch 1 - forward AND
+    backward.  The fixture holds the reference's loss, sub-sampled logits, two full gradients, the gradient norm of each of
+    the 368 parameters that receive one and the total norm (tools/make_golden.py, real reference executed on CPU)."""
     from oracle import pianobart_oracle as O
     g = load_golden('fwd_default')
     pb, lm = build_cuda_model(g['cfg'], int(g['seed']), dtype)
     lm.eval()
     enc, dec, ori, lmask, em, dm = golden_inputs(g)
-    with torch.no_grad():
-        y = lm(enc, dec, em, dm)
+    y = lm(enc, dec, em, dm)
     total, losses = O.pretrain_loss(y, ori, lmask)
     ref = float(g['total'])
     assert abs(total.item() - ref) / ref < LOSS_TOL[dtype]
     st = int(g['logit_stride'])
-    got = torch.cat(y, -1).cpu().numpy()[:, ::st]
+    got = torch.cat(y, -1).detach().cpu().numpy()[:, ::st]
     assert _rel(got, g['logits_sub']) < (2e-4 if dtype == 'fp32' else 5e-2)
     accs = O.pretrain_accuracy(y, ori, lmask)
     if dtype == 'fp32':
         assert np.allclose([a.item() for a in accs], g['accs'], atol=1e-6)
+    # ---- backward through every kernel of the benched step at the benched sequence length
+    lm.zero_grad()
+    total.backward()
+    sd = dict(lm.named_parameters())
+    tol_full = 2e-4 if dtype == 'fp32' else 5e-2
+    for k in g.files:
+        if k.startswith('grad:'):
+            n = k[5:]
+            kk = n if n.startswith('mask_lm') else 'pianobart.' + n
+            assert _rel(sd[kk].grad.cpu().numpy(), g[k]) < tol_full, n
+    names = [str(x) for x in g['grad_norm_names']]
+    want = g['grad_norm_vals']
+    worst, worst_name = 0.0, None
+    seen = 0
+    for n, w in zip(names, want):
+        kk = n if n.startswith('mask_lm') else 'pianobart.' + n
+        if kk not in sd or sd[kk].grad is None:
+            continue
+        seen += 1
+        gn = sd[kk].grad.double().norm().item()
+        # (k_proj.bias gradients are mathematically zero - softmax is shift invariant - so small norms get an absolute floor)
+        e = abs(gn - w) / max(w, (1e-3 if dtype == 'fp32' else 1e-2) * float(g['grad_total_norm']))
+        if e > worst:
+            worst, worst_name = e, n
+    assert seen >= 360, seen          # (decoder_linear.* aliases encoder_linear.* and is listed once)
+    assert worst < (1e-3 if dtype == 'fp32' else 5e-2), (worst_name, worst)
+    gt = torch.sqrt(sum((p.grad.double() ** 2).sum() for n, p in sd.items() if p.grad is not None)).item()
+    assert abs(gt - float(g['grad_total_norm'])) / float(g['grad_total_norm']) < (1e-4 if dtype == 'fp32' else 2e-2)
 
 
 def test_fused_step_matches_autograd_path_and_oracle():

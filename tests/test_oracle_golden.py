@@ -114,3 +114,45 @@ def test_infilling_failure_branch():
     assert loss.shape == (32, 8) and not loss.any()
     assert np.array_equal(loss.astype(np.uint8), g['infill_fail_loss_mask'])
     assert random.random() == float(g['infill_fail_state_after'][0])
+
+
+def test_generation_finetune_loss_pinned_to_executed_reference():
+    """Row A16: oracle.generation_finetune_loss == GenerationTrainer.iteration of the reference (finetune_generation.py:
+    140-258) executed by tools/make_golden.py (genft_tiny.npz): per-head losses, total, gradients."""
+    g = load('genft_tiny')
+    d, el, dl, heads, ffn, max_pos = [int(x) for x in g['cfg']]
+    prm = P.make_params(d, el, dl, ffn, max_pos, int(g['seed']))
+    p = {k: torch.tensor(v).requires_grad_(True) for k, v in prm.items() if not k.startswith('decoder_linear')}
+    p['decoder_linear.weight'], p['decoder_linear.bias'] = p['encoder_linear.weight'], p['encoder_linear.bias']
+    x = torch.from_numpy(g['x'].astype(np.int64))
+    y = torch.from_numpy(g['y'].astype(np.int64))
+    keep = (x[:, :, 0] != 256).float()
+    h, _ = O.pianobart_forward(p, O.Cfg(d, el, dl, heads, ffn, max_pos), x, x, keep, keep)   # y_shift = x (:155)
+    total, losses = O.generation_finetune_loss(O.lm_heads(p, h), y, keep)
+    assert abs(total.item() - float(g['train_total'])) < 1e-5 * float(g['train_total'])
+    assert np.allclose([l.item() for l in losses], g['train_losses'], rtol=1e-5)
+    total.backward()
+    for k in g.files:
+        if k.startswith('grad:'):
+            assert np.allclose(p[k[5:]].grad.numpy(), g[k], atol=1e-6 + 1e-4 * np.abs(g[k]).max()), k
+    gn = np.sqrt(sum(v.grad.double().norm().item() ** 2 for n, v in p.items() if not n.startswith('decoder_linear')))
+    assert abs(gn - float(g['grad_norm_preclip'])) < 1e-4 * float(g['grad_norm_preclip'])
+
+
+def test_generate_default_fixture_matches_oracle_sampler():
+    """The default-size decode fixture: oracle.sample_step on the reference's recorded logits reproduces the tokens the
+    reference's sampler picked (model.py:68-107), consuming numpy's stream in the same order (8 draws per step)."""
+    g = load('generate_default')
+    steps = {int(t): i for i, t in enumerate(g['steps'])}
+    seg = np.cumsum([0, 262, 134, 135, 262, 134, 38, 260, 55])
+    for key in ('A', 'B'):
+        rs = np.random.RandomState(0)
+        mism = 0
+        for t in range(1024):
+            if t not in steps:
+                rs.random_sample(8)
+                continue
+            row = torch.from_numpy(g['tf_logits_' + key][steps[t]])
+            tok = O.sample_step([row[seg[j]:seg[j + 1]] for j in range(8)], rs)
+            mism += int((np.asarray(tok) != g['ref_sampled_' + key][steps[t]]).sum())
+        assert mism == 0, (key, mism)

@@ -12,14 +12,14 @@ def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False)
 
 
-def build_cuda_model(cfg, seed, dtype, lm=True, suppress_specials=False, device='cuda:0'):
+def build_cuda_model(cfg, seed, dtype, lm=True, suppress_specials=False, device='cuda:0', dropout=None):
     from pianobart_b200.modules import BartConfig, PianoBart, PianoBartLM
     from pianobart_b200.vocab import build_octuple_vocab
     d, el, dl, heads, ffn, max_pos = [int(x) for x in cfg]
     e2w, w2e = build_octuple_vocab()
     bc = BartConfig(max_position_embeddings=max_pos, d_model=d, encoder_layers=el, decoder_layers=dl,
                     encoder_ffn_dim=ffn, decoder_ffn_dim=ffn, encoder_attention_heads=heads,
-                    decoder_attention_heads=heads, vocab_size=64)
+                    decoder_attention_heads=heads, vocab_size=64, **({} if dropout is None else {'dropout': dropout}))
     pb = PianoBart(bc, e2w, w2e, dtype=dtype)
     model = PianoBartLM(pb) if lm else pb
     prm = P.make_params(d, el, dl, ffn, max_pos, seed)

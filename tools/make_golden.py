@@ -44,11 +44,12 @@ with open(os.path.join(REF, 'Data', 'Octuple.pkl'), 'rb') as f:
 torch.set_num_threads(8)
 
 
-def build_ref(cfg, seed, suppress_specials=False):
+def build_ref(cfg, seed, suppress_specials=False, dropout=None):
     d, el, dl, heads, ffn, max_pos = cfg
+    kw = {} if dropout is None else {'dropout': dropout}
     bc = BartConfig(max_position_embeddings=max_pos, d_model=d, encoder_layers=el, decoder_layers=dl,
                     encoder_ffn_dim=ffn, decoder_ffn_dim=ffn, encoder_attention_heads=heads,
-                    decoder_attention_heads=heads)
+                    decoder_attention_heads=heads, **kw)
     pb = ref_pb.PianoBart(bc, E2W, W2E)
     lm = ref_model.PianoBartLM(pb)
     prm = P.make_params(d, el, dl, ffn, max_pos, seed)
@@ -230,6 +231,106 @@ def golden_generate():
     np.savez_compressed(os.path.join(OUT, 'generate_tiny.npz'), **out)
 
 
+GEN_DEFAULT_STEPS = list(range(40)) + [63, 64, 127, 128, 129, 255, 256, 383, 511, 512, 767, 1000, 1022, 1023]
+
+
+def golden_generate_default():
+    """BASELINE.json configs[2] scale (default model: d=1024, hd=128, 8 decoder layers, S_enc = 1024).
+    (1) teacher-forced per-step logits of the reference for two 1024-token prompts (one padded, one full) - position t of
+        one full forward == what the reference's generate loop (model.py:42-45) computes at step t for the same prefix;
+    (2) reference PianoBartLM.sample (model.py:68-107) called on those logits for every step in order (numpy seed 0);
+    (3) the reference's REAL generate loop at default model width on a 64-token prompt (the O(S^2) loop is affordable there)."""
+    cfg = (1024, 8, 8, 8, 2048, 1024)
+    S = 1024
+    pb, lm = build_ref(cfg, 3, suppress_specials=True)
+    out = dict(cfg=np.array(cfg), seed=3, steps=np.array(GEN_DEFAULT_STEPS))
+    prompts = {'A': P.synth_ids(1, S, 4321, padded=True, min_len=600), 'B': P.synth_ids(1, S, 4322)}
+    forced = {'A': P.synth_ids(1, S, 99), 'B': P.synth_ids(1, S, 100)}
+    with torch.no_grad():
+        for key in ('A', 'B'):
+            enc = torch.from_numpy(prompts[key])
+            enc_mask = (enc[:, :, 0] != pb.bar_pad_word).float()
+            fz = torch.from_numpy(forced[key])
+            dec = torch.empty_like(fz)
+            dec[0, 0] = torch.tensor(pb.sos_word_np)
+            dec[0, 1:] = fz[0, :-1]
+            y = lm(enc, dec, enc_mask, torch.ones(1, S))
+            logits = torch.cat(y, dim=-1)[0].numpy()
+            out['enc_' + key] = prompts[key].astype(np.int16)
+            out['forced_' + key] = forced[key].astype(np.int16)
+            out['tf_logits_' + key] = logits[GEN_DEFAULT_STEPS].copy()
+            np.random.seed(0)
+            smp = np.stack([lm.sample(y, i).numpy() for i in range(S)])
+            out['ref_sampled_' + key] = smp[GEN_DEFAULT_STEPS].astype(np.int16)
+            print('generate_default', key, 'valid', int(enc_mask.sum()), 'logit absmax', float(np.abs(logits).max()))
+        S2 = 64
+        enc = torch.from_numpy(P.synth_ids(1, S2, 4323, padded=True, min_len=40))
+        enc_mask = (enc[:, :, 0] != pb.bar_pad_word).float()
+        out['enc_short'] = enc.numpy().astype(np.int16)
+        for npseed in (0, 1):
+            np.random.seed(npseed)
+            res = lm(enc, encoder_attention_mask=enc_mask, generate=True, device_num=-1)
+            out['result_short_seed%d' % npseed] = res.numpy().astype(np.int16)
+            print('generate_default short loop seed', npseed, 'len', int((res[0, :, 0] != 256).sum()))
+        res = torch.from_numpy(out['result_short_seed0'].astype(np.int64))
+        n = int((res[0, :, 0] != 256).sum())
+        dec = torch.from_numpy(np.tile(pb.pad_word_np, (1, S2, 1)))
+        dec[0, 0] = torch.tensor(pb.sos_word_np)
+        dec[0, 1:n + 1] = res[0, :n] if n + 1 <= S2 else res[0, :S2 - 1]
+        dec_mask = torch.zeros(1, S2)
+        dec_mask[0, :min(n + 1, S2)] = 1
+        out['tf_logits_short'] = torch.cat(lm(enc, dec, enc_mask, dec_mask), dim=-1).numpy()
+    np.savez_compressed(os.path.join(OUT, 'generate_default.npz'), **out)
+
+
+def golden_genft():
+    """GenerationTrainer.iteration (finetune_generation.py:140-258) EXECUTED: `shapesimilarity` (absent pip package, only
+    feeds the printed FAD metric) is stubbed, dropout is 0 so that train mode is deterministic, lr = 0 so that the
+    optimizer step leaves the weights alone.  Records the per-head losses the reference's compute_loss returned, the
+    total, the accuracies, the pre-clip gradient norm clip_grad_norm_ reported and a few (clipped) gradients."""
+    import types
+    stub = types.ModuleType('shapesimilarity')
+    stub.shape_similarity = lambda a, b: 0.0
+    sys.modules['shapesimilarity'] = stub
+    import finetune_generation as ref_fg
+    cfg = (64, 2, 2, 4, 128, 32)
+    B, S = 4, 32
+    pb, lm = build_ref(cfg, 1, dropout=0.0)
+    x = torch.from_numpy(P.synth_ids(B, S, 210, padded=True))
+    y = torch.from_numpy(P.synth_ids(B, S, 77))
+    tr = ref_fg.GenerationTrainer(pb, [(x, y)], [(x, y)], None, 0.0, None, True, [], model=lm)
+    rec = []
+    real_cl = tr.compute_loss
+    tr.compute_loss = lambda *a: (rec.append(real_cl(*a)), rec[-1])[1]
+    norms = []
+    real_clip = ref_fg.clip_grad_norm_
+    ref_fg.clip_grad_norm_ = lambda params, mx: (norms.append(real_clip(params, mx)), norms[-1])[1]
+    out = dict(cfg=np.array(cfg), seed=1, x=x.numpy().astype(np.int16), y=y.numpy().astype(np.int16))
+    try:
+        v_loss, v_acc, _, _ = tr.valid()
+        out['valid_losses'] = np.array([l.item() for l in rec[:8]])
+        out['valid_loss_rounded'] = v_loss
+        out['valid_acc_rounded'] = np.array(v_acc)
+        del rec[:]
+        t_loss, t_acc, _, _ = tr.train()
+    finally:
+        ref_fg.clip_grad_norm_ = real_clip
+    out['train_losses'] = np.array([l.item() for l in rec[:8]])
+    n_tok = [len(pb.e2w[k]) for k in pb.e2w]
+    extra = [1, 1, 0.3, 1.5, 1, 1, 0.3, 0.3]
+    out['train_total'] = np.float64(sum(l * e * n for l, e, n in zip(out['train_losses'], extra, n_tok)) / sum(n_tok))
+    out['valid_total'] = np.float64(sum(l * e * n for l, e, n in zip(out['valid_losses'], extra, n_tok)) / sum(n_tok))
+    assert abs(out['train_total'] - t_loss) < 1e-4 and abs(out['valid_total'] - v_loss) < 1e-4
+    out['grad_norm_preclip'] = np.float64(float(norms[0]))
+    for k, v in lm.named_parameters():
+        kk = k[len('pianobart.'):] if k.startswith('pianobart.') else k
+        if kk in ('encoder_linear.weight', 'mask_lm.proj.3.weight', 'bart.decoder.layers.1.fc2.weight',
+                  'bart.encoder.layers.0.self_attn.v_proj.weight', 'word_emb.0.lut.weight'):
+            out['grad:' + kk] = v.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, 'genft_tiny.npz'), **out)
+    print('genft total', out['train_total'], 'valid', out['valid_total'], 'gnorm', out['grad_norm_preclip'])
+
+
 def golden_cls():
     cfg = (64, 2, 2, 4, 128, 32)
     d, el, dl, heads, ffn, max_pos = cfg
@@ -281,7 +382,7 @@ def golden_cls():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['tiny', 'mid', 'default', 'noising', 'generate', 'cls']
+    which = sys.argv[1:] or ['tiny', 'mid', 'default', 'noising', 'generate', 'cls', 'generate_default', 'genft']
     if 'tiny' in which:
         golden_forward('fwd_tiny', (64, 2, 2, 4, 128, 32), 1, 5, 32, True,
                        ['encoder_linear.bias', 'word_emb.3.lut.weight', 'bart.decoder.layers.1.encoder_attn.k_proj.weight',
@@ -301,3 +402,7 @@ if __name__ == '__main__':
         golden_generate()
     if 'cls' in which:
         golden_cls()
+    if 'generate_default' in which:
+        golden_generate_default()
+    if 'genft' in which:
+        golden_genft()
