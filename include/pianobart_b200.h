@@ -114,6 +114,10 @@ typedef struct pb_attn_desc {
 } pb_attn_desc;
 int pb_attn_fwd(const pb_attn_desc* d, void* stream);
 int pb_attn_bwd(const pb_attn_desc* d, void* stream);
+/* test hook (fault injection): the TMA producer threads of the attention kernels launched after this call stall a
+ * pseudo-random number of cycles (< max_cycles) before each tile load, so tiles arrive late relative to the softmax warps
+ * and the MMA thread; 0 turns it off.  Results must not depend on it (tests/test_gpu_parity.py).  Returns the old value. */
+int pb_debug_set_attn_delay(int max_cycles);
 
 /* ------------------------------------------------------------------ Octuple front end
  * out[m, 256*i + c] = table[row_off(i) + ids[m,i], c] for the 8 attributes (reference PianoBart.py:9-16,60-67:
@@ -241,6 +245,70 @@ int pb_decode_sample(const float* logits, const double* uniforms, const int* for
  * then t += 1.  done int32 [B] sticky flags, n_written int32 [B]. */
 int pb_decode_advance(const int* cur_tok, int* result, int* done, int* t_dev, int* n_written, int B, int S,
                       const int* pad_host, void* stream);
+
+/* Generation post-processing on the device (reference demo.py:72-102, Octuple2Midi up to the MIDI writer): per sequence the
+ * first row with any attribute >= its <PAD> id or a Pitch > 127 becomes the <EOS> row (PAD + 3) and later rows <PAD>; without
+ * such a row the last row becomes <EOS>.  ids [B,S,8] int32 (ids_int64 = 0) or int64; out int64 [B,S,8]; len int64 [B] =
+ * index of the <EOS> row = number of rows the reference hands to encoding_to_MIDI (0: "Generate Fail"). */
+int pb_octuple_truncate(const void* ids, int ids_int64, long long* out, long long* len, int B, int S, const int* pad_host,
+                        void* stream);
+
+/* ------------------------------------------------------------------ persistent whole-step decode (batch 1)
+ * Replaces the per-token loop body of PianoBartLM.forward(generate=True) (model.py:42-65) for the default model geometry
+ * (d 1024, 8 heads x 128, ffn 2048, 1280-entry Octuple vocabulary): ONE cooperative launch generates `n_steps` tokens.
+ * Every SM streams its slice of the decoder weights and of the K/V caches through a shared-memory ring with bulk copies
+ * that never wait for activations; activation vectors are exchanged between CTAs as tagged 8-byte words (payload + a
+ * per-(token, hop) tag) instead of grid barriers; LayerNorm / bias / GELU / residual / sampling are fused into the
+ * consumers (csrc/decode_persist.cu).
+ * K/V caches use the split-major layout [head][split = key % 18][slot = key / 18][128] (bf16) per layer. */
+#define PB_DECODE_MAX_LAYERS 8
+#define PB_DECODE_NSPLIT 18
+#define PB_DECODE_NSLOT 57
+#define PB_DECODE_PART_WORDS 132 /* words per attention partial: max, sum, 2 pad, out[128] */
+typedef struct pb_decode_layer {
+  const void* wqkv; const float* bqkv;                 /* [3d,d] bf16 (q|k|v rows), [3d]            self_attn          */
+  const void* wo; const float* bo;                     /* self_attn.out_proj                                           */
+  const float* ln1_g; const float* ln1_b;              /* self_attn_layer_norm                                         */
+  const void* wqc; const float* bqc;                   /* encoder_attn.q_proj                                          */
+  const void* woc; const float* boc;                   /* encoder_attn.out_proj                                        */
+  const float* ln2_g; const float* ln2_b;              /* encoder_attn_layer_norm                                      */
+  const void* w1; const float* b1;                     /* fc1 [F,d]                                                    */
+  const void* w2; const float* b2;                     /* fc2 [d,F]                                                    */
+  const float* ln3_g; const float* ln3_b;              /* final_layer_norm                                             */
+  void* self_k; void* self_v;                          /* [8][18][57][128] bf16, appended by the kernel                */
+  const void* cross_k; const void* cross_v;            /* same layout, filled by pb_decode_kv_relayout                 */
+} pb_decode_layer;
+typedef struct pb_decode_persist_desc {
+  pb_decode_layer layer[PB_DECODE_MAX_LAYERS];
+  int n_layers, S_enc, S_max, stop_when_done;
+  const void* emb_table;                               /* [1280,256] bf16, pre-scaled by 16                            */
+  const void* w_in; const float* b_in;                 /* encoder_linear (= decoder_linear) [d,2048]                   */
+  const void* pos_table;                               /* bart.decoder.embed_positions [max_pos+2, d] bf16             */
+  const float* lne_g; const float* lne_b;              /* bart.decoder.layernorm_embedding                             */
+  const void* w_heads; const float* b_heads;           /* 8 LM heads as one [1280,d]                                   */
+  const uint8_t* enc_keep;                             /* [S_enc] encoder key-padding flags (non-zero = visible)       */
+  /* generation state (device): same meaning as for pb_decode_sample / pb_decode_advance, batch 1 */
+  int* t_dev; int* cur_tok; int* result; int* sampled; int* done; int* n_written;
+  const double* uniforms; const int* forced;           /* [S_max,8]; forced may be NULL                                */
+  float* logits_out;                                   /* [1280] fp32 logits of the last executed step (may be NULL)   */
+  /* exchange buffers (device, zero-initialised once; 8-byte words) and the tag epoch */
+  unsigned long long* raw0; unsigned long long* raw1; unsigned long long* raw2;   /* d/2 words each                    */
+  unsigned long long* qkv;                             /* 3d/2 words                                                   */
+  unsigned long long* qc; unsigned long long* ob;      /* d/2 words each                                               */
+  unsigned long long* f1;                              /* F/2 words                                                    */
+  unsigned long long* part;                            /* 8*18*PB_DECODE_PART_WORDS words                              */
+  unsigned long long* logits_ll;                       /* 1280 words                                                   */
+  unsigned long long* tok_ll;                          /* 8 words                                                      */
+  unsigned int* epoch;                                 /* 1 word, zero-initialised once, advanced by the kernel        */
+  int* error_flag;                                     /* set to a non-zero code before a bounded wait traps           */
+} pb_decode_persist_desc;
+/* generates up to n_steps tokens (stops early when stop_when_done and the stop rule fired); seg sizes / temperatures /
+ * nucleus p / <PAD> ids live on the HOST */
+int pb_decode_persist_run(const pb_decode_persist_desc* d, int n_steps, const int* seg_sizes_host, const float* temp_host,
+                          const float* top_p_host, const int* pad_host, void* stream);
+int pb_decode_persist_smem_bytes(void);
+/* cross-attention K/V of one layer: projection layout [S_enc, 2d] (K | V, bf16) -> split-major cache layout */
+int pb_decode_kv_relayout(const void* kv, void* k_out, void* v_out, int S_enc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpianobart_b200.so")
+# PIANOBART_B200_LIB: developer override (A/B runs against another build of the same ABI); never a fallback
+LIB_PATH = os.environ.get("PIANOBART_B200_LIB") or os.path.join(_HERE, "libpianobart_b200.so")
 
 PB_GEMM_OUT_F32 = 1
 PB_GEMM_GELU = 2
@@ -52,6 +53,22 @@ class AttnDesc(C.Structure):
         ("B", C.c_int), ("H", C.c_int), ("Sq", C.c_int), ("Sk", C.c_int), ("hd", C.c_int), ("causal", C.c_int),
         ("scale", C.c_float),
     ]
+
+
+class DecodeLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        'wqkv', 'bqkv', 'wo', 'bo', 'ln1_g', 'ln1_b', 'wqc', 'bqc', 'woc', 'boc', 'ln2_g', 'ln2_b', 'w1', 'b1', 'w2', 'b2',
+        'ln3_g', 'ln3_b', 'self_k', 'self_v', 'cross_k', 'cross_v')]
+
+
+class DecodePersistDesc(C.Structure):
+    """include/pianobart_b200.h: pb_decode_persist_desc"""
+    _fields_ = ([('layer', DecodeLayer * 8), ('n_layers', C.c_int), ('S_enc', C.c_int), ('S_max', C.c_int),
+                 ('stop_when_done', C.c_int)] +
+                [(n, C.c_void_p) for n in (
+                    'emb_table', 'w_in', 'b_in', 'pos_table', 'lne_g', 'lne_b', 'w_heads', 'b_heads', 'enc_keep',
+                    't_dev', 'cur_tok', 'result', 'sampled', 'done', 'n_written', 'uniforms', 'forced', 'logits_out',
+                    'raw0', 'raw1', 'raw2', 'qkv', 'qc', 'ob', 'f1', 'part', 'logits_ll', 'tok_ll', 'epoch', 'error_flag')])
 
 
 class PBError(RuntimeError):

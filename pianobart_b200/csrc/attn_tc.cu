@@ -56,7 +56,18 @@ struct AttnParams {
   __nv_bfloat16* dk; long long lddk;
   __nv_bfloat16* dv; long long lddv;
   long long dq_sb, dk_sb, dv_sb, o_sb;  // batch strides (elements)
+  int dbg_delay;                    // test hook (pb_debug_set_attn_delay): TMA producers stall up to this many cycles per load
 };
+
+// Fault injection for the pipeline tests: the producer thread spins a pseudo-random number of cycles (< max_cycles) before a
+// load, so that tiles arrive late / out of their usual order relative to the softmax warps and the MMA thread.
+__device__ __forceinline__ void chaos_delay(int max_cycles, uint32_t salt) {
+  if (max_cycles <= 0) return;
+  uint32_t h = salt * 2654435761u + blockIdx.x * 40503u + blockIdx.y * 9973u + blockIdx.z * 101u;
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  const long long until = clock64() + (long long)(h % (uint32_t)max_cycles);
+  while (clock64() < until) { }
+}
 
 // ---- tile helpers --------------------------------------------------------------------------------------
 // K-major view of a tile: k-step kk (16 contraction columns) of 8
@@ -178,6 +189,11 @@ __device__ __forceinline__ void carve(uint8_t* raw, Smem4& s, int n) {
 //   exchange max (one named barrier) -> [ld S(j), S(j+1) -> exp2 / max -> st P(j)] x 2 chunks -> arrive.
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 domain: probabilities stay <= 256 between rescales
 constexpr int NSBUF = 3;                    // S buffers in TMEM / K ring depth
+#ifdef PB_SINGLE_PHASE_BARRIERS             // round-1 behaviour, kept only for tools/attn_late_tile_demo.py
+constexpr int NPB = 1;
+#else
+constexpr int NPB = NSBUF;                  // p_full / pv_done ring depth (see the comment at their declaration)
+#endif
 constexpr int FWD_MAX_SK = 8192;            // keys per sequence supported by the in-kernel key-padding bitmap
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -185,7 +201,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                 const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   if (threadIdx.x == 64) PB_TR(0, 63, 0);
-  __shared__ __align__(8) uint64_t q_full, k_full[NSBUF], k_empty[NSBUF], v_full[2], v_empty[2], s_full[NSBUF], p_full, pv_done;
+  // pv_done is a ring of NSBUF barriers (P V(j) commits to pv_done[j % NSBUF]): the softmax warps only look at it when they
+  // rescale O and at the end, i.e. they do NOT observe every phase, and a parity wait is only unambiguous when the phase
+  // before the awaited one is known to be complete.  With one barrier, a late V tile (P V(j-2) still un-issued when the
+  // warps ask for P V(j-1)) made the wait return immediately: O was read / rescaled early and the CTA could reach its
+  // TMEM dealloc with MMAs in flight - the cold-start "unspecified launch failure" of round 1.  With the ring, the phase
+  // before P V(j-1) on its barrier is P V(j-4), which has retired once S(j) is complete (in-order tensor pipe).
+  // p_full is a ring for the mirror-image reason: S runs two blocks ahead, so the softmax warps can finish blocks j, j+1
+  // and j+2 while the MMA thread still waits for the V tile of block j; with a single barrier its next parity wait then
+  // aliased a later phase, and near the end of the key loop that phase never completes (deadlock -> bounded-spin trap).
+  __shared__ __align__(8) uint64_t q_full, k_full[NSBUF], k_empty[NSBUF], v_full[2], v_empty[2], s_full[NSBUF], p_full[NPB], pv_done[NPB], mma_drain;
   __shared__ uint32_t tmem_base_smem;
   __shared__ uint32_t s_keep[FWD_MAX_SK / 32];   // key-padding bitmap of the whole key sequence (built once)
   __shared__ float s_red[2][2][AT];
@@ -203,7 +228,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     mbar_init(&q_full, 1);
     for (int i = 0; i < NSBUF; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&s_full[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    mbar_init(&p_full, NCOMPUTE); mbar_init(&pv_done, 1);
+    mbar_init(&mma_drain, 1);
+    for (int i = 0; i < NPB; ++i) { mbar_init(&pv_done[i], 1); mbar_init(&p_full[i], NCOMPUTE); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -226,16 +252,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         if (i < nkb) {
           const int ks = i % NSBUF;
           mbar_wait(&k_empty[ks], ((uint32_t)(i / NSBUF) & 1) ^ 1);
+          chaos_delay(p.dbg_delay >> 2, 2 * i);
           mbar_expect_tx(&k_full[ks], TILE_BYTES);
           load_tile(sm.t[1 + ks], &tk, &k_full[ks], i * AT, h, b);
         }
         if (i >= 2) {
           const int j = i - 2, vs = j & 1;
           mbar_wait(&v_empty[vs], ((uint32_t)(j >> 1) & 1) ^ 1);
+          chaos_delay(p.dbg_delay, 2 * j + 1);        // late V tiles are what the p_full / pv_done rings exist for
           mbar_expect_tx(&v_full[vs], TILE_BYTES);
           load_tile(sm.t[4 + vs], &tv, &v_full[vs], j * AT, h, b);
         }
       }
+      // producer tail: every slot release (tcgen05.commit arrival on k_empty / v_empty) has landed before the CTA exits
+      for (int i = nkb; i < nkb + NSBUF; ++i) mbar_wait(&k_empty[i % NSBUF], ((uint32_t)(i / NSBUF) & 1) ^ 1);
+      for (int j = nkb; j < nkb + 2; ++j) mbar_wait(&v_empty[j & 1], ((uint32_t)(j >> 1) & 1) ^ 1);
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -253,7 +284,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       constexpr uint32_t idesc_pv = make_idesc_bf16(AT, AT, 0, 1);
       for (int j = 0; j < nkb; ++j) {
         if (j + 2 < nkb) { PB_TR(0, j, 0); issue_s(j + 2); PB_TR(0, j, 1); }
-        mbar_wait(&p_full, j & 1);
+        mbar_wait(&p_full[j % NPB], (uint32_t)(j / NPB) & 1);
         mbar_wait(&v_full[j & 1], (uint32_t)(j >> 1) & 1);
         tc_fence_after();
         PB_TR(0, j, 2);
@@ -263,10 +294,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_bf16_ts(tO, tP + (kk >> 2) * 64 + (kk & 3) * 8, desc_mnmajor(vt, kk), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&pv_done);
+        umma_commit(&pv_done[j % NPB]);
         umma_commit(&v_empty[j & 1]);
         PB_TR(0, j, 3);
       }
+      // no MMA / commit of this CTA is in flight when TMEM is released and the CTA exits
+      umma_commit(&mma_drain);
+      mbar_wait(&mma_drain, 0);
     }
   } else {
     const int cw = warp - 2;                 // 0..7
@@ -327,7 +361,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         need = true;
       }
       if (__any_sync(0xffffffffu, need)) {
-        mbar_wait(&pv_done, (j - 1) & 1);                 // j > 0 here: the previous P V must have landed in O
+        mbar_wait(&pv_done[(j - 1) % NPB], (uint32_t)((j - 1) / NPB) & 1);   // j > 0 here: the previous P V must have landed in O
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -388,7 +422,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       l += rs0 + rs1;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full);
+      mbar_arrive(&p_full[j % NPB]);
       if (trole > 0) PB_TR(trole, j, 2);
       if (has_next) {
         s_red[(j + 1) & 1][hf][r] = bmn * sl2;
@@ -398,7 +432,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       }
       if (trole > 0) PB_TR(trole, j, 3);
     }
-    mbar_wait(&pv_done, (nkb - 1) & 1);
+    mbar_wait(&pv_done[(nkb - 1) % NPB], (uint32_t)((nkb - 1) / NPB) & 1);
     tc_fence_after();
     if (threadIdx.x == 64) PB_TR(0, 63, 2);
     compute_bar_sync();
@@ -443,7 +477,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
                     const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
                     const __grid_constant__ CUtensorMap tdk, const __grid_constant__ CUtensorMap tdv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t kv_full, qdo_full[NQ], qdo_empty[NQ], sdp_full[2], pds_full[2], acc_full;
+  __shared__ __align__(8) uint64_t kv_full, qdo_full[NQ], qdo_empty[NQ], sdp_full[2], pds_full[2], acc_full, mma_drain;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_L[2][QB], s_D[2][QB];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -460,7 +494,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); }
   if (warp == 1 && lane == 0) {
-    mbar_init(&kv_full, 1); mbar_init(&acc_full, 1);
+    mbar_init(&kv_full, 1); mbar_init(&acc_full, 1); mbar_init(&mma_drain, 1);
     for (int i = 0; i < NQ; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&pds_full[i], NCOMPUTE); }
     fence_mbar_init();
@@ -484,12 +518,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         const int st = it % NQ;
         const int q0 = (qb0 + it) * QB;
         mbar_wait(&qdo_empty[st], ((uint32_t)(it / NQ) & 1) ^ 1);
+        chaos_delay(p.dbg_delay, it);
         mbar_expect_tx(&qdo_full[st], 2 * QT_BYTES);
         tma_load_4d(gQ + st * QT_BYTES, &tq, &qdo_full[st], 0, q0, h, b);
         tma_load_4d(gQ + st * QT_BYTES + QT_BYTES / 2, &tq, &qdo_full[st], 64, q0, h, b);
         tma_load_4d(gdO + st * QT_BYTES, &tdo, &qdo_full[st], 0, q0, h, b);
         tma_load_4d(gdO + st * QT_BYTES + QT_BYTES / 2, &tdo, &qdo_full[st], 64, q0, h, b);
       }
+      // producer tail: every ring-slot release has landed before the CTA exits
+      for (int it = niter; it < niter + NQ; ++it) mbar_wait(&qdo_empty[it % NQ], ((uint32_t)(it / NQ) & 1) ^ 1);
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -540,6 +577,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         umma_commit(&qdo_empty[it % NQ]);    // Q / dO ring slot reusable
       }
       umma_commit(&acc_full);
+      umma_commit(&mma_drain);
+      mbar_wait(&mma_drain, 0);
     }
   } else {
     const int cw = warp - 2;
@@ -661,7 +700,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                    const __grid_constant__ CUtensorMap tdq, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t qdo_full, k_full[3], k_empty[3], v_full[2], v_empty[2], s_full[2], dp_full, dp_free, ds_full,
-      acc_full;
+      acc_full, mma_drain;
   __shared__ uint32_t tmem_base_smem;
   __shared__ uint32_t s_bits2[2][4];
   Smem4 sm;
@@ -683,7 +722,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); }
   if (warp == 1 && lane == 0) {
-    mbar_init(&qdo_full, 1); mbar_init(&acc_full, 1); mbar_init(&dp_full, 1);
+    mbar_init(&qdo_full, 1); mbar_init(&acc_full, 1); mbar_init(&dp_full, 1); mbar_init(&mma_drain, 1);
     mbar_init(&dp_free, NCOMPUTE); mbar_init(&ds_full, NCOMPUTE);
     for (int i = 0; i < NK; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); mbar_init(&s_full[i], 1); }
@@ -706,12 +745,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       for (int j = 0; j < nkb; ++j) {
         const int ks = j % NK, vs = j & 1;
         mbar_wait(&k_empty[ks], ((uint32_t)(j / NK) & 1) ^ 1);
+        chaos_delay(p.dbg_delay, 2 * j);
         mbar_expect_tx(&k_full[ks], TILE_BYTES);
         load_tile(sm.t[2 + ks], &tk, &k_full[ks], j * AT, h, b);
         mbar_wait(&v_empty[vs], ((uint32_t)(j >> 1) & 1) ^ 1);
+        chaos_delay(p.dbg_delay, 2 * j + 1);
         mbar_expect_tx(&v_full[vs], TILE_BYTES);
         load_tile(gV + vs * TILE_BYTES, &tv, &v_full[vs], j * AT, h, b);
       }
+      // producer tail: every ring-slot release has landed before the CTA exits
+      for (int j = nkb; j < nkb + NK; ++j) mbar_wait(&k_empty[j % NK], ((uint32_t)(j / NK) & 1) ^ 1);
+      for (int j = nkb; j < nkb + 2; ++j) mbar_wait(&v_empty[j & 1], ((uint32_t)(j >> 1) & 1) ^ 1);
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -766,6 +810,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         PB_TR(0, j, 3);
       }
       umma_commit(&acc_full);
+      umma_commit(&mma_drain);
+      mbar_wait(&mma_drain, 0);
     }
   } else {
     const int cw = warp - 2;
@@ -922,7 +968,15 @@ static int attn_check(const pb_attn_desc* d) {
   return 0;
 }
 
+static int g_attn_dbg_delay = 0;
+extern "C" int pb_debug_set_attn_delay(int max_cycles) {
+  const int prev = g_attn_dbg_delay;
+  g_attn_dbg_delay = max_cycles > 0 ? max_cycles : 0;
+  return prev;
+}
+
 static void fill_params(AttnParams& p, const pb_attn_desc* d) {
+  p.dbg_delay = g_attn_dbg_delay;
   p.B = d->B; p.H = d->H; p.Sq = d->Sq; p.Sk = d->Sk; p.causal = d->causal; p.scale = d->scale;
   p.key_keep = d->key_keep;
   p.o = (__nv_bfloat16*)d->o; p.ldo = d->ldo; p.o_sb = (long long)d->Sq * d->ldo;

@@ -414,6 +414,43 @@ __global__ void decode_advance_kernel(const int* __restrict__ cur_tok, int* __re
   if (threadIdx.x == 0 && t < S) *t_dev = t + 1;
 }
 
+// Octuple2Midi truncation (reference demo.py:72-102) for a batch of generated sequences, one warp per sequence:
+// the first row holding any attribute >= its <PAD> id, or a Pitch > 127 (drums are not generated), becomes the <EOS> row
+// and every later row <PAD>; if there is none the LAST row becomes <EOS>.  len[b] = index of the <EOS> row (the number of
+// rows handed to encoding_to_MIDI; 0 = "Generate Fail (empty)").
+template <typename T>
+__global__ void __launch_bounds__(128) octuple_truncate_kernel(const T* __restrict__ in, long long* __restrict__ out,
+                                                              long long* __restrict__ len, int B, int S, PadMeta pm) {
+  pdl_entry();
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const T* x = in + (long long)b * S * 8;
+  int first = S;
+  for (int i0 = 0; i0 < S && first == S; i0 += 32) {
+    const int i = i0 + lane;
+    bool bad = false;
+    if (i < S) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long v = (long long)x[(long long)i * 8 + j];
+        bad |= v >= pm.pad[j] || (j == 3 && v > 127);
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if (m) first = i0 + __ffs(m) - 1;
+  }
+  const int eos_row = first < S ? first : S - 1;
+  long long* y = out + (long long)b * S * 8;
+  for (int e = lane; e < S * 8; e += 32) {
+    const int i = e >> 3, j = e & 7;
+    long long v = (long long)x[e];
+    if (i == eos_row) v = pm.pad[j] + 3;
+    else if (i > eos_row) v = pm.pad[j];
+    y[e] = v;
+  }
+  if (lane == 0) len[b] = eos_row;
+}
+
 }  // namespace
 
 #define PB_STREAM(s) reinterpret_cast<cudaStream_t>(s)
@@ -499,4 +536,18 @@ extern "C" int pb_decode_advance(const int* cur_tok, int* result, int* done, int
   for (int i = 0; i < 8; ++i) pm.pad[i] = pad_host[i];
   PB_LAUNCH((decode_advance_kernel), 1, ((B + 31) / 32) * 32, 0, PB_STREAM(stream), cur_tok, result, done, t_dev, n_written, B, S, pm);
   return pb_check_launch("decode_advance");
+}
+
+extern "C" int pb_octuple_truncate(const void* ids, int ids_int64, long long* out, long long* len, int B, int S,
+                                   const int* pad_host, void* stream) {
+  if (B <= 0 || S <= 0) return pb_set_error("octuple_truncate: empty batch");
+  PadMeta pm;
+  for (int i = 0; i < 8; ++i) pm.pad[i] = pad_host[i];
+  const int grid = (B + 3) / 4;
+  if (ids_int64) {
+    PB_LAUNCH((octuple_truncate_kernel<long long>), grid, 128, 0, PB_STREAM(stream), (const long long*)ids, out, len, B, S, pm);
+  } else {
+    PB_LAUNCH((octuple_truncate_kernel<int>), grid, 128, 0, PB_STREAM(stream), (const int*)ids, out, len, B, S, pm);
+  }
+  return pb_check_launch("octuple_truncate");
 }

@@ -246,6 +246,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      // producer tail: the release of every slot this CTA filled (a tcgen05.commit arrival, multicast to both CTAs of a
+      // pair) has landed before the CTA exits and its shared memory is handed to the next CTA
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer

@@ -52,10 +52,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // A failed try_wait suspends the thread for a hardware-defined interval, so 2^26 failures is seconds -
 // far beyond any legitimate wait in these kernels.  (No %globaltimer read here: it is a long-scoreboard
 // operation and sat on the critical path of every producer/consumer hand-off.)
+#ifndef PB_MBAR_SPIN_LIMIT
+#define PB_MBAR_SPIN_LIMIT (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > PB_MBAR_SPIN_LIMIT) __trap();
   }
 }
 

@@ -172,12 +172,6 @@ class Plan:
         s = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
         n = 0
         gemm_fns = (self.lib.pb_gemm_bf16, self.lib.pb_gemm_f32)
-        # First execution of a plan in a process: every launch is followed by a stream synchronisation.  About 7 % of cold
-        # process starts otherwise died with "unspecified launch failure" somewhere in their first pass (never later, never
-        # with CUDA_LAUNCH_BLOCKING=1, with or without PDL / lazy module loading - profiles/r1_summary.md section 6); the
-        # root cause is not yet understood, so the first pass is serialised.  One-time cost: ~0.5 k synchronisations.
-        sync_each = (not getattr(self, '_warm', False) and os.environ.get('PIANOBART_B200_FIRST_RUN_SYNC', '1') != '0'
-                     and not torch.cuda.is_current_stream_capturing())
         for name, fn, args in self.ops:
             if fn is None:
                 if on_marker is not None:
@@ -196,9 +190,6 @@ class Plan:
             n += 1
             if rc != 0:
                 raise L.PBError('%s failed (%d): %s' % (name, rc, self.lib.pb_last_error().decode()))
-            if sync_each:
-                torch.cuda.synchronize()
-        self._warm = True
         return n
 
     # ---- op recorders ------------------------------------------------------------------

@@ -63,6 +63,9 @@ class Generator:
         self.self_cache = [z(B, S, 2 * d) for _ in range(lay.dec_layers)]
         self.cross_kv = [z(B * S_enc, 2 * d) for _ in range(lay.dec_layers)]
         self.enc_graph = pb._graph(B, S_enc, 0, False, False, 0.0)  # no dropout (demo.py:149-150 behaviour)
+        # batch 1, default geometry: one persistent cooperative kernel generates many tokens per launch
+        self.persist = (B == 1 and not force_gemm and d == 1024 and F == 2048 and H == 8 and 1 <= lay.dec_layers <= 8
+                        and max(self.S, S_enc) <= 18 * 57 and os.environ.get('PIANOBART_B200_DECODE_PERSIST', '1') != '0')
         self.ntok_arr = (C.c_int * 8)(*E.N_TOKENS)
         self.pad_arr = (C.c_int * 8)(*[int(x) for x in pb.pad_word_np])
         self.temp_arr = (C.c_float * 8)(*[float(x) for x in SAMPLE_T])
@@ -170,7 +173,67 @@ class Generator:
                 P(E._ptr(self.t_dev)), P(E._ptr(self.n_written)), B, S, self.pad_arr)
         self.launches_per_step = len(st.ops)
 
+    def _build_persist(self):
+        """Batch 1: csrc/decode_persist.cu.  Prefill = cross-attention K/V GEMMs + relayout into the split-major cache
+        layout; the decode step itself is not a plan but one cooperative launch per run_steps() call."""
+        pb, lay = self.pb, self.pb.layout
+        d, F, Se, S = self.d, self.F, self.Se, self.S
+        eg = self.enc_graph
+        P = C.c_void_p
+        dev = self.dev
+        zb = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bfloat16)
+        zw = lambda n: torch.zeros(n, device=dev, dtype=torch.int64)
+        nl = lay.dec_layers
+        self.self_k_r = [zb(8, 18, 57, 128) for _ in range(nl)]
+        self.self_v_r = [zb(8, 18, 57, 128) for _ in range(nl)]
+        self.cross_k_r = [zb(8, 18, 57, 128) for _ in range(nl)]
+        self.cross_v_r = [zb(8, 18, 57, 128) for _ in range(nl)]
+        for l in range(nl):
+            ca = 'bart.decoder.layers.%d.encoder_attn' % l
+            self.prefill.gemm(E._ptr(eg.enc_out), self._W(ca + '.wkv'), E._ptr(self.cross_kv[l]), Se, 2 * d, d, d, d, 2 * d,
+                              bias=self._Pf(ca + '.bkv'), name='kv_c%d' % l)
+            self.prefill._add('kv_relayout', self.lib.pb_decode_kv_relayout, P(E._ptr(self.cross_kv[l])),
+                              P(E._ptr(self.cross_k_r[l])), P(E._ptr(self.cross_v_r[l])), Se)
+        self.ll = dict(raw0=zw(d // 2), raw1=zw(d // 2), raw2=zw(d // 2), qkv=zw(3 * d // 2), qc=zw(d // 2), ob=zw(d // 2),
+                       f1=zw(F // 2), part=zw(8 * 18 * 132), logits_ll=zw(E.VOCAB), tok_ll=zw(8))
+        self.epoch = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.err_flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        D = L.DecodePersistDesc()
+        for l in range(nl):
+            lp = 'bart.decoder.layers.%d' % l
+            sa, ca = lp + '.self_attn', lp + '.encoder_attn'
+            Ld = D.layer[l]
+            Ld.wqkv, Ld.bqkv = self._W(sa + '.wqkv'), self._Pf(sa + '.bqkv')
+            Ld.wo, Ld.bo = self._W(sa + '.out_proj.weight'), self._Pf(sa + '.out_proj.bias')
+            Ld.ln1_g, Ld.ln1_b = self._Pf(lp + '.self_attn_layer_norm.weight'), self._Pf(lp + '.self_attn_layer_norm.bias')
+            Ld.wqc, Ld.bqc = self._W(ca + '.q_proj.weight'), self._Pf(ca + '.q_proj.bias')
+            Ld.woc, Ld.boc = self._W(ca + '.out_proj.weight'), self._Pf(ca + '.out_proj.bias')
+            Ld.ln2_g, Ld.ln2_b = self._Pf(lp + '.encoder_attn_layer_norm.weight'), self._Pf(lp + '.encoder_attn_layer_norm.bias')
+            Ld.w1, Ld.b1 = self._W(lp + '.fc1.weight'), self._Pf(lp + '.fc1.bias')
+            Ld.w2, Ld.b2 = self._W(lp + '.fc2.weight'), self._Pf(lp + '.fc2.bias')
+            Ld.ln3_g, Ld.ln3_b = self._Pf(lp + '.final_layer_norm.weight'), self._Pf(lp + '.final_layer_norm.bias')
+            Ld.self_k, Ld.self_v = E._ptr(self.self_k_r[l]), E._ptr(self.self_v_r[l])
+            Ld.cross_k, Ld.cross_v = E._ptr(self.cross_k_r[l]), E._ptr(self.cross_v_r[l])
+        D.n_layers, D.S_enc, D.S_max, D.stop_when_done = nl, Se, S, 0
+        D.emb_table = self._W('emb')
+        D.w_in, D.b_in = self._W('encoder_linear.weight'), self._Pf('encoder_linear.bias')
+        D.pos_table = self._W('bart.decoder.embed_positions.weight')
+        D.lne_g, D.lne_b = self._Pf('bart.decoder.layernorm_embedding.weight'), self._Pf('bart.decoder.layernorm_embedding.bias')
+        D.w_heads, D.b_heads = self._W('heads.w'), self._Pf('heads.b')
+        D.enc_keep = E._ptr(eg.enc_keep)
+        D.t_dev, D.cur_tok, D.result, D.sampled = E._ptr(self.t_dev), E._ptr(self.cur_tok), E._ptr(self.result), E._ptr(self.sampled)
+        D.done, D.n_written, D.uniforms, D.forced = E._ptr(self.done), E._ptr(self.n_written), E._ptr(self.uniforms), None
+        D.logits_out = E._ptr(self.logits)
+        for k, t in self.ll.items():
+            setattr(D, k, E._ptr(t))
+        D.epoch, D.error_flag = E._ptr(self.epoch), E._ptr(self.err_flag)
+        self.pdesc = D
+        self.launches_per_step = 1
+        self._steps_issued = 0
+
     def _build(self):
+        if self.persist:
+            return self._build_persist()
         if self.B <= 8 and not self.force_gemm:
             return self._build_small_batch()
         pb, lay = self.pb, self.pb.layout
@@ -227,6 +290,11 @@ class Generator:
     def _set_forced(self, forced):
         """Teacher forcing (parity tests): the token fed to step t+1 is forced[b, t] instead of the sampled one."""
         P = C.c_void_p
+        if self.persist:
+            self.forced = None if forced is None else forced.to(device=self.dev, dtype=torch.int32).contiguous()
+            self.pdesc.forced = None if forced is None else E._ptr(self.forced)
+            self.pdesc.stop_when_done = 1 if forced is None else 0
+            return
         name, fn, args = self.step.ops[self._sample_idx]
         args = list(args)
         if forced is None:
@@ -258,9 +326,25 @@ class Generator:
         self.result.copy_(pad.view(1, 1, 8).expand_as(self.result))
         if uniforms is not None:
             self.uniforms.copy_(torch.as_tensor(uniforms, dtype=torch.float64).reshape(self.B, self.S, 8), non_blocking=True)
+        if self.persist:
+            self.err_flag.zero_()
+            self._steps_issued = 0
+
+    def _run_persist(self, n):
+        n = min(n, self.S - self._steps_issued)
+        if n <= 0:
+            return 0
+        L.check(self.lib.pb_decode_persist_run(C.byref(self.pdesc), n, self.ntok_arr, self.temp_arr, self.p_arr, self.pad_arr,
+                                               L.stream_ptr()), 'decode_persist')
+        self._steps_issued += n
+        self.launches_per_step = 1.0 / n
+        return 1
 
     def run_steps(self, n):
-        """Replays n decode steps (CUDA graph).  Returns the number of library launches issued."""
+        """Runs n decode steps: one cooperative launch (batch 1, persistent kernel) or n CUDA-graph replays.
+        Returns the number of library launches issued."""
+        if self.persist:
+            return self._run_persist(n)
         if not self.use_graph:
             for _ in range(n):
                 self.step.run()
@@ -294,6 +378,8 @@ class Generator:
 
     def finish(self):
         torch.cuda.synchronize()
+        if self.persist and int(self.err_flag.item()) != 0:
+            raise L.PBError('decode_persist_kernel reported error %d' % int(self.err_flag.item()))
         return self.result.to(torch.int64), self.n_written.cpu().numpy(), self.done.cpu().numpy()
 
 

@@ -125,3 +125,23 @@ def make_plan(ori, max_seq_len, mask_percent=0.15, choices=None):
             if r != 0:
                 loss[:] = 1
     return plan
+
+
+def slice_plan(plan, lo, hi):
+    """Rows [lo, hi) of a batch plan as a stand-alone plan (random-token side table re-indexed).  Data-parallel runs draw
+    ONE logical plan for the global batch - every rank consumes the RNG streams for all samples in global sample order,
+    exactly like the single-process reference (pretrain.py:131-144) - and keep their slice."""
+    B, S = hi - lo, plan.src.shape[1]
+    out = NoisePlan(B, S)
+    out.src[...] = plan.src[lo:hi]
+    out.loss[...] = plan.loss[lo:hi]
+    out.loss_mode[...] = plan.loss_mode[lo:hi]
+    out.choices[...] = plan.choices[lo:hi]
+    used = out.src[out.src <= -3]
+    if used.size:
+        ks = np.unique(-3 - used)                       # side-table rows referenced by the slice, ascending
+        remap = {int(k): i for i, k in enumerate(ks)}
+        out.rand_tok = [plan.rand_tok[int(k)] for k in ks]
+        idx = np.nonzero(out.src <= -3)
+        out.src[idx] = [-3 - remap[int(-3 - v)] for v in out.src[idx]]
+    return out

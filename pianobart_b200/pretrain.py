@@ -15,8 +15,10 @@ fused device step (no per-sample D2H/H2D, no host argmax):
 """
 import ctypes as C
 import os
+import queue
 import shutil
 import sys
+import threading
 
 import numpy as np
 import torch
@@ -139,10 +141,12 @@ class PretrainStep:
         self.d2h_bytes = 24 * 4
 
     # -- stage 1: host plan + H2D + noising kernel
-    def upload(self, ori_batch, choices=None):
-        """ori_batch: (B,S,8) integer tensor or array on the HOST."""
+    def upload(self, ori_batch, choices=None, plan=None):
+        """ori_batch: (B,S,8) integer tensor or array on the HOST.  plan: a NoisePlan drawn ahead of time for exactly
+        this batch (PlanPrefetcher); otherwise it is drawn here."""
         ori = ori_batch.numpy() if isinstance(ori_batch, torch.Tensor) else np.asarray(ori_batch)
-        plan = noising.make_plan(ori, self.S, self.mask_percent, choices)
+        if plan is None:
+            plan = noising.make_plan(ori, self.S, self.mask_percent, choices)
         self.h_ori.numpy()[...] = ori
         self.h_src.numpy()[...] = plan.src
         self.h_loss.numpy()[...] = plan.loss
@@ -229,11 +233,53 @@ class PretrainStep:
         return total, losses, accs
 
 
+class PlanPrefetcher:
+    """Input pipeline stage: a host thread pulls the next batch from the data iterator and draws its noise
+    plan while the GPU executes the current step.  Only this thread touches the Python / numpy RNG streams during an
+    iteration and it handles the batches strictly in order, so the corruption decisions are the ones a sequential run
+    (and the reference, pretrain.py:131-144) draws.  Under data parallelism with `world > 1` the iterator yields the GLOBAL
+    batch on every rank; the plan is drawn for all of it and sliced to this rank's samples (one logical RNG stream)."""
+
+    def __init__(self, data_iter, mask_percent, rank=0, world=1, depth=2):
+        self.it, self.mask_percent, self.rank, self.world = data_iter, mask_percent, rank, world
+        self.q = queue.Queue(maxsize=depth)
+        self.t = threading.Thread(target=self._work, daemon=True)
+        self.t.start()
+
+    def _work(self):
+        try:
+            for batch in self.it:
+                ori = batch.numpy() if isinstance(batch, torch.Tensor) else np.asarray(batch)
+                plan = noising.make_plan(ori, ori.shape[1], self.mask_percent)
+                if self.world > 1:
+                    per = ori.shape[0] // self.world
+                    lo = self.rank * per
+                    plan = noising.slice_plan(plan, lo, lo + per)
+                    ori = ori[lo:lo + per]
+                self.q.put((np.ascontiguousarray(ori), plan))
+            self.q.put(None)
+        except BaseException as e:     # surfaced in the consumer thread
+            self.q.put(e)
+
+    def __iter__(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+
+
 class Pretrainer:
     """Same interface as reference `Pretrainer` (pretrain.py:51-209)."""
 
     def __init__(self, pianobart: PianoBart, train_dataloader, valid_dataloader, lr, batch, max_seq_len, mask_percent,
-                 cpu, cuda_devices=None, process_group=None, verbose=True):
+                 cpu, cuda_devices=None, process_group=None, verbose=True, global_batches=False):
+        """global_batches (data parallel only): the data loaders yield the GLOBAL batch on every rank; each rank draws the
+        noise plan for all of it in global sample order and trains on its slice, so a seeded run makes the corruption
+        decisions of the single-process reference.  Otherwise every rank noises its own batches from
+        its own RNG streams."""
         if cpu or not torch.cuda.is_available():
             raise L.PBError('pianobart_b200.Pretrainer has no CPU path (sm_100a kernels only)')
         dev = 'cuda'
@@ -255,6 +301,12 @@ class Pretrainer:
         self.optim = FusedAdamW(self.pianobart, lr=lr, weight_decay=0.01)
         self.batch, self.max_seq_len, self.mask_percent = batch, max_seq_len, mask_percent
         self.pg = process_group
+        self.rank, self.world = 0, 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.rank, self.world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        self.global_batches = bool(global_batches) and self.world > 1
+        self.prefetch = os.environ.get('PIANOBART_B200_PREFETCH', '1') != '0'
         self._steps = {}
         self._train_mode = True
 
@@ -288,12 +340,29 @@ class Pretrainer:
         lm = st.loss_mask.view(-1, 8).cpu()
         return enc, lm
 
+    def _batches(self, training_data):
+        """(ori, plan) pairs in order: drawn one step ahead on a host thread (default), or inline."""
+        world = self.world if self.global_batches else 1
+        if self.prefetch:
+            return iter(PlanPrefetcher(iter(training_data), self.mask_percent, self.rank, world))
+
+        def inline():
+            for batch in training_data:
+                ori = batch.numpy() if isinstance(batch, torch.Tensor) else np.asarray(batch)
+                plan = noising.make_plan(ori, ori.shape[1], self.mask_percent)
+                if world > 1:
+                    per = ori.shape[0] // world
+                    plan = noising.slice_plan(plan, self.rank * per, (self.rank + 1) * per)
+                    ori = ori[self.rank * per:(self.rank + 1) * per]
+                yield ori, plan
+        return inline()
+
     def iteration(self, training_data, max_seq_len, train=True):
         total_acc, total_losses, nb = np.zeros(8), 0.0, 0
-        for ori_seq_batch in training_data:
+        for ori_seq_batch, plan in self._batches(training_data):
             B, S = ori_seq_batch.shape[0], ori_seq_batch.shape[1]
             st = self._step(B, S)
-            st.upload(ori_seq_batch)
+            st.upload(ori_seq_batch, plan=plan)
             st.noise()
             st.run(train=train)
             total, losses, accs = st.fetch_stats()

@@ -181,6 +181,58 @@ def test_flash_attention_fwd_bwd_vs_torch(B, H, Sq, Sk, causal, pad, fused):
     assert torch.allclose(lse[:, :, :Sq], lse_ref.detach(), atol=2e-2, rtol=1e-3)
 
 
+@pytest.mark.parametrize('causal', [0, 1])
+def test_attention_pipelines_tolerate_late_tiles(causal):
+    """Fault injection (pb_debug_set_attn_delay): the TMA producers of all three attention kernels stall pseudo-random
+    times before their loads, so tiles land late and the softmax warps / the MMA thread drift several blocks apart.
+    Round 1's forward kernel kept p_full / pv_done on single mbarriers whose parity waits aliased in exactly that
+    situation (early release -> O read before the last P V; missed phase -> deadlock -> trap): the cold-start launch
+    failure.  Results must be identical to the undisturbed run and match torch."""
+    L, lib = _lib()
+    dev = 'cuda:0'
+    torch.manual_seed(13)
+    B, H, S, hd = 2, 8, 1024, 128
+    d = H * hd
+    qkv = (torch.randn(B, S, 3 * d, device=dev) * 0.7).bfloat16()
+    keep = (torch.rand(B, S, device=dev) > 0.2).to(torch.uint8); keep[:, 0] = 1
+    do = (torch.randn(B, S, d, device=dev) * 0.5).bfloat16()
+
+    def run(delay):
+        o = torch.zeros(B, S, d, device=dev, dtype=torch.bfloat16)
+        dqkv = torch.zeros_like(qkv)
+        lse = torch.zeros(B, H, S, device=dev); dvec = torch.zeros(B, H, S, device=dev)
+        a = L.AttnDesc()
+        a.q, a.k, a.v, a.o, a.dout = qkv.data_ptr(), qkv.data_ptr() + 2 * d, qkv.data_ptr() + 4 * d, o.data_ptr(), do.data_ptr()
+        a.dq, a.dk, a.dv = dqkv.data_ptr(), dqkv.data_ptr() + 2 * d, dqkv.data_ptr() + 4 * d
+        a.ldq = a.ldk = a.ldv = a.lddq = a.lddk = a.lddv = 3 * d
+        a.ldo = a.lddo = d
+        a.lse, a.dvec, a.key_keep = lse.data_ptr(), dvec.data_ptr(), keep.data_ptr()
+        a.B, a.H, a.Sq, a.Sk, a.hd, a.causal, a.scale = B, H, S, S, hd, causal, hd ** -0.5
+        prev = lib.pb_debug_set_attn_delay(delay)
+        try:
+            L.check(lib.pb_attn_fwd(C.byref(a), L.stream_ptr()), 'attn_fwd')
+            L.check(lib.pb_attn_bwd(C.byref(a), L.stream_ptr()), 'attn_bwd')
+            torch.cuda.synchronize()
+        finally:
+            lib.pb_debug_set_attn_delay(prev)
+        return o, dqkv, lse
+
+    o0, g0, l0 = run(0)
+    for delay in (6000, 40000):
+        o1, g1, l1 = run(delay)
+        assert torch.equal(o0, o1) and torch.equal(l0, l1), delay      # forward: bit-identical (same accumulation order)
+        assert torch.equal(g0, g1), delay
+    qf = qkv[..., :d].float().view(B, S, H, hd).transpose(1, 2)
+    kf = qkv[..., d:2 * d].float().view(B, S, H, hd).transpose(1, 2)
+    vf = qkv[..., 2 * d:].float().view(B, S, H, hd).transpose(1, 2)
+    allow = (keep != 0)[:, None, None, :].expand(B, H, S, S)
+    if causal:
+        allow = allow & torch.ones(S, S, dtype=torch.bool, device=dev).tril()
+    ref = (torch.softmax(((qf @ kf.transpose(-1, -2)) * hd ** -0.5).masked_fill(~allow, float('-inf')), -1) @ vf)
+    ref = ref.transpose(1, 2).reshape(B, S, d)
+    assert ((o0.float() - ref).abs().max() / ref.abs().max()).item() < 3e-2
+
+
 def test_octuple_embed_bwd_vs_index_add():
     """pb_octuple_embed_bwd (shared-memory accumulators per 32-column table slice) against torch index_add, skewed ids."""
     from pianobart_b200.vocab import build_octuple_vocab

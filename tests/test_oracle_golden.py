@@ -156,3 +156,13 @@ def test_generate_default_fixture_matches_oracle_sampler():
             tok = O.sample_step([row[seg[j]:seg[j + 1]] for j in range(8)], rs)
             mism += int((np.asarray(tok) != g['ref_sampled_' + key][steps[t]]).sum())
         assert mism == 0, (key, mism)
+
+
+def test_truncation_oracle_pinned_to_executed_reference():
+    """oracle.postprocess_oracle.octuple_truncate == demo.Octuple2Midi (demo.py:72-102) executed with the MIDI codec stubbed."""
+    from oracle import postprocess_oracle as PO
+    g = load('truncate')
+    for x, edited, n in zip(g['inputs'], g['edited'], g['lengths']):
+        out, length = PO.octuple_truncate(x)
+        assert np.array_equal(out, edited.astype(np.int64))
+        assert (length if length else -1) == int(n) or (length == 0 and n == -1)

@@ -331,6 +331,63 @@ def golden_genft():
     print('genft total', out['train_total'], 'valid', out['valid_total'], 'gnorm', out['grad_norm_preclip'])
 
 
+def golden_truncate():
+    """demo.Octuple2Midi (demo.py:72-102) EXECUTED with `miditoolkit` and the MIDI codec stubbed: records, for a set of
+    generated-looking sequences, the list the reference hands to encoding_to_MIDI (or "Generate Fail")."""
+    import types
+    captured = {}
+    mt = types.ModuleType('miditoolkit')
+    mt.midi = types.SimpleNamespace(parser=types.SimpleNamespace(MidiFile=None))
+    sys.modules['miditoolkit'] = mt
+    for name in ('Data', 'Data.data_generation', 'Data.data_generation.convert'):
+        sys.modules[name] = types.ModuleType(name)
+
+    class _Midi:
+        def dump(self, path):
+            pass
+
+    def enc2midi(lst):
+        captured['list'] = [list(r) for r in lst]
+        return _Midi()
+    conv = sys.modules['Data.data_generation.convert']
+    conv.MIDI_to_encoding = conv.padding = None
+    conv.encoding_to_MIDI = enc2midi
+    import demo as ref_demo
+    S = 1024
+    rs = np.random.RandomState(5)
+    pad = np.array([256, 128, 129, 256, 128, 32, 254, 49])
+    cases = []
+    base = P.synth_ids(8, S, 500)
+    base[:, :, 3] = base[:, :, 3] % 128                      # pitches below the drum range
+    for b in range(8):
+        x = base[b].copy()
+        if b == 1:
+            x[300:] = pad                                    # generation stopped: PAD-filled tail (model.py:63-65)
+        elif b == 2:
+            x[517, 6] = 254 + 1                              # a <MASK> TimeSig inside the sequence
+        elif b == 3:
+            x[40, 3] = 200                                   # drum pitch
+        elif b == 4:
+            x[0] = pad                                       # empty generation
+        elif b == 5:
+            x[S - 1, 0] = 258                                # special token in the last row
+        elif b == 6:
+            x[77, 5] = 32                                    # Velocity == PAD id
+        cases.append(x)
+    out_rows, out_len = [], []
+    for x in cases:
+        captured.clear()
+        t = torch.from_numpy(x.copy())[None]
+        ref_demo.Octuple2Midi(t, '/tmp/_unused.mid')
+        out_rows.append(t[0].numpy().copy())                 # Octuple2Midi edits the squeezed view in place
+        out_len.append(len(captured['list']) if 'list' in captured else -1)
+        if 'list' in captured:
+            assert np.array_equal(np.array(captured['list']), out_rows[-1][:out_len[-1]])
+    np.savez_compressed(os.path.join(OUT, 'truncate.npz'), inputs=np.stack(cases).astype(np.int16),
+                        edited=np.stack(out_rows).astype(np.int16), lengths=np.array(out_len))
+    print('truncate lengths', out_len)
+
+
 def golden_cls():
     cfg = (64, 2, 2, 4, 128, 32)
     d, el, dl, heads, ffn, max_pos = cfg
@@ -382,7 +439,7 @@ def golden_cls():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['tiny', 'mid', 'default', 'noising', 'generate', 'cls', 'generate_default', 'genft']
+    which = sys.argv[1:] or ['tiny', 'mid', 'default', 'noising', 'generate', 'cls', 'generate_default', 'genft', 'truncate']
     if 'tiny' in which:
         golden_forward('fwd_tiny', (64, 2, 2, 4, 128, 32), 1, 5, 32, True,
                        ['encoder_linear.bias', 'word_emb.3.lut.weight', 'bart.decoder.layers.1.encoder_attn.k_proj.weight',
@@ -406,3 +463,5 @@ if __name__ == '__main__':
         golden_generate_default()
     if 'genft' in which:
         golden_genft()
+    if 'truncate' in which:
+        golden_truncate()
