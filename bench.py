@@ -124,7 +124,7 @@ def cpu_baseline(batch=1, steps=2, warmup=1):
                       % (batch, S, steps, os.cpu_count()), 's_per_step': per}
 
 
-def decode_bench(lm, pb, dev, peaks, steps=192, warmup=16):
+def decode_bench(lm, pb, dev, peaks, steps=192, warmup=16, batches=(1, 64)):
     """KV-cache decode (BASELINE.json configs[2]): encoder prompt 1024 tokens, batch 1 and 64; timed region = `steps`
     CUDA-graph replays (one generated Octuple token per sequence per replay), CUDA events on the launching stream."""
     import numpy as np
@@ -134,7 +134,7 @@ def decode_bench(lm, pb, dev, peaks, steps=192, warmup=16):
     out = {}
     d, L, F, S = 1024, 8, 2048, 1024
     w_bytes = 2 * (L * (4 * d * d + 2 * d * d + 2 * d * F) + 2048 * d + d * 1280)
-    for B in (1, 64):
+    for B in batches:
         gen = Generator(lm, B, S, S)
         ids = torch.from_numpy(P.synth_ids(B, S, 4321)).to(dev)
         keep = torch.ones(B, S, device=dev)

@@ -231,6 +231,11 @@ struct Ctx {
   int c, G, h, s, tid, warp, lane;
   uint32_t chunk_no;     // running index of the next chunk to consume (ring slot = chunk_no % RING)
   int* err;
+  long long* tr;         // developer trace (thread 0 of the CTA, last token of the launch) or null
+  int tr_n;
+  __device__ __forceinline__ void stamp() {
+    if (tr != nullptr && tid == 0 && tr_n < 4 * 96) tr[tr_n++] = clock64();
+  }
   __device__ __forceinline__ const uint8_t* chunk_wait() {
     const uint32_t slot = chunk_no % RING;
     mbar_wait_to(&sm->full_bar[slot], (chunk_no / RING) & 1u, err);
@@ -301,9 +306,11 @@ __device__ __forceinline__ void proj_hop(Ctx& cx, int N, int nchunks, const floa
   }
   const uint8_t* base0 = nullptr;
   const uint8_t* base1 = nullptr;
+  cx.stamp();                            // [4h+0] input vector complete (hop h)
   base0 = cx.chunk_wait();
   uint32_t c0 = cx.chunk_no;
   if (nchunks == 2) { ++cx.chunk_no; base1 = cx.chunk_wait(); cx.chunk_no = c0; }
+  cx.stamp();                            // [4h+1] weights in shared memory
   // each warp takes rows warp, warp + 16 (at most two: nrows <= 22)
   float acc[2] = {0.f, 0.f};
   const uint8_t* wrow[2];
@@ -337,6 +344,7 @@ __device__ __forceinline__ void proj_hop(Ctx& cx, int N, int nchunks, const floa
     }
   }
   cons_sync();                           // results published; every warp is done with the weight chunks
+  cx.stamp();                            // [4h+2] dot products done
   cx.chunk_release();
   if (nchunks == 2) cx.chunk_release();
   if (cx.tid < nrows / 2) {
@@ -347,6 +355,7 @@ __device__ __forceinline__ void proj_hop(Ctx& cx, int N, int nchunks, const floa
     if (out_bf) ll_store(out_bf + (n0 >> 1), pack_bf16x2(v0, v1), tag);
     if (out_f32) { ll_store(out_f32 + n0, __float_as_uint(v0), tag); ll_store(out_f32 + n0 + 1, __float_as_uint(v1), tag); }
   }
+  cx.stamp();                            // [4h+3] results stored
 }
 
 // Attention partial of (head h, split s): `nold` cached keys in the K / V ring chunks (+ the new key of this step when
@@ -354,11 +363,13 @@ __device__ __forceinline__ void proj_hop(Ctx& cx, int N, int nchunks, const floa
 __device__ __forceinline__ void attn_partial(Ctx& cx, int nold, bool own_new, bool use_keep, unsigned long long* part,
                                              uint32_t tag) {
   Shared* sm = cx.sm;
+  cx.stamp();
   const uint8_t* kc = cx.chunk_wait();
   const uint32_t c0 = cx.chunk_no;
   ++cx.chunk_no;
   const uint8_t* vc = cx.chunk_wait();
   cx.chunk_no = c0;
+  cx.stamp();
   // scores: warp w takes keys w, w + 16, ...; lane = 4 head dims
   const float4 q4 = *reinterpret_cast<const float4*>(&sm->q[cx.lane * 4]);
   for (int j = cx.warp; j < nold; j += NCW) {
@@ -408,6 +419,7 @@ __device__ __forceinline__ void attn_partial(Ctx& cx, int nold, bool own_new, bo
     sm->po[g][2 * dp + 1] = a1;
   }
   cons_sync();
+  cx.stamp();
   cx.chunk_release();
   cx.chunk_release();
   if (cx.tid < HD) {
@@ -419,6 +431,7 @@ __device__ __forceinline__ void attn_partial(Ctx& cx, int nold, bool own_new, bo
   } else if (cx.tid < HD + 2) {
     ll_store(part + (cx.tid - HD), __float_as_uint(sm->stat[cx.tid - HD]), tag);
   }
+  cx.stamp();
 }
 
 // combine the NSPLIT partials of head h -> o[h*128 .. +128) as tagged bf16x2 words
@@ -590,7 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
   // ============================================================== consumers
   Ctx cx;
   cx.p = &P; cx.sm = sm; cx.c = c; cx.G = G; cx.h = att_h; cx.s = att_s; cx.tid = tid; cx.warp = warp; cx.lane = lane;
-  cx.chunk_no = 0; cx.err = err;
+  cx.chunk_no = 0; cx.err = err; cx.tr = nullptr; cx.tr_n = 0;
   // encoder key-padding flags of this CTA's cross-attention slots (static for the whole generation)
   if (tid < 64) {
     const int j = tid * NSPLIT + att_s;
@@ -607,6 +620,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
     const int t = t0 + st;
     const uint32_t tb = epoch0 + (uint32_t)st * HOPS + 1u;       // tag of hop i of this token = tb + i
     uint32_t hop = 0;
+    cx.tr = (P.trace != nullptr && st == n_steps - 1) ? P.trace + (size_t)c * (4 * 96) : nullptr;
+    cx.stamp();
     // ---------------- front end: 8 embedding rows (table pre-scaled by 16, PianoBart.py:9-16,60-67) -> in_linear + pos
     for (int e2 = tid; e2 < E / 2; e2 += NCONS) {
       const int a = e2 >> 7, col = (e2 & 127) * 2;

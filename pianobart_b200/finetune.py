@@ -1,7 +1,11 @@
 """Sequence- / token-classification finetuning, mirroring reference finetune.py (`FinetuneTrainer`, :75-274).
 
 The backbone forward/backward run on the kernel path through the autograd bridge (modules._BackboneFn); the small
-classifier heads and their loss are PyTorch.  Reference behaviour kept: TokenClassification is built
+classifier heads (< 0.1 % of the FLOPs) and their loss are PyTorch.  The 174 M backbone parameters are
+updated by the fused HF-semantics AdamW kernel over the flat buffer (pretrain.FusedAdamW, clipping off); only the handful
+of head tensors go through the per-tensor HFAdamW below.  Data parallel: one process per GPU, gradients all-reduced (sum)
+over NCCL with the loss normalised by the GLOBAL batch / mask count, so the summed gradient is the reference's full-batch
+gradient (the reference uses single-process nn.DataParallel, finetune.py:101-103).  Reference behaviour kept: TokenClassification is built
 with class_num+1 (finetune.py:98), velocity (class_num >= 5) feeds shifted labels through the replacement decoder front
 end (:194-198), otherwise decoder ids = encoder ids (:211-212); loss = CE masked by encoder non-pad / sum(mask) for token
 tasks, mean CE for sequence tasks (:125-132); optional L2-norm regulariser (:241-243); NO gradient clipping (:250);
@@ -16,6 +20,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from .modules import SequenceClassification, TokenClassification
+from .pretrain import FusedAdamW
 
 
 class HFAdamW(torch.optim.Optimizer):
@@ -49,12 +54,18 @@ class HFAdamW(torch.optim.Optimizer):
 
 class FinetuneTrainer:
     def __init__(self, pianobart, train_dataloader, valid_dataloader, test_dataloader, lr, class_num, hs, testset_shape,
-                 cpu, cuda_devices=None, model=None, SeqClass=False, error=False, weight=None):
+                 cpu, cuda_devices=None, model=None, SeqClass=False, error=False, weight=None, process_group=None):
         if cpu or not torch.cuda.is_available():
             raise L.PBError('pianobart_b200.FinetuneTrainer has no CPU path (sm_100a kernels only)')
         dev = 'cuda'
-        if cuda_devices is not None and len(cuda_devices) >= 1:
+        if process_group is not None:
+            dev += ':' + str(torch.cuda.current_device())
+        elif cuda_devices is not None and len(cuda_devices) >= 1:
             dev += ':' + str(cuda_devices[0])
+        self.pg, self.world = process_group, 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
         self.device = torch.device(dev)
         self.pianobart, self.SeqClass, self.class_num = pianobart, SeqClass, class_num
         if model is not None:
@@ -64,8 +75,15 @@ class FinetuneTrainer:
         else:
             self.model = TokenClassification(pianobart, class_num + 1, hs).to(self.device)
         self.train_data, self.valid_data, self.test_data = train_dataloader, valid_dataloader, test_dataloader
-        params = [p for p in self.model.parameters() if p.requires_grad]
-        self.optim = HFAdamW(params, lr=lr, weight_decay=0.01)
+        # backbone: fused kernel over the flat fp32 buffer (no clipping in the reference's finetune, finetune.py:250);
+        # head / replacement-front-end tensors: per-tensor HFAdamW
+        self.pianobart._ensure_packed()
+        flat_ids = {id(p) for _, p in self.pianobart._named_flat_params()}
+        head_params = [p for p in self.model.parameters() if p.requires_grad and id(p) not in flat_ids
+                       and p is not self.pianobart.bart.shared.weight]
+        self.optim_backbone = FusedAdamW(self.pianobart, lr=lr, weight_decay=0.01, max_grad_norm=0.0)
+        self.optim = HFAdamW(head_params, lr=lr, weight_decay=0.01)
+        self._head_params = head_params
         self.loss_func = nn.CrossEntropyLoss(reduction='none')
         self.testset_shape = testset_shape if not error else (testset_shape[:-1] if testset_shape is not None else None)
         self.weight, self.error = weight, error
@@ -117,13 +135,34 @@ class FinetuneTrainer:
             else:
                 correct, count = torch.sum((y == output).float()), y.shape[0]
                 loss = self.compute_loss(y_hat, y, attn, seq)
+            if self.world > 1:
+                # global normaliser: loss_r = (local sum) / (global count); the rank gradients then SUM to the full-batch one
+                import torch.distributed as dist
+                n_loc = torch.tensor([float(count)], device=self.device)
+                n_all = n_loc.clone()
+                dist.all_reduce(n_all, group=self.pg)
+                loss = loss * (n_loc / n_all).squeeze()
             if self.weight is not None:
-                for param in self.model.parameters():
-                    loss = loss + self.weight * torch.norm(param, p=2)
+                reg = sum(torch.norm(param, p=2) for param in self.model.parameters())
+                loss = loss + self.weight * reg / self.world
             if mode == 0:
-                self.model.zero_grad()
-                loss.backward()          # no clipping in the reference (finetune.py:250)
+                pb = self.pianobart
+                pb._grad.zero_()                      # one memset instead of ~370 per-parameter ones
+                for p in self._head_params:
+                    p.grad = None
+                loss.backward()                       # no clipping in the reference (finetune.py:250)
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(pb._grad, group=self.pg)
+                    for p in self._head_params:
+                        if p.grad is not None:
+                            dist.all_reduce(p.grad, group=self.pg)
+                self.optim_backbone.step()
                 self.optim.step()
+        if self.world > 1:
+            import torch.distributed as dist
+            loss = loss.detach().clone()
+            dist.all_reduce(loss, group=self.pg)      # the global loss value (sum of the normalised rank terms)
         return loss.detach(), correct, count, output
 
     def iteration(self, training_data, mode, seq):
@@ -144,7 +183,7 @@ class FinetuneTrainer:
     def save_checkpoint(self, epoch, train_acc, valid_acc, valid_loss, train_loss, is_best, filename):
         state = {'epoch': epoch + 1, 'state_dict': {k: v.detach().clone() for k, v in self.model.state_dict().items()},
                  'valid_acc': valid_acc, 'valid_loss': valid_loss, 'train_loss': train_loss, 'train_acc': train_acc,
-                 'optimizer': self.optim.state_dict()}
+                 'optimizer': {'heads': self.optim.state_dict(), 'backbone': self.optim_backbone.state_dict()}}
         torch.save(state, filename)
         if is_best:
             shutil.copyfile(filename, filename.split('.')[0] + '_best.ckpt')

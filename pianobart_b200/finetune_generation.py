@@ -6,6 +6,7 @@ attributes, per-attribute CE is multiplied by 0.3 (i = 2, 6, 7) / 1.5 (i = 3) / 
 normalised by sum(n_tok) (:238-250), gradients clipped at 3.0, HF AdamW(lr, weight_decay=0.01).
 The "FAD" shape-similarity metric (:185-223, needs the `shapesimilarity` pip package) is out of scope.
 """
+import shutil
 import sys
 
 import numpy as np
@@ -63,6 +64,20 @@ class GenerationTrainer:
     def valid(self):
         self.model.eval()
         return self.iteration(self.valid_data, 1)
+
+    def test(self):
+        """finetune_generation.py:120-124 without the per-batch argmax dump (the loss / accuracy columns only)."""
+        self.model.eval()
+        return self.iteration(self.test_data, 2)
+
+    def save_checkpoint(self, epoch, train_acc, valid_acc, valid_loss, train_loss, is_best, filename):
+        """finetune_generation.py:272-290: 'state_dict' = the PianoBartLM (reference key names)."""
+        state = {'epoch': epoch + 1, 'state_dict': {k: v.detach().clone() for k, v in self.model.state_dict().items()},
+                 'valid_acc': valid_acc, 'valid_loss': valid_loss, 'train_loss': train_loss, 'train_acc': train_acc,
+                 'optimizer': self.optim.state_dict()}
+        torch.save(state, filename)
+        if is_best:
+            shutil.copyfile(filename, filename.split('.')[0] + '_best.ckpt')
 
     def iteration(self, training_data, mode):
         total_acc, total_loss, nb = np.zeros(8), 0.0, 0

@@ -82,6 +82,10 @@ class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, dec_embeds, owner, graph, want_logits):
         ctx.owner, ctx.graph = owner, graph
+        # the graph's activation buffers (and its dropout seed) belong to the MOST RECENT forward of this shape: remember
+        # which forward this is so that backward can refuse to differentiate an overwritten one
+        graph.fwd_generation = getattr(graph, 'fwd_generation', 0) + 1
+        ctx.generation = graph.fwd_generation
         ctx.has_dec_embeds = dec_embeds is not None
         if dec_embeds is not None:
             n = dec_embeds.numel()
@@ -100,9 +104,10 @@ class _BackboneFn(torch.autograd.Function):
         graph, owner = ctx.graph, ctx.owner
         if graph.bwd is None:
             raise RuntimeError('forward was run without gradient support (torch.no_grad)')
-        if owner._live_graph is not graph:
-            raise RuntimeError('pianobart_b200: backward through a stale forward (another forward with a different '
-                               'shape ran in between); only the most recent forward can be differentiated')
+        if owner._live_graph is not graph or graph.fwd_generation != ctx.generation:
+            raise RuntimeError('pianobart_b200: backward through a stale forward (another forward ran in between and '
+                               'overwrote the saved activations); only the most recent forward can be differentiated - '
+                               'call backward() before the next forward, or run the extra forward under torch.no_grad()')
         owner._prepare_grads()
         dst = graph.dlogits if ctx.want_logits else graph.d_out
         n = g_out.numel()

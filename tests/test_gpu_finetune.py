@@ -63,6 +63,47 @@ def test_token_classification_matches_reference(cn):
     assert _rel(out.detach().cpu().numpy(), g['tokcls%d_logits' % cn]) < 1e-4
 
 
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+@pytest.mark.parametrize('task', ['seqcls', 'tokcls4'])
+def test_finetune_training_gradients_match_reference(task, dtype):
+    """Rows A14 / A15: loss and gradients of one finetune step (backbone through the kernel path, head parameters included)
+    against the executed reference (cls_tiny.npz: reference SequenceClassification / TokenClassification + the loss of
+    finetune.py:125-132, eval-mode arithmetic so that nn.Dropout is off)."""
+    from pianobart_b200.modules import SequenceClassification, TokenClassification
+    g = load_golden('cls_tiny')
+    d = int(g['cfg'][0])
+    pb, _ = build_cuda_model(g['cfg'], int(g['seed']), dtype, lm=False)
+    ids = torch.from_numpy(g['ids'].astype(np.int64)).cuda()
+    mask = (ids[:, :, 0] != pb.bar_pad_word).float()
+    if task == 'seqcls':
+        m = SequenceClassification(pb, class_num=4, hs=d).cuda()
+        _load_extra(m, 'seqcls.', ['attention.ws1.weight', 'attention.ws2.weight', 'classifier.1.weight', 'classifier.1.bias',
+                                   'classifier.3.weight', 'classifier.3.bias'], 9)
+        m.eval()
+        y = torch.from_numpy(g['seqcls_labels']).cuda()
+        loss = torch.nn.functional.cross_entropy(m(ids, mask), y, reduction='none').sum() / ids.shape[0]
+    else:
+        m = TokenClassification(pb, class_num=4, hs=d).cuda()
+        _load_extra(m, 'tokcls4.', ['classifier.1.weight', 'classifier.1.bias', 'classifier.3.weight', 'classifier.3.bias'], 9)
+        m.eval()
+        y = torch.from_numpy(g['tokcls4_labels']).cuda()
+        lg = m(ids, ids, mask, mask)
+        loss = (torch.nn.functional.cross_entropy(lg.permute(0, 2, 1), y, reduction='none') * mask).sum() / mask.sum()
+    m.zero_grad()
+    loss.backward()
+    ref = float(g[task + '_loss'])
+    assert abs(loss.item() - ref) / ref < (1e-5 if dtype == 'fp32' else 1e-2)
+    sd = dict(m.named_parameters())
+    tol = 2e-4 if dtype == 'fp32' else 6e-2
+    n = 0
+    for k in g.files:
+        if k.startswith(task + '_grad:'):
+            name = k.split(':', 1)[1]
+            assert _rel(sd[name].grad.cpu().numpy(), g[k]) < tol, name
+            n += 1
+    assert n >= 8
+
+
 def test_generation_finetune_loss_matches_oracle():
     """finetune_generation.py:140-258 semantics (y_shift = x, decoder-mask loss, extra per-head factors)."""
     from oracle import pianobart_oracle as O

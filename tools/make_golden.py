@@ -408,6 +408,18 @@ def golden_cls():
     mask = (ids[:, :, 0] != pb.bar_pad_word).float()
     with torch.no_grad():
         out['seqcls_logits'] = sc(ids, mask).numpy()
+    # training gradients of the sequence task (finetune.py:125-132,215-221: mean CE over the batch), eval-mode arithmetic
+    GRAD_KEYS = ('pianobart.bart.encoder.layers.0.fc1.weight', 'pianobart.bart.decoder.layers.1.self_attn.out_proj.weight',
+                 'pianobart.encoder_linear.weight', 'pianobart.word_emb.3.lut.weight')
+    y_seq = torch.from_numpy(np.random.RandomState(6).randint(0, 4, size=(B,))).long()
+    sc.zero_grad()
+    loss = torch.nn.functional.cross_entropy(sc(ids, mask), y_seq, reduction='none').sum() / B
+    loss.backward()
+    out['seqcls_labels'] = y_seq.numpy()
+    out['seqcls_loss'] = np.float64(loss.item())
+    for k, v in sc.named_parameters():
+        if k in GRAD_KEYS or k.startswith('classifier') or k.startswith('attention'):
+            out['seqcls_grad:' + k] = v.grad.numpy().copy()
     # token classification (model.py:236-272): class_num=4 (< 5: decoder ids = x) and 8 (>= 5: label embedding)
     for cn in (4, 8):
         pb, _ = build_ref(cfg, 9)
@@ -435,6 +447,19 @@ def golden_cls():
             else:
                 res = tc(ids, ids, mask, mask)
             out['tokcls%d_logits' % cn] = res.numpy()
+        if cn == 4:
+            # training gradients of the token task (finetune.py:125-130,233-235: CE masked by encoder non-pad / sum(mask))
+            y_tok = torch.from_numpy(np.random.RandomState(8).randint(0, cn, size=(B, S))).long()
+            tc.zero_grad()
+            lg = tc(ids, ids, mask, mask)
+            l = torch.nn.functional.cross_entropy(lg.permute(0, 2, 1), y_tok, reduction='none') * mask
+            loss = l.sum() / mask.sum()
+            loss.backward()
+            out['tokcls4_labels'] = y_tok.numpy()
+            out['tokcls4_loss'] = np.float64(loss.item())
+            for k, v in tc.named_parameters():
+                if k in GRAD_KEYS or k.startswith('classifier'):
+                    out['tokcls4_grad:' + k] = v.grad.numpy().copy()
     np.savez_compressed(os.path.join(OUT, 'cls_tiny.npz'), **out)
 
 
