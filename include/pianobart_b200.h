@@ -302,7 +302,10 @@ typedef struct pb_decode_persist_desc {
   unsigned int* epoch;                                 /* 1 word, zero-initialised once, advanced by the kernel        */
   int* error_flag;                                     /* set to a non-zero code before a bounded wait traps           */
   long long* trace;                                    /* developer hook (NULL in production): clock64 stamps of the hops
-                                                          of the launch's LAST token, [gridDim][4 * 96] per CTA         */
+                                                          of the launch's LAST token, [gridDim][6 * 96] per CTA         */
+  int dbg_flags;                                       /* developer experiments (0 in production): 1 = the producer does
+                                                          not copy (no weight / KV traffic, results are garbage);
+                                                          2 = only the first consumer warp polls for inputs            */
 } pb_decode_persist_desc;
 /* generates up to n_steps tokens (stops early when stop_when_done and the stop rule fired); seg sizes / temperatures /
  * nucleus p / <PAD> ids live on the HOST */

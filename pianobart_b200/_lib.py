@@ -68,7 +68,8 @@ class DecodePersistDesc(C.Structure):
                 [(n, C.c_void_p) for n in (
                     'emb_table', 'w_in', 'b_in', 'pos_table', 'lne_g', 'lne_b', 'w_heads', 'b_heads', 'enc_keep',
                     't_dev', 'cur_tok', 'result', 'sampled', 'done', 'n_written', 'uniforms', 'forced', 'logits_out',
-                    'raw0', 'raw1', 'raw2', 'qkv', 'qc', 'ob', 'f1', 'part', 'logits_ll', 'tok_ll', 'epoch', 'error_flag', 'trace')])
+                    'raw0', 'raw1', 'raw2', 'qkv', 'qc', 'ob', 'f1', 'part', 'logits_ll', 'tok_ll', 'epoch', 'error_flag', 'trace')] +
+                [('dbg_flags', C.c_int)])
 
 
 class PBError(RuntimeError):

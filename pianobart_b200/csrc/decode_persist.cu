@@ -234,7 +234,7 @@ struct Ctx {
   long long* tr;         // developer trace (thread 0 of the CTA, last token of the launch) or null
   int tr_n;
   __device__ __forceinline__ void stamp() {
-    if (tr != nullptr && tid == 0 && tr_n < 4 * 96) tr[tr_n++] = clock64();
+    if (tr != nullptr && tid == 0 && tr_n < 6 * 96) tr[tr_n++] = clock64();
   }
   __device__ __forceinline__ const uint8_t* chunk_wait() {
     const uint32_t slot = chunk_no % RING;
@@ -249,12 +249,14 @@ struct Ctx {
 };
 
 // reads a bf16x2-tagged vector of n elements (n / 2 words) into shared memory (permuted fp32)
-__device__ __forceinline__ void read_vec(const Ctx& cx, const unsigned long long* buf, int n, uint32_t tag, float* dst) {
+__device__ __forceinline__ void read_vec(Ctx& cx, const unsigned long long* buf, int n, uint32_t tag, float* dst) {
+  cx.stamp();                            // [6h+0] hop start
   for (int w = cx.tid; w < n / 2; w += NCONS) {
     const float2 f = unpack_bf16x2(ll_wait(buf + w, tag, cx.err));
     dst[xperm(2 * w)] = f.x;
     dst[xperm(2 * w + 1)] = f.y;
   }
+  cx.stamp();                            // [6h+1] this thread's words arrived
   cons_sync();
 }
 // sum and sum of squares over the consumer threads in one pass (two named-barrier syncs)
@@ -272,11 +274,17 @@ __device__ __forceinline__ float2 cons_sum2(float a, float b, float* red) {
 }
 // dst (permuted fp32, D elements) = LayerNorm(tagged vector `buf`): every thread owns one word (two elements); gamma / beta
 // are requested before the poll so that their latency hides behind the wait for the data
-__device__ __forceinline__ void read_ln(const Ctx& cx, const unsigned long long* buf, uint32_t tag, const float* gamma,
+__device__ __forceinline__ void read_ln(Ctx& cx, const unsigned long long* buf, uint32_t tag, const float* gamma,
                                         const float* beta, float* dst) {
+  cx.stamp();                            // [6h+0] hop start
   const float2 g = *reinterpret_cast<const float2*>(gamma + 2 * cx.tid);
   const float2 b = *reinterpret_cast<const float2*>(beta + 2 * cx.tid);
+  if (cx.p->dbg_flags & 2) {            // experiment: one warp polls every word first, the others sleep on the barrier
+    if (cx.warp == 0) for (int w = cx.lane; w < D / 2; w += 32) ll_wait(buf + w, tag, cx.err);
+    cons_sync();
+  }
   const float2 f = unpack_bf16x2(ll_wait(buf + cx.tid, tag, cx.err));
+  cx.stamp();                            // [6h+1] this thread's word arrived
   const float2 st = cons_sum2(f.x + f.y, f.x * f.x + f.y * f.y, cx.sm->red);
   const float mean = st.x * (1.0f / D);
   const float var = fmaxf(st.y * (1.0f / D) - mean * mean, 0.f);
@@ -306,11 +314,11 @@ __device__ __forceinline__ void proj_hop(Ctx& cx, int N, int nchunks, const floa
   }
   const uint8_t* base0 = nullptr;
   const uint8_t* base1 = nullptr;
-  cx.stamp();                            // [4h+0] input vector complete (hop h)
+  cx.stamp();                            // [6h+2] input vector complete (hop h)
   base0 = cx.chunk_wait();
   uint32_t c0 = cx.chunk_no;
   if (nchunks == 2) { ++cx.chunk_no; base1 = cx.chunk_wait(); cx.chunk_no = c0; }
-  cx.stamp();                            // [4h+1] weights in shared memory
+  cx.stamp();                            // [6h+3] weights in shared memory
   // each warp takes rows warp, warp + 16 (at most two: nrows <= 22)
   float acc[2] = {0.f, 0.f};
   const uint8_t* wrow[2];
@@ -344,7 +352,7 @@ __device__ __forceinline__ void proj_hop(Ctx& cx, int N, int nchunks, const floa
     }
   }
   cons_sync();                           // results published; every warp is done with the weight chunks
-  cx.stamp();                            // [4h+2] dot products done
+  cx.stamp();                            // [6h+4] dot products done
   cx.chunk_release();
   if (nchunks == 2) cx.chunk_release();
   if (cx.tid < nrows / 2) {
@@ -355,7 +363,7 @@ __device__ __forceinline__ void proj_hop(Ctx& cx, int N, int nchunks, const floa
     if (out_bf) ll_store(out_bf + (n0 >> 1), pack_bf16x2(v0, v1), tag);
     if (out_f32) { ll_store(out_f32 + n0, __float_as_uint(v0), tag); ll_store(out_f32 + n0 + 1, __float_as_uint(v1), tag); }
   }
-  cx.stamp();                            // [4h+3] results stored
+  cx.stamp();                            // [6h+5] results stored
 }
 
 // Attention partial of (head h, split s): `nold` cached keys in the K / V ring chunks (+ the new key of this step when
@@ -448,13 +456,19 @@ __device__ __forceinline__ void attn_combine(Ctx& cx, int h, const unsigned long
 #pragma unroll
     for (int s = 0; s < NSPLIT; ++s) M = fmaxf(M, sm->po[0][2 * s]);
     float Lsum = 0.f, acc = 0.f;
-#pragma unroll 6
+    // all 18 partial words of this dim are requested before the first one is examined (18 dependent L2 round trips made
+    // this hop the longest of the layer in the first version); a word whose tag is not there yet is re-polled
+    unsigned long long pw[NSPLIT];
+#pragma unroll
+    for (int s = 0; s < NSPLIT; ++s) pw[s] = ll_load(part_h + (size_t)s * PB_DECODE_PART_WORDS + 4 + cx.tid);
+#pragma unroll
     for (int s = 0; s < NSPLIT; ++s) {
       const float m = sm->po[0][2 * s];
       const float w = (m == -INFINITY) ? 0.f : __expf(m - M);
-      const float o = __uint_as_float(ll_wait(part_h + (size_t)s * PB_DECODE_PART_WORDS + 4 + cx.tid, tag_in, cx.err));
+      uint32_t ow = (uint32_t)pw[s];
+      if ((uint32_t)(pw[s] >> 32) != tag_in) ow = ll_wait(part_h + (size_t)s * PB_DECODE_PART_WORDS + 4 + cx.tid, tag_in, cx.err);
       Lsum += w * sm->po[0][2 * s + 1];
-      acc += w * o;
+      acc += w * __uint_as_float(ow);
     }
     const float r = Lsum > 0.f ? acc / Lsum : 0.f;
     const float other = __shfl_xor_sync(0xffffffffu, r, 1);
@@ -581,7 +595,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
             if (stopped) break;
           }
           const Chunk ch = sch.get(i, t);
-          if (ch.bytes > 0) {
+          if (ch.bytes > 0 && !(P.dbg_flags & 1)) {
             pb::mbar_expect_tx(&sm->full_bar[slot], ch.bytes);
             bulk_load(sm->ring[slot], ch.src, ch.bytes, &sm->full_bar[slot], ch.kv ? pol_kv : pol_w);
           } else {
@@ -620,7 +634,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
     const int t = t0 + st;
     const uint32_t tb = epoch0 + (uint32_t)st * HOPS + 1u;       // tag of hop i of this token = tb + i
     uint32_t hop = 0;
-    cx.tr = (P.trace != nullptr && st == n_steps - 1) ? P.trace + (size_t)c * (4 * 96) : nullptr;
+    cx.tr = (P.trace != nullptr && st == n_steps - 1) ? P.trace + (size_t)c * (6 * 96) : nullptr;
     cx.stamp();
     // ---------------- front end: 8 embedding rows (table pre-scaled by 16, PianoBart.py:9-16,60-67) -> in_linear + pos
     for (int e2 = tid; e2 < E / 2; e2 += NCONS) {
@@ -631,6 +645,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
       sm->x[xperm(2 * e2)] = f.x;
       sm->x[xperm(2 * e2 + 1)] = f.y;
     }
+    cx.stamp();
     cons_sync();
     proj_hop<E>(cx, D, 2, sm->x, P.b_in, nullptr, reinterpret_cast<const bf16*>(P.pos_table) + (size_t)(t + 2) * D, false,
                 P.raw0, nullptr, tb + hop);
@@ -646,6 +661,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
       ++hop;
       if (att_h >= 0) {
         const bool own_new = (t % NSPLIT) == att_s;
+        cx.stamp();
         if (tid < 3 * (HD / 2)) {
           const int which = tid / (HD / 2), w = tid % (HD / 2);
           const float2 f = unpack_bf16x2(ll_wait(P.qkv + (which * D + att_h * HD) / 2 + w, tag_qkv, err));
@@ -661,6 +677,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
           }
         }
         if (own_new) asm volatile("fence.proxy.async.global;" ::: "memory");   // later bulk copies (async proxy) read these rows
+        cx.stamp();
         cons_sync();
         attn_partial(cx, split_count(t, att_s), own_new, false,
                      P.part + (size_t)(att_h * NSPLIT + att_s) * PB_DECODE_PART_WORDS, tb + hop);
@@ -684,11 +701,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
       ++hop;
       // ---- cross attention partial
       if (att_h >= 0) {
+        cx.stamp();
         if (tid < HD / 2) {
           const float2 f = unpack_bf16x2(ll_wait(P.qc + (att_h * HD) / 2 + tid, tag_qc, err));
           sm->q[2 * tid] = f.x * 0.08838834764831845f;
           sm->q[2 * tid + 1] = f.y * 0.08838834764831845f;
         }
+        cx.stamp();
         cons_sync();
         attn_partial(cx, split_count(P.S_enc, att_s), false, true,
                      P.part + (size_t)(att_h * NSPLIT + att_s) * PB_DECODE_PART_WORDS, tb + hop);

@@ -33,7 +33,8 @@ def main():
     gen.start(ids, torch.ones(1, S, device=dev), np.random.RandomState(0).random_sample((1, S, 8)), forced)
     gen.run_steps(int(os.environ.get('TRACE_AT', '500')))
     torch.cuda.synchronize()
-    tr = torch.zeros(148, 4 * 96, dtype=torch.int64, device=dev)
+    tr = torch.zeros(148, 6 * 96, dtype=torch.int64, device=dev)
+    gen.pdesc.dbg_flags = int(os.environ.get('DBG_FLAGS', '0'))
     gen.pdesc.trace = E._ptr(tr)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -44,27 +45,31 @@ def main():
     t = tr.cpu().numpy()
     np.save('gpurun_out/r2_decode_trace.npy', t)
     print('8 steps: %.1f us/step' % (ms * 1e3 / 8))
-    names = ['front'] + ['L%d.%s' % (l, n) for l in range(8) for n in ('qkv', 'spart', 'wo', 'qc', 'cpart', 'woc', 'fc1', 'fc2')] + ['heads']
+    names = ['L%d.%s' % (l, n) for l in range(8) for n in ('qkv', 'spart', 'wo', 'qc', 'cpart', 'woc', 'fc1', 'fc2')] + ['heads']
+    full = [c for c in range(148) if int((t[c] != 0).sum()) == 396]
     for cta in (1, 0, 100):
-        x = t[cta]
-        n = int((x != 0).sum())
-        x = x[:n]
-        print('CTA %d: %d stamps, token span %d cycles' % (cta, n, x[-1] - x[0]))
-        if (n - 1) % 4 != 0:
-            continue
-        hops = (n - 1) // 4
-        s = x[1:].reshape(hops, 4)
-        prev = np.concatenate([[x[0]], s[:-1, 3]])
+        x = t[cta][:396]
+        print('CTA %d: token span %d cycles; front %s' % (cta, x[-1] - x[0], np.diff(x[:6]).tolist()))
+        s = x[6:].reshape(-1, 6)
+        prev = np.concatenate([[x[5]], s[:-1, 5]])
         agg = {}
-        for i in range(hops):
-            nm = names[i].split('.')[-1] if i < len(names) else 'x'
-            a = agg.setdefault(nm, [0, 0, 0, 0, 0])
-            a[0] += s[i, 0] - prev[i]; a[1] += s[i, 1] - s[i, 0]; a[2] += s[i, 2] - s[i, 1]; a[3] += s[i, 3] - s[i, 2]; a[4] += 1
-        print('  hop     n  wait_input  wait_weights  compute  store   (avg cycles)')
+        for i in range(len(s)):
+            nm = names[i].split('.')[-1]
+            a = agg.setdefault(nm, np.zeros(7))
+            a[0] += s[i, 0] - prev[i]
+            a[1:6] += np.diff(s[i])
+            a[6] += 1
+        print('  hop      gap own_word vec+LN weights compute  store | period   (avg cycles)')
         for nm, a in agg.items():
-            print('  %-6s %2d  %10.0f  %12.0f  %7.0f  %5.0f' % (nm, a[4], a[0] / a[4], a[1] / a[4], a[2] / a[4], a[3] / a[4]))
-        tot = [sum(a[k] for a in agg.values()) for k in range(4)]
-        print('  total cycles: wait_input %d  wait_weights %d  compute %d  store %d' % tuple(tot))
+            v = a[:6] / a[6]
+            print('  %-6s' % nm, ' '.join('%7.0f' % q for q in v), '| %7.0f' % v.sum())
+    S = np.stack([t[c][6:396].reshape(-1, 6) for c in full])
+    own = S[:, :, 1] - S[:, :, 0]
+    work = S[:, :, 5] - S[:, :, 1]
+    print('per hop over %d CTAs (layer 1): own_word min / median / max | work-after-input median / max' % len(full))
+    for h in range(8, 16):
+        o, w = own[:, h], work[:, h]
+        print('  %-9s %6d %6d %6d | %6d %6d' % (names[h], o.min(), int(np.median(o)), o.max(), int(np.median(w)), w.max()))
 
 
 if __name__ == '__main__':

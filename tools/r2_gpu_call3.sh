@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-( timeout 300 python tools/gpu_decode_trace.py ) > gpurun_out/r2_decode_trace.log 2>&1
-cat gpurun_out/r2_decode_trace.log | tail -60
+for f in 0; do
+( DBG_FLAGS=$f timeout 300 python tools/gpu_decode_trace.py ) > gpurun_out/r2_decode_trace_f$f.log 2>&1
+echo "== DBG_FLAGS=$f"; cat gpurun_out/r2_decode_trace_f$f.log | head -60
+done
