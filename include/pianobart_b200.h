@@ -292,10 +292,11 @@ typedef struct pb_decode_persist_desc {
   const double* uniforms; const int* forced;           /* [S_max,8]; forced may be NULL                                */
   float* logits_out;                                   /* [1280] fp32 logits of the last executed step (may be NULL)   */
   /* exchange buffers (device, zero-initialised once; 8-byte words) and the tag epoch */
-  unsigned long long* raw0; unsigned long long* raw1; unsigned long long* raw2;   /* d/2 words each                    */
-  unsigned long long* qkv;                             /* 3d/2 words                                                   */
-  unsigned long long* qc; unsigned long long* ob;      /* d/2 words each                                               */
-  unsigned long long* f1;                              /* F/2 words                                                    */
+  /* (the first seven are polled by every CTA and hold 4 words per 128-byte line: allocate 4x the word count) */
+  unsigned long long* raw0; unsigned long long* raw1; unsigned long long* raw2;   /* 4 * d/2 words each                */
+  unsigned long long* qkv;                             /* 4 * 3d/2 words                                               */
+  unsigned long long* qc; unsigned long long* ob;      /* 4 * d/2 words each                                           */
+  unsigned long long* f1;                              /* 4 * F/2 words                                                */
   unsigned long long* part;                            /* 8*18*PB_DECODE_PART_WORDS words                              */
   unsigned long long* logits_ll;                       /* 1280 words                                                   */
   unsigned long long* tok_ll;                          /* 8 words                                                      */
@@ -303,9 +304,9 @@ typedef struct pb_decode_persist_desc {
   int* error_flag;                                     /* set to a non-zero code before a bounded wait traps           */
   long long* trace;                                    /* developer hook (NULL in production): clock64 stamps of the hops
                                                           of the launch's LAST token, [gridDim][6 * 96] per CTA         */
-  int dbg_flags;                                       /* developer experiments (0 in production): 1 = the producer does
-                                                          not copy (no weight / KV traffic, results are garbage);
-                                                          2 = only the first consumer warp polls for inputs            */
+  int dbg_flags;                                       /* developer experiment (0 in production): 1 = the producer does not
+                                                          copy (no weight / KV traffic, results are garbage) - separates
+                                                          the dependency-chain latency from the streaming time         */
 } pb_decode_persist_desc;
 /* generates up to n_steps tokens (stops early when stop_when_done and the stop rule fired); seg sizes / temperatures /
  * nucleus p / <PAD> ids live on the HOST */

@@ -109,10 +109,15 @@ __device__ __forceinline__ int xperm(int e) {
   return (e & ~255) + ((r & 4) << 5) + ((r >> 3) << 2) + (r & 3);
 }
 
+// Exchange vectors that EVERY CTA polls (raw0/1/2, qkv, qc, ob, f1) keep only 4 words (one 32-byte sector) per 128-byte
+// line: the polling traffic of 148 SMs then spreads over 4x more L2 slices (measured: with dense vectors the ~32 hot lines
+// of a vector made an L2 round trip cost 700-2500 cycles instead of ~300, and that latency is paid twice per hop).
+__device__ __forceinline__ int lls(int w) { return ((w >> 2) << 4) | (w & 3); }
+
 // pair range of CTA c for a projection with P row pairs
 __device__ __forceinline__ void pair_range(int P, int c, int G, int& p0, int& p1) {
-  p0 = (int)(((long long)c * P) / G);
-  p1 = (int)(((long long)(c + 1) * P) / G);
+  p0 = (int)(((unsigned)c * (unsigned)P) / (unsigned)G);            // c < 2^8, P <= 1536: 32-bit arithmetic is exact
+  p1 = (int)(((unsigned)(c + 1) * (unsigned)P) / (unsigned)G);
 }
 // cached keys of split s when the sequence holds `n` keys (keys j < n with j % NSPLIT == s)
 __device__ __forceinline__ int split_count(int n, int s) { return n > s ? (n - s + NSPLIT - 1) / NSPLIT : 0; }
@@ -252,7 +257,7 @@ struct Ctx {
 __device__ __forceinline__ void read_vec(Ctx& cx, const unsigned long long* buf, int n, uint32_t tag, float* dst) {
   cx.stamp();                            // [6h+0] hop start
   for (int w = cx.tid; w < n / 2; w += NCONS) {
-    const float2 f = unpack_bf16x2(ll_wait(buf + w, tag, cx.err));
+    const float2 f = unpack_bf16x2(ll_wait(buf + lls(w), tag, cx.err));
     dst[xperm(2 * w)] = f.x;
     dst[xperm(2 * w + 1)] = f.y;
   }
@@ -279,11 +284,7 @@ __device__ __forceinline__ void read_ln(Ctx& cx, const unsigned long long* buf, 
   cx.stamp();                            // [6h+0] hop start
   const float2 g = *reinterpret_cast<const float2*>(gamma + 2 * cx.tid);
   const float2 b = *reinterpret_cast<const float2*>(beta + 2 * cx.tid);
-  if (cx.p->dbg_flags & 2) {            // experiment: one warp polls every word first, the others sleep on the barrier
-    if (cx.warp == 0) for (int w = cx.lane; w < D / 2; w += 32) ll_wait(buf + w, tag, cx.err);
-    cons_sync();
-  }
-  const float2 f = unpack_bf16x2(ll_wait(buf + cx.tid, tag, cx.err));
+  const float2 f = unpack_bf16x2(ll_wait(buf + lls(cx.tid), tag, cx.err));
   cx.stamp();                            // [6h+1] this thread's word arrived
   const float2 st = cons_sum2(f.x + f.y, f.x * f.x + f.y * f.y, cx.sm->red);
   const float mean = st.x * (1.0f / D);
@@ -360,7 +361,7 @@ __device__ __forceinline__ void proj_hop(Ctx& cx, int N, int nchunks, const floa
     float v0 = cx.sm->out[2 * cx.tid] + eb0, v1 = cx.sm->out[2 * cx.tid + 1] + eb1;   // (the position row is only used without GELU)
     if (gelu) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
     if (resid) { v0 += resid[xperm(n0)]; v1 += resid[xperm(n0 + 1)]; }
-    if (out_bf) ll_store(out_bf + (n0 >> 1), pack_bf16x2(v0, v1), tag);
+    if (out_bf) ll_store(out_bf + lls(n0 >> 1), pack_bf16x2(v0, v1), tag);
     if (out_f32) { ll_store(out_f32 + n0, __float_as_uint(v0), tag); ll_store(out_f32 + n0 + 1, __float_as_uint(v1), tag); }
   }
   cx.stamp();                            // [6h+5] results stored
@@ -472,7 +473,7 @@ __device__ __forceinline__ void attn_combine(Ctx& cx, int h, const unsigned long
     }
     const float r = Lsum > 0.f ? acc / Lsum : 0.f;
     const float other = __shfl_xor_sync(0xffffffffu, r, 1);
-    if ((cx.tid & 1) == 0) ll_store(obuf + ((h * HD + cx.tid) >> 1), pack_bf16x2(r, other), tag_out);
+    if ((cx.tid & 1) == 0) ll_store(obuf + lls((h * HD + cx.tid) >> 1), pack_bf16x2(r, other), tag_out);
   }
   cons_sync();
 }
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
         cx.stamp();
         if (tid < 3 * (HD / 2)) {
           const int which = tid / (HD / 2), w = tid % (HD / 2);
-          const float2 f = unpack_bf16x2(ll_wait(P.qkv + (which * D + att_h * HD) / 2 + w, tag_qkv, err));
+          const float2 f = unpack_bf16x2(ll_wait(P.qkv + lls((which * D + att_h * HD) / 2 + w), tag_qkv, err));
           float* dst = which == 0 ? sm->q : (which == 1 ? sm->knew : sm->vnew);
           const float sc = which == 0 ? 0.08838834764831845f : 1.0f;       // hd^-0.5
           dst[2 * w] = f.x * sc;
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persist_kernel(const __gri
       if (att_h >= 0) {
         cx.stamp();
         if (tid < HD / 2) {
-          const float2 f = unpack_bf16x2(ll_wait(P.qc + (att_h * HD) / 2 + tid, tag_qc, err));
+          const float2 f = unpack_bf16x2(ll_wait(P.qc + lls((att_h * HD) / 2 + tid), tag_qc, err));
           sm->q[2 * tid] = f.x * 0.08838834764831845f;
           sm->q[2 * tid + 1] = f.y * 0.08838834764831845f;
         }

@@ -69,6 +69,11 @@ struct GemmKParams {
   int tma_c;    // C is stored with tmap_c
   int tma_pre;  // 0: none, 1: residual rows, 2: aux rows (MUL_AUX / MUL_DGELU operand) are loaded with tmap_pre
   int tma_x;    // aux output (AUX_PREACT / AUX_DGELU) is stored with tmap_x
+  // Tail splitting (cta_group::2, 256-wide tiles, no batching / split-K): the persistent grid has `slots` CTA pairs; when
+  // the tiles left over after the last full wave fill at most half of the slots, each of them is issued as two 256 x 128
+  // units (UMMA N = 128 from the same shared-memory stages), so the partial wave costs half a tile time instead of a whole
+  // one: 64 x 4 tiles on 74 pairs run in 3.5 instead of 4 tile times (out_proj, dO, q_c, dH*: profiles/r2_summary.md).
+  int full_units;   // units [0, full_units) are whole tiles; later units are (tile, column half) pairs.  -1: no splitting
 };
 
 // CG2: cta_group::2 - a pair of CTAs (one TPC) computes a 256 x BLOCK_N tile; each CTA stages its own 128 rows of A and
@@ -173,9 +178,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = tmem_base_smem;
 
   const long long units_per_batch = (long long)p.num_m_blocks * p.num_n_blocks * p.split_k;
+  auto ncol0 = [&](int n_blk, int nh) { return n_blk * BLOCK_N + (nh == 2 ? BLOCK_N / 2 : 0); };
 
   // unit index -> (m_blk, n_blk, split, h, b); m fastest so concurrently running CTAs share a B tile.
-  auto decode = [&](long long w, int& m_blk, int& n_blk, int& split, int& h, int& b) {
+  auto decode = [&](long long w, int& m_blk, int& n_blk, int& split, int& h, int& b, int& nh) {
+    nh = 0;                                   // 0: whole BLOCK_N-wide tile, 1 / 2: its first / second column half
+    if (CG2 && p.full_units >= 0 && w >= p.full_units) {
+      const long long e = w - p.full_units;
+      nh = 1 + (int)(e & 1);
+      w = p.full_units + (e >> 1);
+    }
     long long batch = w / units_per_batch;
     int r = (int)(w - batch * units_per_batch);
     m_blk = r % p.num_m_blocks;
@@ -198,11 +210,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (long long w = unit0; w < p.total_units; w += unit_stride) {
-        int m_blk, n_blk, split, h, b, kb0, kb1;
-        decode(w, m_blk, n_blk, split, h, b);
+        int m_blk, n_blk, split, h, b, kb0, kb1, nh;
+        decode(w, m_blk, n_blk, split, h, b, nh);
         k_range(m_blk, n_blk, split, kb0, kb1);
-        // this CTA's 128 rows of A and its share of the B tile
-        const int m0 = m_blk * M_TILE + (int)rank * BLOCK_M, n0 = n_blk * BLOCK_N + (int)rank * Cfg::B_ROWS;
+        // this CTA's 128 rows of A and its share of the B tile (a half-width unit uses the first B_ROWS / 2 rows of the box)
+        const int m0 = m_blk * M_TILE + (int)rank * BLOCK_M, n0 = ncol0(n_blk, nh) + (int)rank * (nh ? Cfg::B_ROWS / 2 : Cfg::B_ROWS);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_gen + stage * Cfg::STAGE_BYTES;
@@ -256,16 +268,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(M_TILE, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_full = make_idesc_bf16(M_TILE, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_half = make_idesc_bf16(M_TILE, BLOCK_N / 2, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (long long w = unit0; w < p.total_units; w += unit_stride) {
-        int m_blk, n_blk, split, h, b, kb0, kb1;
-        decode(w, m_blk, n_blk, split, h, b);
+        int m_blk, n_blk, split, h, b, kb0, kb1, nh;
+        decode(w, m_blk, n_blk, split, h, b, nh);
         k_range(m_blk, n_blk, split, kb0, kb1);
         if (kb1 <= kb0) continue;  // nothing to accumulate; the epilogue skips this unit as well
+        const uint32_t idesc = nh ? idesc_half : idesc_full;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -329,10 +343,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (tma_x) tma_prefetch_desc(&tmap_x);
     }
     for (long long w = unit0; w < p.total_units; w += unit_stride) {
-      int m_blk, n_blk, split, h, b, kb0, kb1;
-      decode(w, m_blk, n_blk, split, h, b);
+      int m_blk, n_blk, split, h, b, kb0, kb1, nh;
+      decode(w, m_blk, n_blk, split, h, b, nh);
       k_range(m_blk, n_blk, split, kb0, kb1);
       if (kb1 <= kb0) continue;
+      const int nc0 = ncol0(n_blk, nh);                         // first column of this unit
+      const int chw = nh ? CH_PER_WARP / 2 : CH_PER_WARP;       // 32-column chunks per epilogue warp
       const int row0w = m_blk * M_TILE + (int)rank * BLOCK_M + quad * 32;   // first row of this warp's 32-row block
       const int row = row0w + lane;
       const bool row_ok = row < p.M;
@@ -344,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // per chunk sit on the epilogue's critical path)
       asm volatile("bar.sync 1, 256;" ::: "memory");   // every warp is done with the previous tile's bias
       for (int i = etid; i < BLOCK_N; i += NUM_EPI_WARPS * 32) {
-        const int col = n_blk * BLOCK_N + i;
+        const int col = nc0 + i;
         s_bias[i] = (p.bias != nullptr && first_split && col < p.N) ? __ldg(p.bias + col) : 0.f;
       }
       // Global operands of the epilogue (residual rows, gelu' / aux operand) are fetched one 32-column chunk ahead -
@@ -358,7 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const __nv_bfloat16* aux_row = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux;
       const __nv_bfloat16* pre_row = want_aux ? aux_row : res_row;
       auto issue_loads = [&](int chi, uint4 (&rr)[4]) {
-        const int c0 = n_blk * BLOCK_N + (half * CH_PER_WARP + chi) * 32;
+        const int c0 = nc0 + (half * chw + chi) * 32;
         if (pre_tma) {
           if (lane == 0 && c0 < p.N) {
             mbar_expect_tx(ld_bar, 2048);
@@ -399,10 +415,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
-      for (int chi = 0; chi < CH_PER_WARP; ++chi) {
-        const int ch = half * CH_PER_WARP + chi;
+      for (int chi = 0; chi < chw; ++chi) {
+        const int ch = half * chw + chi;
         uint32_t v[32];
-        const int col0 = n_blk * BLOCK_N + ch * 32;
+        const int col0 = nc0 + ch * 32;
         if (col0 >= p.N || row0w >= p.M) break;       // warp-uniform: nothing of this chunk (or any later one) exists
         const bool full = (col0 + 32 <= p.N);
         bool pf_res = want_res && full, pf_aux = want_aux && full;
@@ -414,11 +430,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 4; ++g) rpre[g] = *reinterpret_cast<const uint4*>(ld_buf + lane * 64 + ((g ^ sw) << 4));
           __syncwarp();                               // every lane has read the slot: the next box may land in it
-          if (chi + 1 < CH_PER_WARP) issue_loads(chi + 1, npre);
+          if (chi + 1 < chw) issue_loads(chi + 1, npre);
           // out-of-range rows / columns of the box are zero-filled: use the staged values whenever they are requested
           pf_aux = (p.tma_pre == 2);
           pf_res = (p.tma_pre == 1) && first_split;
-        } else if (chi + 1 < CH_PER_WARP) {
+        } else if (chi + 1 < chw) {
           issue_loads(chi + 1, npre);
         }
         tmem_ld_wait();
@@ -812,6 +828,16 @@ extern "C" int pb_gemm_bf16(const pb_gemm_desc* d, void* stream_) {
   if ((d->flags & PB_GEMM_GELU) && kp.split_k > 1) return pb_set_error("pb_gemm_bf16: GELU with split_k");
   kp.batch_h = nh; kp.batch_b = nb;
   kp.total_units = (long long)kp.num_m_blocks * kp.num_n_blocks * kp.split_k * nh * nb;
+  kp.full_units = -1;
+  static const int tail_env = getenv("PIANOBART_B200_TAIL_SPLIT") ? atoi(getenv("PIANOBART_B200_TAIL_SPLIT")) : 1;
+  if (cg2 && tail_env && kp.split_k == 1 && nh * nb == 1 && !d->causal) {
+    const long long slots = pb_num_sms() / 2, T = kp.total_units;
+    const long long tail = T % slots;
+    if (T > slots && tail > 0 && 2 * tail <= slots) {
+      kp.full_units = (int)(T - tail);
+      kp.total_units = kp.full_units + 2 * tail;
+    }
+  }
   kp.c = d->c; kp.ldc = d->ldc; kp.c_stride_h = d->c_stride_h; kp.c_stride_b = d->c_stride_b;
   kp.bias = d->bias;
   kp.residual = d->residual; kp.ldr = d->ldr; kp.r_stride_h = d->r_stride_h; kp.r_stride_b = d->r_stride_b;

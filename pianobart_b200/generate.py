@@ -194,8 +194,8 @@ class Generator:
                               bias=self._Pf(ca + '.bkv'), name='kv_c%d' % l)
             self.prefill._add('kv_relayout', self.lib.pb_decode_kv_relayout, P(E._ptr(self.cross_kv[l])),
                               P(E._ptr(self.cross_k_r[l])), P(E._ptr(self.cross_v_r[l])), Se)
-        self.ll = dict(raw0=zw(d // 2), raw1=zw(d // 2), raw2=zw(d // 2), qkv=zw(3 * d // 2), qc=zw(d // 2), ob=zw(d // 2),
-                       f1=zw(F // 2), part=zw(8 * 18 * 132), logits_ll=zw(E.VOCAB), tok_ll=zw(8))
+        self.ll = dict(raw0=zw(2 * d), raw1=zw(2 * d), raw2=zw(2 * d), qkv=zw(6 * d), qc=zw(2 * d), ob=zw(2 * d),
+                       f1=zw(2 * F), part=zw(8 * 18 * 132), logits_ll=zw(E.VOCAB), tok_ll=zw(8))
         self.epoch = torch.zeros(1, device=dev, dtype=torch.int32)
         self.err_flag = torch.zeros(1, device=dev, dtype=torch.int32)
         D = L.DecodePersistDesc()

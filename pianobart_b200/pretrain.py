@@ -243,6 +243,11 @@ class PlanPrefetcher:
     def __init__(self, data_iter, mask_percent, rank=0, world=1, depth=2):
         self.it, self.mask_percent, self.rank, self.world = data_iter, mask_percent, rank, world
         self.q = queue.Queue(maxsize=depth)
+        # The plan generator is pure Python: while it runs it holds the GIL, and the trainer thread returning from its
+        # per-step device synchronisation would wait up to one interpreter switch interval (5 ms by default = 15 % of a
+        # 31 ms step, measured) before it can launch the next step.  A short interval bounds that bubble to ~0.2 ms.
+        self._old_switch = sys.getswitchinterval()
+        sys.setswitchinterval(min(self._old_switch, 2e-4))
         self.t = threading.Thread(target=self._work, daemon=True)
         self.t.start()
 
@@ -260,6 +265,8 @@ class PlanPrefetcher:
             self.q.put(None)
         except BaseException as e:     # surfaced in the consumer thread
             self.q.put(e)
+        finally:
+            sys.setswitchinterval(self._old_switch)
 
     def __iter__(self):
         while True:

@@ -109,6 +109,34 @@ def test_gemm_tc_epilogues_and_splitk():
 
 
 
+@pytest.mark.parametrize('b_mn,N,K', [(0, 768, 512), (1, 1024, 320), (0, 1280, 256)])
+def test_gemm_tc_tail_split_units(b_mn, N, K):
+    """cta_group::2 persistent grid with a partial last wave: the left-over 256 x 256 tiles are issued as two 256 x 128 units
+    (runtime UMMA N = 128 on the same stages).  M = 8192 gives 32 x {3, 4, 5} tiles on 74 pair slots (tails 22, 54 -> not
+    split, 12); bias + residual epilogue through the TMA path; against torch fp32."""
+    L, lib = _lib()
+    dev = 'cuda:0'
+    torch.manual_seed(7)
+    M = 8192
+    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device=dev) * 0.1).bfloat16()
+    w_st = W.t().contiguous() if b_mn else W
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev).bfloat16()
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    d = L.GemmDesc()
+    d.a, d.b, d.c, d.bias, d.residual = A.data_ptr(), w_st.data_ptr(), out.data_ptr(), bias.data_ptr(), res.data_ptr()
+    d.M, d.N, d.K, d.lda, d.ldb, d.ldc, d.ldr = M, N, K, K, (N if b_mn else K), N, N
+    d.b_mn_major = b_mn
+    d.alpha, d.flags, d.split_k = 1.0, 0, 1
+    L.check(lib.pb_gemm_bf16(C.byref(d), L.stream_ptr()), 'gemm')
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias + res.float()
+    assert _rel(out.float().cpu(), ref.cpu()) < 1e-2
+    # every tile / unit was written (no stale zeros anywhere)
+    assert (out.float().abs().sum(0) > 0).all() and (out.float().abs().sum(1) > 0).all()
+
+
 # --------------------------------------------------------------------------- fused attention vs torch fp32
 @pytest.mark.parametrize('B,H,Sq,Sk,causal,pad,fused', [
     (1, 1, 128, 128, 0, 0, True),      # single tile

@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-for f in 0; do
-( DBG_FLAGS=$f timeout 300 python tools/gpu_decode_trace.py ) > gpurun_out/r2_decode_trace_f$f.log 2>&1
-echo "== DBG_FLAGS=$f"; cat gpurun_out/r2_decode_trace_f$f.log | head -60
-done
+( timeout 600 python -m pytest tests/test_gpu_generate.py -q -x -k "default or loop" 2>&1 | tail -5 )
+( DBG_FLAGS=0 timeout 300 python tools/gpu_decode_trace.py ) > gpurun_out/r2_decode_trace_f0.log 2>&1
+cat gpurun_out/r2_decode_trace_f0.log | head -30
