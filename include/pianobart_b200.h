@@ -130,6 +130,23 @@ int pb_octuple_embed_fwd(const void* ids, int ids_int64, const void* table, void
 int pb_octuple_embed_bwd(const void* ids, int ids_int64, const void* dx, float* dtable, long long M,
                          const int* n_tokens_host, float scale, int dtype, void* stream);
 
+/* Fused front end (PianoBart.py:60-71 + modeling_bart.py:521-526 / 649-655) - the concatenated embedding [M,2048] never
+ * exists: table_proj [1280, d] holds T[off_a + r] = 16 E_a[r] W_a^T (in_linear restricted to attribute a's 256 columns,
+ * tabulated once per step by 8 small GEMMs), and per token
+ *   y0[m] = sum_a T[off_a + ids[m,a]] + bias + pos_rows[m % S]          (pre-LayerNorm sum, kept for backward)
+ *   h0[m] = dropout(LayerNorm(y0[m]; gamma, beta))                       (out_site as in pb_layernorm_fwd_drop)
+ * d <= 2048 (bf16) / 1024 (fp32), multiple of the 16-byte pack.  pos_rows points at row 2 of the learned position table. */
+typedef struct pb_drop_site pb_drop_site;
+int pb_octuple_front_fwd(const void* ids, int ids_int64, const void* table_proj, const float* bias, const void* pos_rows,
+                         int S, const float* gamma, const float* beta, void* y0, void* h0, float* mean, float* rstd,
+                         long long M, int d, const int* n_tokens_host, float eps, const pb_drop_site* out_site, int dtype,
+                         int* err_flag, void* stream);
+/* one-hot rows of the Octuple ids: out[m, off_a + ids[m,a]] = 1 (a = 0..7), 0 elsewhere; out [M, sum(n_tokens)] in `dtype`.
+ * Backward of the fused front end: G = onehot^T dy0 as one GEMM replaces the scatter-add of pb_octuple_embed_bwd. */
+int pb_octuple_onehot(const void* ids, int ids_int64, void* out, long long M, const int* n_tokens_host, int dtype, void* stream);
+/* stream-ordered memset(ptr, 0, bytes) */
+int pb_fill_zero(void* ptr, long long bytes, void* stream);
+
 /* ------------------------------------------------------------------ LayerNorm (HF BartEncoder/DecoderLayer
  * self_attn_layer_norm / encoder_attn_layer_norm / final_layer_norm / layernorm_embedding, eps 1e-5)
  * mean/rstd: [M] fp32 saved for backward.  d % 8 == 0 (bf16) / % 4 (fp32), d <= 2048 / 1024. */
@@ -138,11 +155,11 @@ int pb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void*
 /* dropout sites (see pb_gemm_desc): `out` site masks the LayerNorm OUTPUT (layernorm_embedding -> dropout);
  * for backward, `in` site masks the incoming dy the same way, `out` site produces the second tensor dx_drop =
  * mask(dx) (gradient of the dropped-out Linear output feeding this LayerNorm) and dbias then sums dx_drop. */
-typedef struct pb_drop_site {
+struct pb_drop_site {
   const unsigned long long* seed; /* NULL = disabled */
   unsigned int op, thresh;
   float scale;
-} pb_drop_site;
+};
 int pb_layernorm_fwd_drop(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                           long long M, int d, float eps, const pb_drop_site* out_site, int dtype, void* stream);
 int pb_layernorm_bwd_drop(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,

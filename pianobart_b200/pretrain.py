@@ -110,12 +110,14 @@ class PretrainStep:
         self.graph = pb._graph(B, S, S, True, True, dropout)
         M = B * S
         self.M = M
-        # pinned host staging + device inputs
-        self.h_ori = torch.empty(B, S, 8, dtype=torch.int16).pin_memory()
-        self.h_src = torch.empty(B, S, dtype=torch.int32).pin_memory()
-        self.h_loss = torch.empty(B, S, dtype=torch.uint8).pin_memory()
-        self.h_mode = torch.empty(B, dtype=torch.int32).pin_memory()
-        self.h_rand = torch.zeros(max(1, M), 8, dtype=torch.int32).pin_memory()
+        # pinned host staging (two sets: the trainer stages batch i+1 while the copies of batch i may still be queued)
+        # + device inputs
+        self._stage = [dict(ori=torch.empty(B, S, 8, dtype=torch.int16).pin_memory(),
+                            src=torch.empty(B, S, dtype=torch.int32).pin_memory(),
+                            loss=torch.empty(B, S, dtype=torch.uint8).pin_memory(),
+                            mode=torch.empty(B, dtype=torch.int32).pin_memory(),
+                            rand=torch.zeros(max(1, M), 8, dtype=torch.int32).pin_memory()) for _ in range(2)]
+        self._stage_i = 0
         self.d_ori = torch.empty(B, S, 8, dtype=torch.int16, device=dev)
         self.d_src = torch.empty(B, S, dtype=torch.int32, device=dev)
         self.d_loss = torch.empty(B, S, dtype=torch.uint8, device=dev)
@@ -147,21 +149,24 @@ class PretrainStep:
         ori = ori_batch.numpy() if isinstance(ori_batch, torch.Tensor) else np.asarray(ori_batch)
         if plan is None:
             plan = noising.make_plan(ori, self.S, self.mask_percent, choices)
-        self.h_ori.numpy()[...] = ori
-        self.h_src.numpy()[...] = plan.src
-        self.h_loss.numpy()[...] = plan.loss
-        self.h_mode.numpy()[...] = plan.loss_mode
+        h = self._stage[self._stage_i]
+        self._stage_i ^= 1
+        h['ori'].numpy()[...] = ori
+        h['src'].numpy()[...] = plan.src
+        h['loss'].numpy()[...] = plan.loss
+        h['mode'].numpy()[...] = plan.loss_mode
         nr = len(plan.rand_tok)
         if nr:
-            self.h_rand.numpy()[:nr] = np.asarray(plan.rand_tok, dtype=np.int32)
-        self.d_ori.copy_(self.h_ori, non_blocking=True)
-        self.d_src.copy_(self.h_src, non_blocking=True)
-        self.d_loss.copy_(self.h_loss, non_blocking=True)
-        self.d_mode.copy_(self.h_mode, non_blocking=True)
+            h['rand'].numpy()[:nr] = np.asarray(plan.rand_tok, dtype=np.int32)
+        # stream-ordered: these copies run after every kernel already queued, i.e. after the previous step has consumed
+        # the device input buffers
+        self.d_ori.copy_(h['ori'], non_blocking=True)
+        self.d_src.copy_(h['src'], non_blocking=True)
+        self.d_loss.copy_(h['loss'], non_blocking=True)
+        self.d_mode.copy_(h['mode'], non_blocking=True)
         if nr:
-            self.d_rand[:nr].copy_(self.h_rand[:nr], non_blocking=True)
-        self.h2d_bytes = (self.h_ori.numel() * 2 + self.h_src.numel() * 4 + self.h_loss.numel() + self.h_mode.numel() * 4
-                          + nr * 32)
+            self.d_rand[:nr].copy_(h['rand'][:nr], non_blocking=True)
+        self.h2d_bytes = (h['ori'].numel() * 2 + h['src'].numel() * 4 + h['loss'].numel() + h['mode'].numel() * 4 + nr * 32)
         return plan
 
     def noise(self):
@@ -366,12 +371,23 @@ class Pretrainer:
 
     def iteration(self, training_data, max_seq_len, train=True):
         total_acc, total_losses, nb = np.zeros(8), 0.0, 0
-        for ori_seq_batch, plan in self._batches(training_data):
-            B, S = ori_seq_batch.shape[0], ori_seq_batch.shape[1]
-            st = self._step(B, S)
-            st.upload(ori_seq_batch, plan=plan)
+        it = self._batches(training_data)
+
+        def stage(item):
+            """Host -> pinned -> device copies of one batch, queued behind whatever the stream is already running."""
+            if item is None:
+                return None
+            ori, plan = item
+            st = self._step(ori.shape[0], ori.shape[1])
+            st.upload(ori, plan=plan)
+            return st
+        st = stage(next(it, None))
+        while st is not None:
             st.noise()
             st.run(train=train)
+            # one step ahead: the next batch (its plan was drawn by the prefetch thread) is staged and its H2D copies
+            # are queued while the GPU still executes this step; only then the step's scalars are read back (sync)
+            nxt = stage(next(it, None))
             total, losses, accs = st.fetch_stats()
             if self.verbose:
                 sys.stdout.write('Loss: {:06f} | loss: {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}\n'.format(total, *losses))
@@ -379,6 +395,7 @@ class Pretrainer:
             total_losses += total
             total_acc += accs
             nb += 1
+            st = nxt
         nb = max(nb, 1)
         return round(total_losses / nb, 3), [round(float(x) / nb, 3) for x in total_acc]
 
