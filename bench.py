@@ -246,8 +246,9 @@ def decode_bench(lm, pb, dev, peaks, steps=192, warmup=16, batches=(1, 64)):
         ach = byts / (ms / 1e3) / 1e9
         out['batch%d' % B] = {'tokens_per_s': B * steps / (ms / 1e3), 'us_per_step': ms / steps * 1e3,
                               'steps': steps, 'launches': launches,
-                              'kernel': 'decode_persist_kernel (one cooperative launch)' if getattr(gen, 'persist', False)
-                              else 'CUDA graph of per-op kernels',
+                              'kernel': ('decode_persist_kernel (one cooperative launch)' if getattr(gen, 'persist', False) else
+                                         'decode_batch_kernel (one cooperative launch)' if getattr(gen, 'persist_batch', False)
+                                         else 'CUDA graph of per-op kernels'),
                               'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                                            'frac': ach / peaks['hbm_gbs'], 'algorithmic_bytes_per_step': byts / steps}}
         del gen

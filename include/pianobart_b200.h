@@ -333,6 +333,37 @@ int pb_decode_persist_smem_bytes(void);
 /* cross-attention K/V of one layer: projection layout [S_enc, 2d] (K | V, bf16) -> split-major cache layout */
 int pb_decode_kv_relayout(const void* kv, void* k_out, void* v_out, int S_enc, void* stream);
 
+/* ------------------------------------------------------------------ persistent whole-step decode (batch 64)
+ * Same role as pb_decode_persist_run for a batch of 64 sequences (csrc/decode_batch.cu): one cooperative launch generates
+ * n_steps tokens per sequence; projections on mma.sync tiles with the weights streamed ahead through a shared-memory ring,
+ * LayerNorm / bias / GELU / residual fused, (sequence, head) attention units streaming their K / V from caches laid out
+ * [sequence][head][key][128] (bf16), sampler and stop rule in the last phases; phases are separated by grid barriers.
+ * All activation buffers are bf16 [64, width]; `layer[i].self_k/self_v` are [64][8][S_max][128], `cross_k/cross_v`
+ * [64][8][S_enc][128] (pb_decode_kv_relayout_batch). */
+typedef struct pb_decode_batch_desc {
+  pb_decode_layer layer[PB_DECODE_MAX_LAYERS];
+  int n_layers, S_enc, S_max, B;
+  const void* emb_table; const void* w_in; const float* b_in; const void* pos_table;
+  const float* lne_g; const float* lne_b; const void* w_heads; const float* b_heads;
+  const uint8_t* enc_keep;                             /* [64, S_enc] or NULL                                           */
+  int* t_dev; int* cur_tok; int* result; int* sampled; int* done; int* n_written;   /* as for pb_decode_sample / _advance */
+  const double* uniforms; const int* forced;           /* [64, S_max, 8]; forced may be NULL                            */
+  float* logits;                                       /* [64, 1280] fp32: logits of the last executed step             */
+  void* xemb;                                          /* [64, 2048]                                                    */
+  void* raw0; void* raw1; void* raw2; void* hn;        /* [64, d] each                                                  */
+  void* qkv;                                           /* [64, 3d]                                                      */
+  void* qc; void* ob;                                  /* [64, d] each                                                  */
+  void* f1;                                            /* [64, F]                                                       */
+  float* stats;                                        /* [3][64][2] fp32, zero-initialised once: LayerNorm row statistics  */
+  unsigned int* barrier;                               /* grid-barrier counter (reset by every launch)                  */
+  int* error_flag;
+  long long* trace;                                    /* developer hook (NULL in production): clock64 before / after every
+                                                          grid barrier of the launch's last token, [gridDim][2 * 80]     */
+} pb_decode_batch_desc;
+int pb_decode_batch_run(const pb_decode_batch_desc* d, int n_steps, const int* seg_sizes_host, const float* temp_host,
+                        const float* top_p_host, const int* pad_host, void* stream);
+int pb_decode_kv_relayout_batch(const void* kv, void* k_out, void* v_out, int B, int S_enc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

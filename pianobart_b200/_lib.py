@@ -72,6 +72,15 @@ class DecodePersistDesc(C.Structure):
                 [('dbg_flags', C.c_int)])
 
 
+class DecodeBatchDesc(C.Structure):
+    """include/pianobart_b200.h: pb_decode_batch_desc"""
+    _fields_ = ([('layer', DecodeLayer * 8), ('n_layers', C.c_int), ('S_enc', C.c_int), ('S_max', C.c_int), ('B', C.c_int)] +
+                [(n, C.c_void_p) for n in (
+                    'emb_table', 'w_in', 'b_in', 'pos_table', 'lne_g', 'lne_b', 'w_heads', 'b_heads', 'enc_keep',
+                    't_dev', 'cur_tok', 'result', 'sampled', 'done', 'n_written', 'uniforms', 'forced', 'logits',
+                    'xemb', 'raw0', 'raw1', 'raw2', 'hn', 'qkv', 'qc', 'ob', 'f1', 'stats', 'barrier', 'error_flag', 'trace')])
+
+
 class PBError(RuntimeError):
     pass
 

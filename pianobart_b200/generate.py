@@ -60,12 +60,17 @@ class Generator:
         ns = (max(S, S_enc) + 127) // 128
         self.attn_ws = z(B * H * ns * (self.hd + 2), dt=f32)
         self.attn_tickets = z(B * H, dt=i32)
-        self.self_cache = [z(B, S, 2 * d) for _ in range(lay.dec_layers)]
+        self.self_cache = None      # (allocated below only for the per-op paths)
         self.cross_kv = [z(B * S_enc, 2 * d) for _ in range(lay.dec_layers)]
         self.enc_graph = pb._graph(B, S_enc, 0, False, False, 0.0)  # no dropout (demo.py:149-150 behaviour)
         # batch 1, default geometry: one persistent cooperative kernel generates many tokens per launch
-        self.persist = (B == 1 and not force_gemm and d == 1024 and F == 2048 and H == 8 and 1 <= lay.dec_layers <= 8
-                        and max(self.S, S_enc) <= 18 * 57 and os.environ.get('PIANOBART_B200_DECODE_PERSIST', '1') != '0')
+        default_geom = (d == 1024 and F == 2048 and H == 8 and 1 <= lay.dec_layers <= 8 and max(self.S, S_enc) <= 18 * 57
+                        and not force_gemm and os.environ.get('PIANOBART_B200_DECODE_PERSIST', '1') != '0')
+        self.persist = default_geom and B == 1
+        # batch 64, default geometry: the batched persistent kernel (csrc/decode_batch.cu)
+        self.persist_batch = default_geom and B == 64
+        if not (self.persist or self.persist_batch):
+            self.self_cache = [z(B, S, 2 * d) for _ in range(lay.dec_layers)]
         self.ntok_arr = (C.c_int * 8)(*E.N_TOKENS)
         self.pad_arr = (C.c_int * 8)(*[int(x) for x in pb.pad_word_np])
         self.temp_arr = (C.c_float * 8)(*[float(x) for x in SAMPLE_T])
@@ -199,7 +204,57 @@ class Generator:
         self.epoch = torch.zeros(1, device=dev, dtype=torch.int32)
         self.err_flag = torch.zeros(1, device=dev, dtype=torch.int32)
         D = L.DecodePersistDesc()
+        self._fill_layers(D)
+        D.n_layers, D.S_enc, D.S_max, D.stop_when_done = nl, Se, S, 0
+        self._fill_common(D)
+        D.enc_keep = E._ptr(eg.enc_keep)
+        D.logits_out = E._ptr(self.logits)
+        for k, t in self.ll.items():
+            setattr(D, k, E._ptr(t))
+        D.epoch, D.error_flag = E._ptr(self.epoch), E._ptr(self.err_flag)
+        self.pdesc = D
+        self.launches_per_step = 1
+        self._steps_issued = 0
+
+    def _build_persist_batch(self):
+        """Batch 64: csrc/decode_batch.cu.  Prefill = cross-attention K/V GEMMs + relayout to [seq][head][key][128]."""
+        pb, lay = self.pb, self.pb.layout
+        B, d, F, Se, S = self.B, self.d, self.F, self.Se, self.S
+        eg = self.enc_graph
+        P = C.c_void_p
+        dev = self.dev
+        zb = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bfloat16)
+        nl = lay.dec_layers
+        self.self_k_r = [zb(B, 8, S, 128) for _ in range(nl)]
+        self.self_v_r = [zb(B, 8, S, 128) for _ in range(nl)]
+        self.cross_k_r = [zb(B, 8, Se, 128) for _ in range(nl)]
+        self.cross_v_r = [zb(B, 8, Se, 128) for _ in range(nl)]
         for l in range(nl):
+            ca = 'bart.decoder.layers.%d.encoder_attn' % l
+            self.prefill.gemm(E._ptr(eg.enc_out), self._W(ca + '.wkv'), E._ptr(self.cross_kv[l]), B * Se, 2 * d, d, d, d, 2 * d,
+                              bias=self._Pf(ca + '.bkv'), name='kv_c%d' % l)
+            self.prefill._add('kv_relayout', self.lib.pb_decode_kv_relayout_batch, P(E._ptr(self.cross_kv[l])),
+                              P(E._ptr(self.cross_k_r[l])), P(E._ptr(self.cross_v_r[l])), B, Se)
+        self.act = dict(xemb=zb(B, 2048), raw0=zb(B, d), raw1=zb(B, d), raw2=zb(B, d), hn=zb(B, d), qkv=zb(B, 3 * d),
+                        qc=zb(B, d), ob=zb(B, d), f1=zb(B, F))
+        self.barrier = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.err_flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.ln_stats = torch.zeros(3 * 64 * 2, device=dev, dtype=torch.float32)
+        D = L.DecodeBatchDesc()
+        self._fill_layers(D)
+        D.n_layers, D.S_enc, D.S_max, D.B = nl, Se, S, B
+        self._fill_common(D)
+        D.enc_keep = E._ptr(eg.enc_keep)
+        D.logits = E._ptr(self.logits)
+        for k, t in self.act.items():
+            setattr(D, k, E._ptr(t))
+        D.barrier, D.error_flag, D.stats = E._ptr(self.barrier), E._ptr(self.err_flag), E._ptr(self.ln_stats)
+        self.pdesc = D
+        self.launches_per_step = 1
+        self._steps_issued = 0
+
+    def _fill_layers(self, D):
+        for l in range(self.pb.layout.dec_layers):
             lp = 'bart.decoder.layers.%d' % l
             sa, ca = lp + '.self_attn', lp + '.encoder_attn'
             Ld = D.layer[l]
@@ -214,24 +269,19 @@ class Generator:
             Ld.ln3_g, Ld.ln3_b = self._Pf(lp + '.final_layer_norm.weight'), self._Pf(lp + '.final_layer_norm.bias')
             Ld.self_k, Ld.self_v = E._ptr(self.self_k_r[l]), E._ptr(self.self_v_r[l])
             Ld.cross_k, Ld.cross_v = E._ptr(self.cross_k_r[l]), E._ptr(self.cross_v_r[l])
-        D.n_layers, D.S_enc, D.S_max, D.stop_when_done = nl, Se, S, 0
+
+    def _fill_common(self, D):
         D.emb_table = self._W('emb')
         D.w_in, D.b_in = self._W('encoder_linear.weight'), self._Pf('encoder_linear.bias')
         D.pos_table = self._W('bart.decoder.embed_positions.weight')
         D.lne_g, D.lne_b = self._Pf('bart.decoder.layernorm_embedding.weight'), self._Pf('bart.decoder.layernorm_embedding.bias')
         D.w_heads, D.b_heads = self._W('heads.w'), self._Pf('heads.b')
-        D.enc_keep = E._ptr(eg.enc_keep)
         D.t_dev, D.cur_tok, D.result, D.sampled = E._ptr(self.t_dev), E._ptr(self.cur_tok), E._ptr(self.result), E._ptr(self.sampled)
         D.done, D.n_written, D.uniforms, D.forced = E._ptr(self.done), E._ptr(self.n_written), E._ptr(self.uniforms), None
-        D.logits_out = E._ptr(self.logits)
-        for k, t in self.ll.items():
-            setattr(D, k, E._ptr(t))
-        D.epoch, D.error_flag = E._ptr(self.epoch), E._ptr(self.err_flag)
-        self.pdesc = D
-        self.launches_per_step = 1
-        self._steps_issued = 0
 
     def _build(self):
+        if self.persist_batch:
+            return self._build_persist_batch()
         if self.persist:
             return self._build_persist()
         if self.B <= 8 and not self.force_gemm:
@@ -290,10 +340,11 @@ class Generator:
     def _set_forced(self, forced):
         """Teacher forcing (parity tests): the token fed to step t+1 is forced[b, t] instead of the sampled one."""
         P = C.c_void_p
-        if self.persist:
+        if self.persist or self.persist_batch:
             self.forced = None if forced is None else forced.to(device=self.dev, dtype=torch.int32).contiguous()
             self.pdesc.forced = None if forced is None else E._ptr(self.forced)
-            self.pdesc.stop_when_done = 1 if forced is None else 0
+            if self.persist:
+                self.pdesc.stop_when_done = 1 if forced is None else 0
             return
         name, fn, args = self.step.ops[self._sample_idx]
         args = list(args)
@@ -326,16 +377,18 @@ class Generator:
         self.result.copy_(pad.view(1, 1, 8).expand_as(self.result))
         if uniforms is not None:
             self.uniforms.copy_(torch.as_tensor(uniforms, dtype=torch.float64).reshape(self.B, self.S, 8), non_blocking=True)
-        if self.persist:
+        if self.persist or self.persist_batch:
             self.err_flag.zero_()
             self._steps_issued = 0
+        if self.persist_batch:
+            self.ln_stats.zero_()
 
     def _run_persist(self, n):
         n = min(n, self.S - self._steps_issued)
         if n <= 0:
             return 0
-        L.check(self.lib.pb_decode_persist_run(C.byref(self.pdesc), n, self.ntok_arr, self.temp_arr, self.p_arr, self.pad_arr,
-                                               L.stream_ptr()), 'decode_persist')
+        fn = self.lib.pb_decode_batch_run if self.persist_batch else self.lib.pb_decode_persist_run
+        L.check(fn(C.byref(self.pdesc), n, self.ntok_arr, self.temp_arr, self.p_arr, self.pad_arr, L.stream_ptr()), 'decode_persist')
         self._steps_issued += n
         self.launches_per_step = 1.0 / n
         return 1
@@ -343,7 +396,7 @@ class Generator:
     def run_steps(self, n):
         """Runs n decode steps: one cooperative launch (batch 1, persistent kernel) or n CUDA-graph replays.
         Returns the number of library launches issued."""
-        if self.persist:
+        if self.persist or self.persist_batch:
             return self._run_persist(n)
         if not self.use_graph:
             for _ in range(n):
@@ -378,7 +431,7 @@ class Generator:
 
     def finish(self):
         torch.cuda.synchronize()
-        if self.persist and int(self.err_flag.item()) != 0:
+        if (self.persist or self.persist_batch) and int(self.err_flag.item()) != 0:
             raise L.PBError('decode_persist_kernel reported error %d' % int(self.err_flag.item()))
         return self.result.to(torch.int64), self.n_written.cpu().numpy(), self.done.cpu().numpy()
 
