@@ -270,6 +270,36 @@ int pb_decode_advance(const int* cur_tok, int* result, int* done, int* t_dev, in
 int pb_octuple_truncate(const void* ids, int ids_int64, long long* out, long long* len, int B, int S, const int* pad_host,
                         void* stream);
 
+/* ------------------------------------------------------------------ finetuning classifier heads (all fp32)
+ * SequenceClassification (model.py:128-143,195-218) and TokenClassification (model.py:236-272) around the backbone; the
+ * wide Linears (1024 -> 128 / 256, 4096 -> 256, 64 -> 1024) are pb_gemm_* calls, these are the remaining pieces.
+ * `act` folds the preceding activation into the operand: 0 none, 1 ReLU (nn.ReLU of both classifiers), 2 tanh
+ * (SelfAttention, model.py:141).  Backward entry points ACCUMULATE (+=) into dw / dbias / dtable and overwrite dx / da / dp. */
+/* nn.Dropout: y[i] = keep(site, i) ? x[i] * site->scale : 0 (same counter-based mask family as the backbone's sites);
+ * applied to the incoming gradient it is its own backward */
+int pb_dropout_apply(const float* x, float* y, long long n, const pb_drop_site* site, void* stream);
+/* y[m, c] = sum_k act(x[m, k]) w[c, k] + bias[c],  N <= 16 outputs (Linear(256, class_num), SelfAttention.ws2) */
+int pb_smalln_linear_fwd(const float* x, const float* w, const float* bias, float* y, long long M, int N, int K, int act,
+                         void* stream);
+/* dx[m, k] = act'(x[m, k]) sum_c dy[m, c] w[c, k] (dx may be NULL);  dw[c, k] += sum_m dy[m, c] act(x[m, k]);
+ * dbias[c] += sum_m dy[m, c] (may be NULL) */
+int pb_smalln_linear_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias, long long M,
+                         int N, int K, int act, void* stream);
+/* softmax over the SEQUENCE axis of a [B, S, R] tensor (model.py:142 softmax(dim=1); padding rows are not masked), R <= 8 */
+int pb_seq_softmax_fwd(const float* a, float* p, int B, int S, int R, void* stream);
+int pb_seq_softmax_bwd(const float* p, const float* dp, float* da, int B, int S, int R, void* stream);
+/* attention pooling (model.py:209 torch.bmm(attn_mat, x)): m[b, r, :] = sum_s p[b, s, r] x[b, s, :];
+ * backward: dx[b, s, :] = sum_r p[b, s, r] dm[b, r, :], dp[b, s, r] = x[b, s, :] . dm[b, r, :] */
+int pb_attn_pool_fwd(const float* p, const float* x, float* m, int B, int S, int R, int D, void* stream);
+int pb_attn_pool_bwd(const float* p, const float* x, const float* dm, float* dx, float* dp, int B, int S, int R, int D,
+                     void* stream);
+/* Embeddings.forward (PianoBart.py:15-16) for a small table: out[m, :] = table[ids[m], :] * scale (ids int64; an id outside
+ * [0, n_rows) sets *err_flag and yields a zero row);  backward: dtable[ids[m], :] += scale * dout[m, :], n_rows * d <= 12288 */
+int pb_rows_gather(const long long* ids, const float* table, float* out, long long M, int n_rows, int d, float scale,
+                   int* err_flag, void* stream);
+int pb_rows_scatter_add(const long long* ids, const float* dout, float* dtable, long long M, int n_rows, int d, float scale,
+                        void* stream);
+
 /* ------------------------------------------------------------------ persistent whole-step decode (batch 1)
  * Replaces the per-token loop body of PianoBartLM.forward(generate=True) (model.py:42-65) for the default model geometry
  * (d 1024, 8 heads x 128, ffn 2048, 1280-entry Octuple vocabulary): ONE cooperative launch generates `n_steps` tokens.

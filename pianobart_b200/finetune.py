@@ -1,9 +1,10 @@
 """Sequence- / token-classification finetuning, mirroring reference finetune.py (`FinetuneTrainer`, :75-274).
 
-The backbone forward/backward run on the kernel path through the autograd bridge (modules._BackboneFn); the small
-classifier heads (< 0.1 % of the FLOPs) and their loss are PyTorch.  The 174 M backbone parameters are
-updated by the fused HF-semantics AdamW kernel over the flat buffer (pretrain.FusedAdamW, clipping off); only the handful
-of head tensors go through the per-tensor HFAdamW below.  Data parallel: one process per GPU, gradients all-reduced (sum)
+The backbone forward/backward run on the kernel path through the autograd bridge (modules._BackboneFn); the classifier
+heads, the replacement decoder front end and the masked cross-entropy with its argmax / accuracy are library
+launches as well (heads.py, csrc/cls_heads.cu, pb_heads_ce).  The 174 M backbone parameters are updated by the fused
+HF-semantics AdamW kernel over the flat buffer (pretrain.FusedAdamW, clipping off); the handful of head tensors go through
+the same kernel, one launch per tensor (HFAdamW below).  Data parallel: one process per GPU, gradients all-reduced (sum)
 over NCCL with the loss normalised by the GLOBAL batch / mask count, so the summed gradient is the reference's full-batch
 gradient (the reference uses single-process nn.DataParallel, finetune.py:101-103).  Reference behaviour kept: TokenClassification is built
 with class_num+1 (finetune.py:98), velocity (class_num >= 5) feeds shifted labels through the replacement decoder front
@@ -11,7 +12,7 @@ end (:194-198), otherwise decoder ids = encoder ids (:211-212); loss = CE masked
 tasks, mean CE for sequence tasks (:125-132); optional L2-norm regulariser (:241-243); NO gradient clipping (:250);
 optimizer: HF-semantics AdamW(lr, weight_decay=0.01) over all parameters.
 """
-import copy
+import ctypes as C
 import shutil
 
 import numpy as np
@@ -19,37 +20,41 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from . import heads
 from .modules import SequenceClassification, TokenClassification
 from .pretrain import FusedAdamW
 
 
 class HFAdamW(torch.optim.Optimizer):
-    """transformers 4.29 `AdamW` semantics (eps added before bias correction, decay after the update with plain lr);
-    torch.optim.AdamW differs."""
+    """transformers 4.29 `AdamW` semantics (eps added before bias correction, decay after the update with plain lr;
+    torch.optim.AdamW differs) for the few tensors outside the backbone's flat buffer: one pb_adamw
+    launch per tensor, no clipping."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
     @torch.no_grad()
     def step(self):
+        lib, st_ptr = L.lib(), L.stream_ptr()
         for g in self.param_groups:
             b1, b2 = g['betas']
             for p in g['params']:
                 if p.grad is None:
                     continue
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise L.PBError('HFAdamW: parameters must be contiguous fp32 CUDA tensors (no CPU path)')
                 st = self.state[p]
                 if not st:
                     st['step'] = 0
                     st['exp_avg'] = torch.zeros_like(p)
                     st['exp_avg_sq'] = torch.zeros_like(p)
                 st['step'] += 1
-                st['exp_avg'].mul_(b1).add_(p.grad, alpha=1 - b1)
-                st['exp_avg_sq'].mul_(b2).addcmul_(p.grad, p.grad, value=1 - b2)
-                denom = st['exp_avg_sq'].sqrt().add_(g['eps'])
-                step_size = g['lr'] * (1 - b2 ** st['step']) ** 0.5 / (1 - b1 ** st['step'])
-                p.addcdiv_(st['exp_avg'], denom, value=-step_size)
-                if g['weight_decay'] > 0:
-                    p.add_(p, alpha=-g['lr'] * g['weight_decay'])
+                grad = p.grad.contiguous()
+                L.check(lib.pb_adamw(C.c_void_p(p.data_ptr()), C.c_void_p(st['exp_avg'].data_ptr()),
+                                     C.c_void_p(st['exp_avg_sq'].data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(None),
+                                     C.c_longlong(p.numel()), C.c_float(g['lr']), C.c_float(b1), C.c_float(b2),
+                                     C.c_float(g['eps']), C.c_float(g['weight_decay']), st['step'], C.c_void_p(None),
+                                     C.c_float(0.0), C.c_float(1.0), C.c_float(1.0), st_ptr), 'adamw')
 
 
 class FinetuneTrainer:
@@ -84,16 +89,22 @@ class FinetuneTrainer:
         self.optim_backbone = FusedAdamW(self.pianobart, lr=lr, weight_decay=0.01, max_grad_norm=0.0)
         self.optim = HFAdamW(head_params, lr=lr, weight_decay=0.01)
         self._head_params = head_params
-        self.loss_func = nn.CrossEntropyLoss(reduction='none')
         self.testset_shape = testset_shape if not error else (testset_shape[:-1] if testset_shape is not None else None)
         self.weight, self.error = weight, error
 
     def compute_loss(self, predict, target, loss_mask, seq):
-        loss = self.loss_func(predict, target)
+        """finetune.py:125-132 with the reference's argument layout (token tasks: predict is [B, C, S])."""
         if not seq:
-            loss = loss * loss_mask
-            return torch.sum(loss) / torch.sum(loss_mask)
-        return torch.sum(loss) / loss.shape[0]
+            predict = predict.permute(0, 2, 1)
+        return self._loss(predict, target, loss_mask, seq)[0]
+
+    def _loss(self, y_hat, y, attn, seq):
+        """-> (loss, #correct, argmax): masked CE / sum(mask) for token tasks, mean CE for sequence tasks - one pb_heads_ce pass"""
+        if seq:
+            return heads.masked_ce(y_hat, y, None)
+        M = y_hat.shape[0] * y_hat.shape[1]
+        loss, correct, am = heads.masked_ce(y_hat.reshape(M, -1), y.reshape(M), attn.reshape(M))
+        return loss, correct, am.view(y.shape)
 
     def train(self):
         self.model.train()
@@ -128,13 +139,9 @@ class FinetuneTrainer:
                     y_shift, attn_shift = x.clone(), attn.clone()
                 y_hat = self.model(input_ids_encoder=x, input_ids_decoder=y_shift, encoder_attention_mask=attn,
                                    decoder_attention_mask=attn_shift)
-            output = y_hat.argmax(-1)
-            if not seq:
-                correct, count = torch.sum((y == output).float() * attn), torch.sum(attn).item()
-                loss = self.compute_loss(y_hat.permute(0, 2, 1), y, attn, seq)
-            else:
-                correct, count = torch.sum((y == output).float()), y.shape[0]
-                loss = self.compute_loss(y_hat, y, attn, seq)
+            loss, correct, output = self._loss(y_hat, y, attn, seq)
+            output = output.long()
+            count = y.shape[0] if seq else torch.sum(attn).item()
             if self.world > 1:
                 # global normaliser: loss_r = (local sum) / (global count); the rank gradients then SUM to the full-batch one
                 import torch.distributed as dist

@@ -71,7 +71,8 @@ class Embeddings(nn.Module):
         self.d_model = d_model
 
     def forward(self, x):
-        return self.lut(x) * math.sqrt(self.d_model)
+        from . import heads
+        return heads.embed_rows(x, self.lut.weight, math.sqrt(self.d_model))     # pb_rows_gather / pb_rows_scatter_add
 
 
 class _BackboneFn(torch.autograd.Function):
@@ -321,9 +322,11 @@ class PianoBart(nn.Module):
         self._ensure_packed()
         dec_embeds = None
         if self.decoder_emb is not None and input_ids_decoder is not None:
-            # PianoBart.py:63-66,71: decoder stream = decoder_linear(decoder_emb(ids)); tiny (class_num x 64 table,
-            # 64 -> d projection), kept in PyTorch; the result enters the kernel path as decoder input embeddings
-            dec_embeds = self.decoder_linear(self.decoder_emb(input_ids_decoder))
+            # PianoBart.py:63-66,71: decoder stream = decoder_linear(decoder_emb(ids)) (class_num x 64 table, 64 -> d
+            # projection): gather kernel + GEMM (heads.py); the result enters the backbone plan as decoder input embeddings
+            from . import heads
+            lin = self.decoder_linear
+            dec_embeds = heads.linear(self.decoder_emb(input_ids_decoder), lin.weight, lin.bias, self.pb_dtype)
         B, Se = input_ids_encoder.shape[0], input_ids_encoder.shape[1]
         Sd = 0 if input_ids_decoder is None else input_ids_decoder.shape[1]
         if max(Se, Sd) + 2 > self.layout.max_pos + 2:
@@ -397,39 +400,61 @@ class PianoBartLM(nn.Module):
 
 
 class SelfAttention(nn.Module):
-    """model.py:128-143."""
+    """model.py:128-143: softmax over the sequence axis of ws2(tanh(ws1(h))), returned as [B, r, S]."""
 
     def __init__(self, input_dim, da, r):
         super().__init__()
         self.ws1 = nn.Linear(input_dim, da, bias=False)
         self.ws2 = nn.Linear(da, r, bias=False)
 
-    def forward(self, h):
-        attn_mat = torch.softmax(self.ws2(torch.tanh(self.ws1(h))), dim=1)
-        return attn_mat.permute(0, 2, 1)
+    def probs(self, h, pb_dtype):
+        """[B, S, r] attention weights: tcgen05 GEMM (ws1), tanh folded into the r-output projection (ws2), sequence softmax"""
+        from . import heads
+        a1 = heads.linear(h, self.ws1.weight, None, pb_dtype)
+        a2 = heads.linear(a1, self.ws2.weight, None, pb_dtype, act_in=heads.ACT_TANH)
+        return heads.seq_softmax(a2)
+
+    def forward(self, h, pb_dtype=None):
+        return self.probs(h, E.PB_BF16 if pb_dtype is None else pb_dtype).permute(0, 2, 1)
+
+
+def _classifier(seq, x, pb_dtype, training, seeds):
+    """nn.Sequential(Dropout(0.1), Linear(k, 256), ReLU, Linear(256, class_num)) on the kernel path (model.py:173-178,
+    244-249); the modules only hold the parameters (state_dict keys classifier.1.* / classifier.3.*)."""
+    from . import heads
+    drop, lin1, _, lin2 = seq[0], seq[1], seq[2], seq[3]
+    if lin2.out_features > heads.SMALL_N:
+        raise ValueError('pianobart_b200 classifier heads support class_num <= %d' % heads.SMALL_N)
+    x = heads.dropout(x, drop.p, training, seeds)
+    h1 = heads.linear(x, lin1.weight, lin1.bias, pb_dtype)
+    return heads.linear(h1, lin2.weight, lin2.bias, pb_dtype, act_in=heads.ACT_RELU)   # ReLU folded into the operand load
 
 
 class SequenceClassification(nn.Module):
-    """model.py:165-218: backbone called with decoder ids = encoder ids (model.py:204); the pooled head is
-    negligible arithmetic and stays in PyTorch for now."""
+    """model.py:165-218: backbone called with decoder ids = encoder ids (model.py:204), then the self-attentive pooled head
+    (K15) - every op a library launch (heads.py, csrc/cls_heads.cu)."""
 
     def __init__(self, pianobart, class_num, hs, da=128, r=4):
         super().__init__()
         self.pianobart = pianobart
         self.attention = SelfAttention(hs, da, r)
         self.classifier = nn.Sequential(nn.Dropout(0.1), nn.Linear(hs * r, 256), nn.ReLU(), nn.Linear(256, class_num))
+        self._seeds = None
 
     def forward(self, input_ids_encoder, encoder_attention_mask=None):
+        from . import heads
         x = self.pianobart(input_ids_encoder=input_ids_encoder, input_ids_decoder=input_ids_encoder,
                            encoder_attention_mask=encoder_attention_mask,
                            decoder_attention_mask=encoder_attention_mask).last_hidden_state
-        attn_mat = self.attention(x)
-        m = torch.bmm(attn_mat, x)
-        return self.classifier(m.view(m.size()[0], -1))
+        if self._seeds is None:
+            self._seeds = heads.DropSeeds(x.device)
+        dt = self.pianobart.pb_dtype
+        m = heads.attn_pool(self.attention.probs(x, dt), x)          # == torch.bmm(attn_mat, x), [B, r, hs]
+        return _classifier(self.classifier, m.reshape(m.shape[0], -1), dt, self.training, self._seeds)
 
 
 class TokenClassification(nn.Module):
-    """model.py:236-272."""
+    """model.py:236-272 (K16)."""
 
     def __init__(self, pianobart, class_num, hs, d_model=64):
         super().__init__()
@@ -438,8 +463,12 @@ class TokenClassification(nn.Module):
             self.pianobart.change_decoder_embedding(Embeddings(n_token=class_num, d_model=d_model),
                                                     nn.Linear(d_model, pianobart.bartConfig.d_model))
         self.classifier = nn.Sequential(nn.Dropout(0.1), nn.Linear(hs, 256), nn.ReLU(), nn.Linear(256, class_num))
+        self._seeds = None
 
     def forward(self, input_ids_encoder, input_ids_decoder, encoder_attention_mask=None, decoder_attention_mask=None):
+        from . import heads
         x = self.pianobart(input_ids_encoder, input_ids_decoder, encoder_attention_mask,
                            decoder_attention_mask).last_hidden_state
-        return self.classifier(x)
+        if self._seeds is None:
+            self._seeds = heads.DropSeeds(x.device)
+        return _classifier(self.classifier, x, self.pianobart.pb_dtype, self.training, self._seeds)
