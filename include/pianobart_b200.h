@@ -198,6 +198,13 @@ int pb_colsum(const void* x, float* out, long long M, int N, long long ld, int d
 int pb_heads_ce(const float* logits, const int* targets, const float* mask, const float* den, float* loss_num,
                 float* correct, void* dlogits, int* argmax_out, long long M, int nseg, const int* seg_sizes_host,
                 const float* weights_host, float grad_scale, int dtype, void* stream);
+/* The same computation FUSED with the heads' GEMM (north-star fusion 3; tcgen05, bf16): logits = h W^T + bias are
+ * accumulated in TMEM per 128-row tile and reduced there - they never reach HBM.  h bf16 [M, K] (row stride ldh), w bf16
+ * [sum(seg_sizes), K] (model.py:119-126, the eight Linear heads stacked), bias fp32; the other arguments as for pb_heads_ce.
+ * dlogits bf16 [M, sum(seg_sizes)] (NULL in evaluation).  K % 64 == 0, every segment 32..496 classes, sum % 8 == 0. */
+int pb_heads_ce_fused(const void* h, long long ldh, const void* w, const float* bias, const int* targets, const float* mask,
+                      const float* den, float* loss_num, float* correct, void* dlogits, int* argmax_out, long long M, int K,
+                      int nseg, const int* seg_sizes_host, const float* weights_host, float grad_scale, void* stream);
 /* den[s] += sum_m mask[m, s]   (pretrain.py:117 denominators) */
 int pb_mask_sums(const float* mask, float* den, long long M, int nseg, void* stream);
 

@@ -421,10 +421,10 @@ class BackboneGraph:
         self.Mo = Mo
         self.d_out = self.buf('d_out', Mo, d)  # gradient wrt last hidden state (input of backward)
 
-        if self.with_heads:
-            self.logits = self.buf('logits', Mo, VOCAB, dtype=torch.float32)
-            f.gemm(_ptr(self.out), self.W('heads.w'), _ptr(self.logits), Mo, VOCAB, d, d, d, VOCAB,
-                   bias=self.Pf('heads.b'), flags=L.PB_GEMM_OUT_F32, name='heads')
+        # (the heads GEMM lives in its own lazily built plan, heads_plan(): the fused heads + cross-entropy kernel of the
+        # training step never materialises the fp32 logits, only PianoBartLM.forward() / the fp32 mode do)
+        self._logits = None
+        self._heads_plan = None
 
         if bw is None:
             return
@@ -719,8 +719,28 @@ class BackboneGraph:
             else:
                 self.dec_keep.copy_((dec_keep.reshape(-1) != 0), non_blocking=True)
 
+    @property
+    def logits(self):
+        """fp32 logits [Mo, 1280] of the eight MLM heads (allocated on first use)"""
+        if self._logits is None:
+            self._logits = self.buf('logits', self.Mo, VOCAB, dtype=torch.float32)
+        return self._logits
+
+    def heads_plan(self):
+        """model.py:119-126 as one N = 1280 GEMM with bias into `logits`"""
+        if self._heads_plan is None:
+            d = self.d
+            hp = Plan(self.dtype)
+            hp.gemm(_ptr(self.out), self.W('heads.w'), _ptr(self.logits), self.Mo, VOCAB, d, d, d, VOCAB,
+                    bias=self.Pf('heads.b'), flags=L.PB_GEMM_OUT_F32, name='heads')
+            self._heads_plan = hp
+        return self._heads_plan
+
     def forward(self):
-        return self.fwd.run()
+        n = self.fwd.run()
+        if self.with_heads:
+            n += self.heads_plan().run()
+        return n
 
     def backward(self):
         return self.bwd.run()

@@ -108,6 +108,9 @@ class PretrainStep:
         self.dev = dev
         self.lib = L.lib()
         self.graph = pb._graph(B, S, S, True, True, dropout)
+        # north-star fusion 3 (bf16 mode): MLM heads + masked CE in one kernel (csrc/heads_ce_tc.cu)
+        self.fused_ce = (pb.pb_dtype == E.PB_BF16 and self.graph.d % 64 == 0
+                         and os.environ.get('PIANOBART_B200_FUSED_CE', '1') != '0')
         M = B * S
         self.M = M
         # pinned host staging (two sets: the trainer stages batch i+1 while the copies of batch i may still be queued)
@@ -200,11 +203,22 @@ class PretrainStep:
             import torch.distributed as dist
             dist.all_reduce(self.stats[16:24], group=self.pg)  # global denominators (pretrain.py:117 on the full batch)
         n = g.fwd.run(profile=profile)
-        L.check(lib.pb_heads_ce(P(g.logits.data_ptr()), P(self.targets.data_ptr()), P(self.loss_mask.data_ptr()),
-                                P(self.stats.data_ptr() + 64), P(self.stats.data_ptr()), P(self.stats.data_ptr() + 32),
-                                P(g.dlogits.data_ptr()) if train else P(None), P(None), C.c_longlong(M), 8, self.seg,
-                                self.w, C.c_float(self.grad_scale), pb.pb_dtype, s), 'heads_ce')
-        n += 2
+        if self.fused_ce:
+            # heads GEMM + masked CE + accuracy + dlogits in one tcgen05 kernel: the fp32 logits never reach HBM
+            L.check(lib.pb_heads_ce_fused(P(g.out.data_ptr()), C.c_longlong(g.d), P(g.W('heads.w')), P(g.Pf('heads.b')),
+                                          P(self.targets.data_ptr()), P(self.loss_mask.data_ptr()),
+                                          P(self.stats.data_ptr() + 64), P(self.stats.data_ptr()),
+                                          P(self.stats.data_ptr() + 32), P(g.dlogits.data_ptr()) if train else P(None),
+                                          P(None), C.c_longlong(M), g.d, 8, self.seg, self.w, C.c_float(self.grad_scale), s),
+                    'heads_ce_fused')
+            n += 1
+        else:
+            n += g.heads_plan().run(profile=profile)
+            L.check(lib.pb_heads_ce(P(g.logits.data_ptr()), P(self.targets.data_ptr()), P(self.loss_mask.data_ptr()),
+                                    P(self.stats.data_ptr() + 64), P(self.stats.data_ptr()), P(self.stats.data_ptr() + 32),
+                                    P(g.dlogits.data_ptr()) if train else P(None), P(None), C.c_longlong(M), 8, self.seg,
+                                    self.w, C.c_float(self.grad_scale), pb.pb_dtype, s), 'heads_ce')
+            n += 2
         if train:
             pb._grad.zero_()
             if self.world > 1:

@@ -168,3 +168,71 @@ def test_head_optimizer_matches_hf_adamw_semantics():
         ref = ref - ss * m / (np.sqrt(v) + 1e-6)
         ref = ref - 1e-3 * 0.01 * ref
     assert np.abs(p.detach().double().cpu().numpy() - ref).max() < 1e-6
+
+
+# ------------------------------------------------------------------ north-star fusion 3: MLM heads + masked CE in one kernel
+@pytest.mark.parametrize('M,K', [(16 * 1024, 1024), (300, 64), (128, 128), (1, 64)])
+def test_fused_heads_ce_matches_gemm_plus_ce_and_torch(M, K):
+    """pb_heads_ce_fused (logits only ever in TMEM) against (a) the unfused library path pb_gemm_bf16 + pb_heads_ce and
+    (b) torch fp32 cross-entropy on the same bf16 operands (model.py:119-126 + pretrain.py:112-118,163-189)."""
+    from pianobart_b200 import _lib as L, engine as E
+    lib = L.lib()
+    P = C.c_void_p
+    V, seg_sizes = E.VOCAB, E.N_TOKENS
+    g = torch.Generator().manual_seed(100 + M)
+    h = (torch.randn(M, K, generator=g) * 1.0).to(torch.bfloat16).cuda()
+    w = (torch.randn(V, K, generator=g) * (2.0 / K ** 0.5)).to(torch.bfloat16).cuda()
+    bias = (torch.randn(V, generator=g) * 0.5).cuda()
+    tg = torch.stack([torch.randint(0, n, (M,), generator=g) for n in seg_sizes], dim=1).to(torch.int32).cuda()
+    mk = (torch.rand(M, 8, generator=g) < 0.3).float().cuda()
+    if M > 4:
+        mk[3] = 0.0
+    den = torch.zeros(8, device='cuda')
+    L.check(lib.pb_mask_sums(P(mk.data_ptr()), P(den.data_ptr()), C.c_longlong(M), 8, L.stream_ptr()), 'mask_sums')
+    den.clamp_(min=1.0)
+    seg = (C.c_int * 8)(*seg_sizes)
+    wts = (C.c_float * 8)(262, 134, 262, 134, 38, 135, 55, 260)
+
+    loss_f, cor_f = torch.zeros(8, device='cuda'), torch.zeros(8, device='cuda')
+    dl_f = torch.full((M, V), 7.0, dtype=torch.bfloat16, device='cuda')
+    am_f = torch.full((M, 8), -1, dtype=torch.int32, device='cuda')
+    L.check(lib.pb_heads_ce_fused(P(h.data_ptr()), C.c_longlong(K), P(w.data_ptr()), P(bias.data_ptr()), P(tg.data_ptr()),
+                                  P(mk.data_ptr()), P(den.data_ptr()), P(loss_f.data_ptr()), P(cor_f.data_ptr()),
+                                  P(dl_f.data_ptr()), P(am_f.data_ptr()), C.c_longlong(M), K, 8, seg, wts, C.c_float(0.7),
+                                  L.stream_ptr()), 'heads_ce_fused')
+    # (a) unfused library path
+    logits = torch.empty(M, V, dtype=torch.float32, device='cuda')
+    plan = E.Plan(E.PB_BF16)
+    plan.gemm(h.data_ptr(), w.data_ptr(), logits.data_ptr(), M, V, K, K, K, V, bias=bias.data_ptr(), flags=L.PB_GEMM_OUT_F32)
+    plan.run()
+    loss_u, cor_u = torch.zeros(8, device='cuda'), torch.zeros(8, device='cuda')
+    dl_u = torch.empty(M, V, dtype=torch.bfloat16, device='cuda')
+    am_u = torch.empty(M, 8, dtype=torch.int32, device='cuda')
+    L.check(lib.pb_heads_ce(P(logits.data_ptr()), P(tg.data_ptr()), P(mk.data_ptr()), P(den.data_ptr()), P(loss_u.data_ptr()),
+                            P(cor_u.data_ptr()), P(dl_u.data_ptr()), P(am_u.data_ptr()), C.c_longlong(M), 8, seg, wts,
+                            C.c_float(0.7), E.PB_BF16, L.stream_ptr()), 'heads_ce')
+    torch.cuda.synchronize()
+    assert _rel(loss_f, loss_u) < 2e-5
+    assert float((am_f != am_u).float().mean()) < 1e-4          # (equal logits up to accumulation order: ties only)
+    assert float((cor_f - cor_u).abs().max()) <= max(2.0, 1e-4 * M)
+    d = (dl_f.float() - dl_u.float()).abs()
+    scale = dl_u.float().abs().max()
+    assert float(d.max()) <= 0.01 * float(scale) + 1e-12         # one bf16 rounding step of the largest entries
+    # (b) torch fp32 on the same operands
+    lg = (h.float() @ w.float().t() + bias).requires_grad_(True)
+    total = 0.0
+    off = 0
+    for s, n in enumerate(seg_sizes):
+        ce = F.cross_entropy(lg[:, off:off + n], tg[:, s].long(), reduction='none')
+        num = (ce * mk[:, s]).sum()
+        assert abs(float(loss_f[s]) - float(num)) <= 2e-3 * max(1.0, abs(float(num)))
+        total = total + num / den[s] * wts[s] / 1280.0 * 0.7
+        off += n
+    total.backward()
+    assert float((dl_f.float() - lg.grad).abs().max()) <= 0.01 * float(lg.grad.abs().max()) + 1e-12
+    # evaluation mode: no dlogits, same statistics
+    loss_e, cor_e = torch.zeros(8, device='cuda'), torch.zeros(8, device='cuda')
+    L.check(lib.pb_heads_ce_fused(P(h.data_ptr()), C.c_longlong(K), P(w.data_ptr()), P(bias.data_ptr()), P(tg.data_ptr()),
+                                  P(mk.data_ptr()), P(den.data_ptr()), P(loss_e.data_ptr()), P(cor_e.data_ptr()), P(None),
+                                  P(None), C.c_longlong(M), K, 8, seg, wts, C.c_float(1.0), L.stream_ptr()), 'heads_ce_fused')
+    assert _rel(loss_e, loss_f) < 1e-5 and torch.equal(cor_e, cor_f)
