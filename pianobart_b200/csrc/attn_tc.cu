@@ -24,6 +24,8 @@
 // stores from an operand tile that is free by then.
 #include "ptx.cuh"
 #include "pb_internal.h"
+#include <stdlib.h>
+#include <type_traits>
 
 namespace pb {
 
@@ -137,6 +139,47 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// packed fp32 pairs (Blackwell FFMA2 / FADD2): one issue slot for two lanes of the softmax's scale-and-shift and row sums
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// 2^y for a pair of log2-domain arguments on the FMA / integer pipes (no MUFU): round-to-nearest split y = k + f with the
+// magic-number trick, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16
+// rounding of P), k added into the exponent field.  Arguments below -120 give 2^-120 (0 after the bf16 P V product).  The
+// softmax sends a share of the pairs of a row here so that the MUFU pipe (ex2: ~10.5 cycles per warp instruction measured on
+// B200, i.e. ~1340 cycles per 128 x 128 block) and the FMA pipe work on the exponentials of a block side by side.  With one
+// softmax warp per scheduler the gain saturates early (a polynomial pair costs 10 extra issue slots at ~0.5 IPC, about what
+// its two MUFU slots cost): 1450 cycles per block without it, 1250 at 25-37 %, 1420 at 50 % (profiles/r2_summary.md).
+__device__ __forceinline__ float2 exp2_poly2(float2 y) {
+  y.x = fmaxf(y.x, -120.f);
+  y.y = fmaxf(y.y, -120.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 t = fadd2(y, magic);
+  const float2 r = fadd2(t, nmagic);
+  const float2 f = fadd2(y, make_float2(-r.x, -r.y));
+  float2 p = ffma2(make_float2(0.0551716685295105f, 0.0551716685295105f), f, make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = ffma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  float2 e;
+  e.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  e.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return e;
 }
 // bit i of the result = column (c0 + i) of this key block may be attended by query qg:
 // key-padding bitmap word AND (causal: kg0 + c0 + i <= qg)
@@ -459,6 +502,532 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
   if (threadIdx.x == 64) PB_TR(0, 63, 4);
+}
+
+// ===================================================================================== forward, two CTAs per SM
+// Same arithmetic as attn_fwd_kernel with the opposite trade: every resource is single-buffered (Q, one K tile, one V tile =
+// 96 KB of shared memory; S/P + O = 256 TMEM columns; 192 threads) so that TWO CTAs are resident per SM, and the overlap of
+// tensor pipe, MUFU pipe and TMA comes from the two CTAs running out of phase instead of from look-ahead inside one CTA:
+// while one CTA's softmax warps exponentiate block j (MUFU-bound, ~1000 cycles per 128 x 128 block) the other CTA's S / P V
+// products own the tensor pipe, and a CTA's prologue (Q / K TMA latency, key bitmap) and epilogue (O store) hide behind its
+// neighbour's steady state - a one-tile CTA of the look-ahead kernel spends a third of its life there (profiles/r1_summary).
+// A softmax thread owns a whole row (4 warps, no row-max exchange between threads).  Within a CTA every barrier alternates
+// strictly (S(j) -> softmax(j) -> P V(j) -> S(j+1), in-order tensor pipe), so no parity wait can alias a later phase:
+// s_full(j) is committed after P V(j-1), which is why the O rescale needs no barrier of its own.
+constexpr int F2_THREADS = 64 + 128;
+
+__global__ void __launch_bounds__(F2_THREADS, 2)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                 const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 64) PB_TR(0, 63, 0);
+  __shared__ __align__(8) uint64_t q_full, k_full, k_empty, v_full, v_empty, s_full, p_full, o_full, mma_drain;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ uint32_t s_keep[FWD_MAX_SK / 32];
+  Smem4 sm;
+  carve(smem_raw, sm, 3);  // 0 Q, 1 K, 2 V
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * AT;
+  int nkb = (p.Sk + AT - 1) / AT;
+  if (p.causal) nkb = min(nkb, qb + 1);
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&q_full, 1); mbar_init(&k_full, 1); mbar_init(&k_empty, 1); mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
+    mbar_init(&s_full, 1); mbar_init(&p_full, 128); mbar_init(&o_full, 1); mbar_init(&mma_drain, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  if (threadIdx.x == 64) PB_TR(0, 63, 1);
+  const uint32_t tmem = tmem_base_smem;
+  const uint32_t tS = tmem, tO = tmem + AT;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(&q_full, TILE_BYTES);
+      load_tile(sm.t[0], &tq, &q_full, q0, h, b);
+      // release order of the slots is K(j) [after S(j-1)], V(j) [after P V(j-1)], K(j+1) [after S(j)], ...: one thread
+      // waiting in that order never holds a ready load back
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(&k_empty, ((uint32_t)j & 1) ^ 1);
+        chaos_delay(p.dbg_delay >> 2, 2 * j);
+        mbar_expect_tx(&k_full, TILE_BYTES);
+        load_tile(sm.t[1], &tk, &k_full, j * AT, h, b);
+        mbar_wait(&v_empty, ((uint32_t)j & 1) ^ 1);
+        chaos_delay(p.dbg_delay, 2 * j + 1);
+        mbar_expect_tx(&v_full, TILE_BYTES);
+        load_tile(sm.t[2], &tv, &v_full, j * AT, h, b);
+      }
+      // producer tail
+      mbar_wait(&k_empty, ((uint32_t)nkb & 1) ^ 1);
+      mbar_wait(&v_empty, ((uint32_t)nkb & 1) ^ 1);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_pv = make_idesc_bf16(AT, AT, 0, 1);
+      mbar_wait(&q_full, 0);
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(&k_full, (uint32_t)j & 1);
+        tc_fence_after();
+        PB_TR(0, j, 0);
+        // S(j) overwrites P(j-1): P V(j-1) precedes it in the in-order tensor pipe
+        mma_tile<false, false>(tS, sm.a[0], sm.a[1], false);
+        umma_commit(&s_full);
+        umma_commit(&k_empty);
+        PB_TR(0, j, 1);
+        mbar_wait(&p_full, (uint32_t)j & 1);
+        mbar_wait(&v_full, (uint32_t)j & 1);
+        tc_fence_after();
+        PB_TR(0, j, 2);
+        // O += P V: A = P from TMEM (packed bf16, 64 columns), B = V tile as MN-major operand
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ts(tO, tS + kk * 8, desc_mnmajor(sm.a[2], kk), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&v_empty);
+        PB_TR(0, j, 3);
+      }
+      umma_commit(&o_full);
+      umma_commit(&mma_drain);
+      mbar_wait(&mma_drain, 0);
+    }
+  } else {
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;          // tile row = TMEM lane
+    const int tid = threadIdx.x - 64;        // 0..127
+    const int qg = q0 + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    const bool causal = p.causal != 0;
+    float m_used = -INFINITY, l = 0.f;
+    const int trole = (lane == 0 && (warp == 2 || warp == 4)) ? (warp == 2 ? 1 : 2) : -1;
+    for (int k0 = 0; k0 < nkb * AT; k0 += 128) {
+      const int kc = k0 + tid;
+      bool kp = kc < p.Sk;
+      if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc] != 0;
+      const uint32_t w = __ballot_sync(0xffffffffu, kp);
+      if (lane == 0) s_keep[kc >> 5] = w;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int j = 0; j < nkb; ++j) {
+      uint32_t msk[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) msk[c] = chunk_mask(s_keep[j * 4 + c], causal, qg, j * AT + c * 32);
+      if (trole > 0) PB_TR(trole, j, 0);
+      mbar_wait(&s_full, (uint32_t)j & 1);
+      tc_fence_after();
+      if (trole > 0) PB_TR(trole, j, 1);
+      // pass 1: masked row maximum
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (msk[c] == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) { bm0 = fmaxf(bm0, __uint_as_float(v[i])); bm1 = fmaxf(bm1, __uint_as_float(v[i + 1])); }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            bm0 = fmaxf(bm0, ((msk[c] >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+            bm1 = fmaxf(bm1, ((msk[c] >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : -INFINITY);
+          }
+        }
+      }
+      const float m_blk = fmaxf(bm0, bm1) * sl2;
+      if (trole > 0) PB_TR(trole, j, 2);
+      // lazy rescale: keep the old reference unless the maximum grew by more than 2^8
+      float f = 1.0f;
+      bool need = false;
+      if (m_used == -INFINITY) {
+        m_used = m_blk;
+      } else if (m_blk > m_used + RESCALE_THRESHOLD) {
+        f = ex2(m_used - m_blk);
+        m_used = m_blk;
+        need = true;
+      }
+      if (__any_sync(0xffffffffu, need)) {     // (P V(j-1) has retired: s_full(j) was committed after it)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tO + lane_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          tmem_st32(tO + lane_addr + c * 32, v);
+        }
+        l *= f;
+      }
+      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+      if (trole > 0) PB_TR(trole, j, 3);
+      // pass 2: exponentials; P chunk c (32 keys = 16 packed columns) lands on S columns already consumed
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld32(tS + lane_addr + c * 32, sv);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        const bool all = msk[c] == 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x0 = __uint_as_float(sv[2 * i]), x1 = __uint_as_float(sv[2 * i + 1]);
+          if (!all) {
+            x0 = ((msk[c] >> (2 * i)) & 1u) ? x0 : -INFINITY;
+            x1 = ((msk[c] >> (2 * i + 1)) & 1u) ? x1 : -INFINITY;
+          }
+          const float e0 = ex2(fmaf(x0, sl2, neg_m)), e1 = ex2(fmaf(x1, sl2, neg_m));
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          rs0 += e0;
+          rs1 += e1;
+        }
+        tmem_st16(tS + lane_addr + c * 16, pk);
+      }
+      l += rs0 + rs1;
+      tmem_st_wait();
+      if (trole > 0) PB_TR(trole, j, 4);
+      tc_fence_before();
+      mbar_arrive(&p_full);
+      if (trole > 0) PB_TR(trole, j, 5);
+    }
+    mbar_wait(&o_full, 0);
+    tc_fence_after();
+    if (threadIdx.x == 64) PB_TR(0, 63, 2);
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    // O rows -> the Q tile (every S MMA has retired) -> two bulk tensor stores
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      stage_row_chunk(sm.t[0], r, c >> 1, c & 1, v, inv);
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) { store_tile_tma(&to, sm.t[0], q0, h, b); bulk_wait_read<0>(); }
+    if (qg < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qg] = (l > 0.f) ? (m_used + log2f(l)) : INFINITY;
+    if (threadIdx.x == 64) PB_TR(0, 63, 3);
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 256);
+}
+
+// ===================================================================================== forward, two Q tiles per CTA
+// The production forward kernel.  One CTA owns TWO consecutive 128-query tiles (a, b) of a (batch, head) and one softmax
+// warpgroup per tile (4 warps, thread = row, no exchange between threads); K / V tiles are shared by the two tiles and
+// double-buffered.  The single MMA thread alternates between the tiles,
+//     ... P V_a(j), S_a(j+1), P V_b(j), S_b(j+1), P V_a(j+1), ...
+// so while warpgroup a exponentiates S_a(j+1) - a MUFU-bound stretch - the tensor pipe runs tile b's products and vice
+// versa (TMEM: S_a | S_b | O_a | O_b = 512 columns; P_t is written back, packed, over the S_t columns it was derived from).
+// Per tile every hand-off alternates strictly, S_t(j) -> softmax_t(j) -> P V_t(j) -> S_t(j+1) (in-order tensor pipe), so no
+// parity wait can alias a later phase, and s_full_t(j) is committed after P V_t(j-1): the lazy O rescale needs no barrier of
+// its own.  K(j+2) / V(j+2) are requested when S_b(j) / P V_b(j) retire, two block periods before their first use (a TMA
+// refill takes 2000-3000 cycles under load, tools/gpu_attn_trace2.py).  Causal: tile a visits one key block fewer than b.
+#ifndef PB_F3_POLY_MASK
+#define PB_F3_POLY_MASK 0x2492   // pairs 1, 4, 7, 10, 13 of every 16: the measured balance point of the MUFU and FMA pipes
+#endif
+constexpr int F3_THREADS = 64 + 256 + 64;   // TMA, MMA, 8 softmax warps, 2 register-donor warps
+
+__global__ void __launch_bounds__(F3_THREADS, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                 const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 64) PB_TR(0, 63, 0);
+  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], o_full[2], stagger, mma_drain;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ uint32_t s_keep[FWD_MAX_SK / 32];
+  Smem4 sm;
+  carve(smem_raw, sm, 6);  // 0-1 Q_a Q_b, 2-3 K ring, 4-5 V ring
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // causal: query tiles near the end of the sequence visit the most key blocks - schedule them first
+  const int qp = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qp * 2 * AT;
+  const int nkb_all = (p.Sk + AT - 1) / AT;
+  int nk[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    nk[t] = p.causal ? min(nkb_all, 2 * qp + t + 1) : nkb_all;
+    if (q0 + t * AT >= p.Sq) nk[t] = 0;                 // tile b beyond the sequence
+  }
+  const int na = nk[0], nb = max(nk[0], nk[1]);        // (na >= 1 always; nk[1] is 0 or >= na)
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&q_full, 1); mbar_init(&mma_drain, 1); mbar_init(&stagger, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  if (threadIdx.x == 64) PB_TR(0, 63, 1);
+  const uint32_t tmem = tmem_base_smem;
+
+  // Register budget (setmaxnreg, balanced per SM sub-partition = warp index mod 4): 12 warps are launched at 168 registers;
+  // on every sub-partition one warp that needs few (TMA producer, MMA issuer, two idle donor warps) hands registers back and
+  // the two softmax warps there grow to 224, so that a softmax thread keeps its whole S row (128 values) in registers next
+  // to the packed P chunk it builds.
+  if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (elect_one()) {
+      mbar_expect_tx(&q_full, 2 * TILE_BYTES);
+      load_tile(sm.t[0], &tq, &q_full, q0, h, b);
+      load_tile(sm.t[1], &tq, &q_full, q0 + AT, h, b);
+      // slot release order: K(j) [after S_b(j-2)], V(j) [after P V_b(j-2)], K(j+1) [after S_b(j-1)], ...
+      for (int j = 0; j < nb; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = ((uint32_t)(j >> 1) & 1) ^ 1;
+        mbar_wait(&k_empty[s], ph);
+        chaos_delay(p.dbg_delay >> 2, 2 * j);
+        mbar_expect_tx(&k_full[s], TILE_BYTES);
+        load_tile(sm.t[2 + s], &tk, &k_full[s], j * AT, h, b);
+        mbar_wait(&v_empty[s], ph);
+        chaos_delay(p.dbg_delay, 2 * j + 1);
+        mbar_expect_tx(&v_full[s], TILE_BYTES);
+        load_tile(sm.t[4 + s], &tv, &v_full[s], j * AT, h, b);
+      }
+      // producer tail: every slot release (tcgen05.commit arrival) has landed before the CTA exits
+      for (int j = nb; j < nb + 2; ++j) {
+        mbar_wait(&k_empty[j & 1], ((uint32_t)(j >> 1) & 1) ^ 1);
+        mbar_wait(&v_empty[j & 1], ((uint32_t)(j >> 1) & 1) ^ 1);
+      }
+    }
+  } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (elect_one()) {
+      constexpr uint32_t idesc_pv = make_idesc_bf16(AT, AT, 0, 1);
+      const bool two = nk[1] > 0;
+      auto issue_s = [&](int t, int j) {           // S_t(j) = Q_t K(j)^T; overwrites P_t(j-1), read by the P V_t(j-1) issued before it
+        mma_tile<false, false>(tmem + t * AT, sm.a[t], sm.a[2 + (j & 1)], false);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {          // O_t += P_t(j) V(j): A = packed bf16 P over the S_t columns, B = V tile MN-major
+        const uint32_t tP = tmem + t * AT, tO = tmem + 2 * AT + t * AT, vt = sm.a[4 + (j & 1)];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ts(tO, tP + kk * 8, desc_mnmajor(vt, kk), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+      };
+      mbar_wait_spin(&q_full, 0);
+      mbar_wait_spin(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      if (two) {
+        // Tile b starts about half a block period after tile a (warpgroup a signals `stagger` part-way through its first
+        // block): the two softmax warpgroups then run out of phase - one exponentiates while the other waits for its
+        // products - instead of contending for the MUFU pipe and then leaving the tensor pipe idle together.  The phase
+        // offset persists: both tiles have the same period.
+        mbar_wait_spin(&stagger, 0);
+        issue_s(1, 0);
+      }
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < nb; ++j) {
+        const int s = j & 1, sn = (j + 1) & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1, phn = (uint32_t)((j + 1) >> 1) & 1;
+        bool v_ok = false, k_ok = false;
+        if (j < na) {
+          PB_TR(0, j, 0);
+          mbar_wait_spin(&p_full[0], (uint32_t)j & 1);
+          mbar_wait_spin(&v_full[s], ph); v_ok = true;
+          tc_fence_after();
+          PB_TR(0, j, 1);
+          issue_pv(0, j);
+          if (j + 1 < na) {
+            mbar_wait_spin(&k_full[sn], phn); k_ok = true;
+            tc_fence_after();
+            issue_s(0, j + 1);
+          } else {
+            umma_commit(&o_full[0]);
+          }
+          if (!two) {                                // single-tile CTA (sequence tail): tile a releases the slots
+            umma_commit(&v_empty[s]);
+            if (j + 1 < na) umma_commit(&k_empty[sn]);
+          }
+          PB_TR(0, j, 2);
+        }
+        if (two) {
+          mbar_wait_spin(&p_full[1], (uint32_t)j & 1);
+          if (!v_ok) mbar_wait_spin(&v_full[s], ph);
+          tc_fence_after();
+          PB_TR(0, j, 3);
+          issue_pv(1, j);
+          umma_commit(&v_empty[s]);
+          if (j + 1 < nb) {
+            if (!k_ok) mbar_wait_spin(&k_full[sn], phn);
+            tc_fence_after();
+            issue_s(1, j + 1);
+            umma_commit(&k_empty[sn]);
+          } else {
+            umma_commit(&o_full[1]);
+          }
+          PB_TR(0, j, 4);
+        }
+      }
+      // no MMA / commit of this CTA is in flight when TMEM is released and the CTA exits
+      umma_commit(&mma_drain);
+      mbar_wait(&mma_drain, 0);
+    }
+  } else if (warp >= 10) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");     // donor warps: nothing else to do
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int t = (warp - 2) >> 2;           // tile / warpgroup
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;          // tile row = TMEM lane
+    const int tid = threadIdx.x - 64;        // 0..255
+    const int qg = q0 + t * AT + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem + t * AT + lane_addr, tO = tmem + 2 * AT + t * AT + lane_addr;
+    const float sl2 = p.scale * LOG2E;
+    const bool causal = p.causal != 0;
+    const int nkt = nk[t];
+    float m_used = -INFINITY, l = 0.f;
+    const int trole = (lane == 0 && (warp == 2 || warp == 6)) ? (warp == 2 ? 1 : 2) : -1;
+    for (int k0 = 0; k0 < nb * AT; k0 += 256) {
+      const int kc = k0 + tid;
+      bool kp = kc < p.Sk;
+      if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc] != 0;
+      const uint32_t w = __ballot_sync(0xffffffffu, kp);
+      if (lane == 0 && kc < FWD_MAX_SK) s_keep[kc >> 5] = w;
+    }
+    compute_bar_sync();
+    for (int j = 0; j < nkt; ++j) {
+      uint32_t msk[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) msk[c] = chunk_mask(s_keep[j * 4 + c], causal, qg, j * AT + c * 32);
+      if (trole > 0) PB_TR(trole, j, 0);
+      mbar_wait(&s_full[t], (uint32_t)j & 1);
+      tc_fence_after();
+      if (trole > 0) PB_TR(trole, j, 1);
+      // the whole S row (128 fp32 values) is read from TMEM once and stays in registers for both passes
+      uint32_t v0[32], v1[32], v2[32], v3[32];
+      tmem_ld32(tS, v0); tmem_ld32(tS + 32, v1); tmem_ld32(tS + 64, v2); tmem_ld32(tS + 96, v3);
+      tmem_ld_wait();
+      // pass 1: masked row maximum
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+      auto rmax = [&](const uint32_t (&v)[32], uint32_t m) {
+        if (m == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) { bm0 = fmaxf(bm0, __uint_as_float(v[i])); bm1 = fmaxf(bm1, __uint_as_float(v[i + 1])); }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            bm0 = fmaxf(bm0, ((m >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+            bm1 = fmaxf(bm1, ((m >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : -INFINITY);
+          }
+        }
+      };
+      rmax(v0, msk[0]); rmax(v1, msk[1]); rmax(v2, msk[2]); rmax(v3, msk[3]);
+      const float m_blk = fmaxf(bm0, bm1) * sl2;
+      if (trole > 0) PB_TR(trole, j, 2);
+      // lazy rescale: keep the old reference unless the maximum grew by more than 2^8
+      float f = 1.0f;
+      bool need = false;
+      if (m_used == -INFINITY) {
+        m_used = m_blk;
+      } else if (m_blk > m_used + RESCALE_THRESHOLD) {
+        f = ex2(m_used - m_blk);
+        m_used = m_blk;
+        need = true;
+      }
+      if (__any_sync(0xffffffffu, need)) {     // (P V_t(j-1) has retired: s_full_t(j) was committed after it)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tO + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          tmem_st32(tO + c * 32, v);
+        }
+        l *= f;
+      }
+      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+      if (trole > 0) PB_TR(trole, j, 3);
+      // pass 2: exponentials; P chunk c (32 keys = 16 packed columns) is written back over the S columns
+      // (an unmasked and a masked instance of the chunk body behind a warp-uniform branch: masked key blocks - padding, the
+      // causal diagonal - are the minority, and predicated-off mask instructions would still cost their issue slots)
+      float2 rs = make_float2(0.f, 0.f);
+      const float2 sl2v = make_float2(sl2, sl2), negv = make_float2(neg_m, neg_m);
+      auto expo = [&](auto masked, const uint32_t (&sv)[32], uint32_t m, int c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 x = make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1]));
+          if constexpr (decltype(masked)::value) {
+            x.x = ((m >> (2 * i)) & 1u) ? x.x : -INFINITY;      // masked entries are -inf -> ex2 gives 0
+            x.y = ((m >> (2 * i + 1)) & 1u) ? x.y : -INFINITY;
+          }
+          const float2 y = ffma2(x, sl2v, negv);
+          float2 e;
+          if constexpr (!decltype(masked)::value) {
+            if ((PB_F3_POLY_MASK >> i) & 1) e = exp2_poly2(y);   // this share of the pairs on the FMA pipe
+            else e = make_float2(ex2(y.x), ex2(y.y));
+          } else {
+            e = make_float2(ex2(y.x), ex2(y.y));                 // (-inf must give exactly 0)
+          }
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(e.x, e.y);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          rs = fadd2(rs, e);
+        }
+        tmem_st16(tS + c * 16, pk);
+      };
+      const bool unmasked = __all_sync(0xffffffffu, (msk[0] & msk[1] & msk[2] & msk[3]) == 0xffffffffu);
+      if (unmasked) {
+        expo(std::false_type{}, v0, msk[0], 0);
+        if (t == 0 && j == 0) mbar_arrive(&stagger);
+        expo(std::false_type{}, v1, msk[1], 1); expo(std::false_type{}, v2, msk[2], 2); expo(std::false_type{}, v3, msk[3], 3);
+      } else {
+        expo(std::true_type{}, v0, msk[0], 0);
+        if (t == 0 && j == 0) mbar_arrive(&stagger);
+        expo(std::true_type{}, v1, msk[1], 1); expo(std::true_type{}, v2, msk[2], 2); expo(std::true_type{}, v3, msk[3], 3);
+      }
+      const float rs0 = rs.x, rs1 = rs.y;
+      l += rs0 + rs1;
+      tmem_st_wait();
+      if (trole > 0) PB_TR(trole, j, 4);
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+      if (trole > 0) PB_TR(trole, j, 5);
+    }
+    if (nkt > 0) {
+      mbar_wait(&o_full[t], 0);
+      tc_fence_after();
+      if (threadIdx.x == 64) PB_TR(0, 63, 2);
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      // O rows -> this tile's Q buffer (every S_t MMA has retired) -> two bulk tensor stores
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tO + c * 32, v);
+        tmem_ld_wait();
+        stage_row_chunk(sm.t[t], r, c >> 1, c & 1, v, inv);
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + t) : "memory");
+      if ((tid & 127) == 0) { store_tile_tma(&to, sm.t[t], q0 + t * AT, h, b); bulk_wait_read<0>(); }
+      if (qg < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qg] = (l > 0.f) ? (m_used + log2f(l)) : INFINITY;
+      if (threadIdx.x == 64) PB_TR(0, 63, 3);
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
 // ===================================================================================== backward: dK, dV
@@ -997,10 +1566,32 @@ extern "C" int pb_attn_fwd(const pb_attn_desc* d, void* stream_) {
   if (attn_tmap(&to, d->o, d->Sq, d->ldo, d->H, d->B, (long long)d->Sq * d->ldo)) return -1;
   AttnParams p;
   fill_params(p, d);
+  dim3 grid((d->Sq + AT - 1) / AT, d->H, d->B);
+  // PIANOBART_B200_ATTN_FWD: 3 (default) two Q tiles per CTA; 2 single-buffered CTAs, two per SM; 1 one-tile look-ahead kernel
+  static const int variant = []() { const char* e = getenv("PIANOBART_B200_ATTN_FWD"); return e ? atoi(e) : 3; }();
+  if (variant == 3) {
+    static bool attr3 = false;
+    const int smem3 = 6 * TILE_BYTES + 1024;
+    if (set_smem(attn_fwd3_kernel, smem3, attr3)) return -1;
+    dim3 grid3((d->Sq + 2 * AT - 1) / (2 * AT), d->H, d->B);
+    PB_LAUNCH(attn_fwd3_kernel, grid3, F3_THREADS, smem3, stream, tq, tk, tv, to, p);
+    return pb_check_launch("attn_fwd3_kernel");
+  }
+  if (variant == 2) {
+    // single-buffered CTAs, two resident per SM (96 KB of shared memory and 256 TMEM columns each)
+    static bool attr2 = false;
+    const int smem2 = 3 * TILE_BYTES + 1024;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (e != cudaSuccess) return pb_set_cuda_error("cudaFuncSetAttribute(attn_fwd2 carveout)", e);
+    }
+    if (set_smem(attn_fwd2_kernel, smem2, attr2)) return -1;
+    PB_LAUNCH(attn_fwd2_kernel, grid, F2_THREADS, smem2, stream, tq, tk, tv, to, p);
+    return pb_check_launch("attn_fwd2_kernel");
+  }
   static bool attr = false;
   const int smem = 6 * TILE_BYTES + 1024;
   if (set_smem(attn_fwd_kernel, smem, attr)) return -1;
-  dim3 grid((d->Sq + AT - 1) / AT, d->H, d->B);
   PB_LAUNCH(attn_fwd_kernel, grid, NTHREADS, smem, stream, tq, tk, tv, to, p);
   return pb_check_launch("attn_fwd_kernel");
 }
