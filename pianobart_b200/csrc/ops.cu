@@ -613,13 +613,51 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
     const float norm = sqrtf(*gnorm_sq) * grad_scale;
     coef *= fminf(1.f, max_norm / (norm + 1e-6f));
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * coef;
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    float pi = p[i] - step_size * mi / (sqrtf(vi) + eps);
+  auto upd = [&](float& pi, float& mi, float& vi, float gi) {
+    gi *= coef;
+    mi = beta1 * mi + (1.f - beta1) * gi;
+    vi = beta2 * vi + (1.f - beta2) * gi * gi;
+    pi = pi - step_size * mi / (sqrtf(vi) + eps);
     pi -= lr * wd * pi;
-    m[i] = mi; v[i] = vi; p[i] = pi;
+  };
+  // 16-byte accesses, two independent packs per thread and iteration (30 bytes move per element: the kernel is pure HBM
+  // streaming and needs the loads of a whole iteration in flight at once); callers pass 16-byte aligned pointers
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < n4;
+    float4 P0 = reinterpret_cast<const float4*>(p)[i], M0 = reinterpret_cast<const float4*>(m)[i];
+    float4 V0 = reinterpret_cast<const float4*>(v)[i], G0 = reinterpret_cast<const float4*>(g)[i];
+    float4 P1, M1, V1, G1;
+    if (two) {
+      P1 = reinterpret_cast<const float4*>(p)[i2]; M1 = reinterpret_cast<const float4*>(m)[i2];
+      V1 = reinterpret_cast<const float4*>(v)[i2]; G1 = reinterpret_cast<const float4*>(g)[i2];
+    }
+    upd(P0.x, M0.x, V0.x, G0.x); upd(P0.y, M0.y, V0.y, G0.y); upd(P0.z, M0.z, V0.z, G0.z); upd(P0.w, M0.w, V0.w, G0.w);
+    reinterpret_cast<float4*>(p)[i] = P0; reinterpret_cast<float4*>(m)[i] = M0; reinterpret_cast<float4*>(v)[i] = V0;
+    if (p_bf16) {
+      uint2 o;
+      *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(P0.x * bf16_scale, P0.y * bf16_scale);
+      *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(P0.z * bf16_scale, P0.w * bf16_scale);
+      reinterpret_cast<uint2*>(p_bf16)[i] = o;
+    }
+    if (two) {
+      upd(P1.x, M1.x, V1.x, G1.x); upd(P1.y, M1.y, V1.y, G1.y); upd(P1.z, M1.z, V1.z, G1.z); upd(P1.w, M1.w, V1.w, G1.w);
+      reinterpret_cast<float4*>(p)[i2] = P1; reinterpret_cast<float4*>(m)[i2] = M1; reinterpret_cast<float4*>(v)[i2] = V1;
+      if (p_bf16) {
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(P1.x * bf16_scale, P1.y * bf16_scale);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(P1.z * bf16_scale, P1.w * bf16_scale);
+        reinterpret_cast<uint2*>(p_bf16)[i2] = o;
+      }
+    }
+  }
+  // tail (n not a multiple of 4)
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, mi, vi, g[i]);
+    p[i] = pi; m[i] = mi; v[i] = vi;
     if (p_bf16) p_bf16[i] = __float2bfloat16(pi * bf16_scale);
   }
 }
@@ -878,6 +916,9 @@ extern "C" int pb_adamw(float* p, float* m, float* v, const float* g, void* p_bf
                         float grad_scale, float bf16_scale, void* stream) {
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g)) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(p_bf16) & 7) != 0)
+    return pb_set_error("adamw: pointers must be 16-byte aligned (bf16 copy: 8-byte)");
   PB_LAUNCH((adamw_kernel), grid_for(n, 256 * 8, 8), 256, 0, PB_STREAM(stream), p, m, v, g, (bf16*)p_bf16, n, lr, beta1, beta2, eps, wd, step_size, gnorm_sq, max_norm, grad_scale, bf16_scale);
   return pb_check_launch("adamw");
 }

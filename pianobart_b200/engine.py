@@ -158,6 +158,7 @@ class Plan:
         self.dtype = dtype
         self.ops = []
         self._keep = []  # keep ctypes structs / arrays alive
+        self._side_events = []
 
     def _add(self, name, fn, *args):
         self.ops.append((name, fn, args))
@@ -166,18 +167,41 @@ class Plan:
         """Host-side marker (no launch): run() hands the payload to `on_marker` when it reaches it."""
         self.ops.append(('marker', None, payload))
 
-    def run(self, stream=None, on_marker=None, profile=None):
+    def run(self, stream=None, on_marker=None, profile=None, side_stream=None):
         """profile: optional list; every GEMM launch is then bracketed by CUDA events on the launching
-        stream and (name, flops, start_event, end_event) is appended (bench.py roofline)."""
-        s = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+        stream and (name, flops, start_event, end_event) is appended (bench.py roofline).
+        side_stream: a second CUDA stream for the bias-gradient column sums: they are HBM-bound, have no consumer before the
+        optimizer, and otherwise sit serially between tensor-bound GEMMs; each one starts when its producer has finished
+        (event) and runs next to the following GEMMs.  The main stream joins the side stream at every marker (the
+        data-parallel reducer ships the layer's gradients there) and at the end of the plan - always before any later op
+        rewrites a column-sum source (those buffers are reused once per layer, after the layer's marker)."""
+        main = torch.cuda.current_stream() if stream is None else None
+        s = C.c_void_p(main.cuda_stream if stream is None else stream)
+        use_side = side_stream is not None and main is not None and profile is None
+        ss = C.c_void_p(side_stream.cuda_stream) if use_side else None
         n = 0
+        n_side = 0
+        pending = False
         gemm_fns = (self.lib.pb_gemm_bf16, self.lib.pb_gemm_f32)
         for name, fn, args in self.ops:
             if fn is None:
+                if pending:
+                    main.wait_stream(side_stream)
+                    pending = False
                 if on_marker is not None:
                     on_marker(*args)
                 continue
-            if profile is not None and fn in gemm_fns:
+            if use_side and name == 'colsum':
+                ev = self._side_events[n_side] if n_side < len(self._side_events) else None
+                if ev is None:
+                    ev = torch.cuda.Event()
+                    self._side_events.append(ev)
+                n_side += 1
+                ev.record(main)
+                side_stream.wait_event(ev)
+                rc = fn(*args, ss)
+                pending = True
+            elif profile is not None and fn in gemm_fns:
                 d = args[0]._obj
                 flops = 2.0 * d.M * d.N * d.K * max(1, d.batch_h) * max(1, d.batch_b) * (0.5 if d.causal else 1.0)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -190,6 +214,8 @@ class Plan:
             n += 1
             if rc != 0:
                 raise L.PBError('%s failed (%d): %s' % (name, rc, self.lib.pb_last_error().decode()))
+        if pending:
+            main.wait_stream(side_stream)
         return n
 
     # ---- op recorders ------------------------------------------------------------------
@@ -743,7 +769,15 @@ class BackboneGraph:
         return n
 
     def backward(self):
-        return self.bwd.run()
+        return self.bwd.run(side_stream=self.side_stream())
+
+    def side_stream(self):
+        """second stream for the bias-gradient column sums of the backward plan (Plan.run); PIANOBART_B200_SIDE_COLSUM=0 off"""
+        if os.environ.get('PIANOBART_B200_SIDE_COLSUM', '1') == '0':
+            return None
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
 
 def profile_gemms(step):
