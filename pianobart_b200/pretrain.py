@@ -202,6 +202,13 @@ class PretrainStep:
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.stats[16:24], group=self.pg)  # global denominators (pretrain.py:117 on the full batch)
+        side = g.side_stream() if train else None
+        if side is not None:
+            # the 695 MB gradient buffer is cleared on the side stream while the forward pass runs (nothing reads or writes
+            # it before backward; the previous step's optimizer, its last reader, precedes this point on the main stream)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                L.check(lib.pb_fill_zero(P(pb._grad.data_ptr()), C.c_longlong(pb._grad.numel() * 4), L.stream_ptr()), 'fill_zero')
         n = g.fwd.run(profile=profile)
         if self.fused_ce:
             # heads GEMM + masked CE + accuracy + dlogits in one tcgen05 kernel: the fp32 logits never reach HBM
@@ -220,7 +227,10 @@ class PretrainStep:
                                     self.w, C.c_float(self.grad_scale), pb.pb_dtype, s), 'heads_ce')
             n += 2
         if train:
-            pb._grad.zero_()
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
+            else:
+                pb._grad.zero_()
             if self.world > 1:
                 from .parallel import BucketReducer
                 red = BucketReducer(pb._grad, self.pg, comm_stream=self.comm_stream)
