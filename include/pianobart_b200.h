@@ -114,6 +114,10 @@ typedef struct pb_attn_desc {
 } pb_attn_desc;
 int pb_attn_fwd(const pb_attn_desc* d, void* stream);
 int pb_attn_bwd(const pb_attn_desc* d, void* stream);
+/* pb_attn_bwd in two parts: _prep fills dvec = rowsum(dout * o) (HBM-bound; may run on another stream next to an unrelated
+ * GEMM), _main computes dq / dk / dv from a dvec that is complete */
+int pb_attn_bwd_prep(const pb_attn_desc* d, void* stream);
+int pb_attn_bwd_main(const pb_attn_desc* d, void* stream);
 /* test hook (fault injection): the TMA producer threads of the attention kernels launched after this call stall a
  * pseudo-random number of cycles (< max_cycles) before each tile load, so tiles arrive late relative to the softmax warps
  * and the MMA thread; 0 turns it off.  Results must not depend on it (tests/test_gpu_parity.py).  Returns the old value. */

@@ -1596,7 +1596,21 @@ extern "C" int pb_attn_fwd(const pb_attn_desc* d, void* stream_) {
   return pb_check_launch("attn_fwd_kernel");
 }
 
-extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
+// D = rowsum(dO * O) per (batch, head, query): HBM-bound, small footprint - the engine runs it on its side stream next to a
+// weight-gradient GEMM (pb_attn_bwd_prep + pb_attn_bwd_main); pb_attn_bwd is the two back to back
+extern "C" int pb_attn_bwd_prep(const pb_attn_desc* d, void* stream_) {
+  if (attn_check(d)) return -1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long rows = (long long)d->B * d->Sq * d->H;
+  long long blocks = (rows * 16 / 2 + 255) / 256;                       // two rows per thread
+  const long long cap = (long long)pb_num_sms() * 16;
+  const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+  PB_LAUNCH(attn_bwd_prep_kernel, grid, 256, 0, stream, (const __nv_bfloat16*)d->o, (const __nv_bfloat16*)d->dout, d->dvec, d->B, d->H,
+            d->Sq, d->ldo, (long long)d->Sq * d->ldo, d->lddo, (long long)d->Sq * d->lddo);
+  return pb_check_launch("attn_bwd_prep_kernel");
+}
+
+extern "C" int pb_attn_bwd_main(const pb_attn_desc* d, void* stream_) {
   if (attn_check(d)) return -1;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CUtensorMap tq, tk, tv, tdo;
@@ -1606,15 +1620,6 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
   if (attn_tmap(&tdo, d->dout, d->Sq, d->lddo, d->H, d->B, (long long)d->Sq * d->lddo)) return -1;
   AttnParams p;
   fill_params(p, d);
-  {
-    const long long rows = (long long)d->B * d->Sq * d->H;
-    long long blocks = (rows * 16 / 2 + 255) / 256;                       // two rows per thread
-    const long long cap = (long long)pb_num_sms() * 16;
-    const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
-    PB_LAUNCH(attn_bwd_prep_kernel, grid, 256, 0, stream, (const __nv_bfloat16*)d->o, (const __nv_bfloat16*)d->dout, d->dvec, d->B, d->H,
-              d->Sq, d->ldo, (long long)d->Sq * d->ldo, d->lddo, (long long)d->Sq * d->lddo);
-    if (pb_check_launch("attn_bwd_prep_kernel")) return -1;
-  }
   static bool attr1 = false, attr2 = false;
   const int smem1 = 2 * TILE_BYTES + 2 * NQ * QT_BYTES + 1024, smem2 = 7 * TILE_BYTES + 1024;
   if (set_smem(attn_bwd_dkv_kernel, smem1, attr1)) return -1;
@@ -1632,6 +1637,11 @@ extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
   dim3 g2((d->Sq + AT - 1) / AT, d->H, d->B);
   PB_LAUNCH(attn_bwd_dq_kernel, g2, NTHREADS, smem2, stream, tq, tk, tv, tdo, tdq, p);
   return pb_check_launch("attn_bwd_dq_kernel");
+}
+
+extern "C" int pb_attn_bwd(const pb_attn_desc* d, void* stream_) {
+  if (pb_attn_bwd_prep(d, stream_)) return -1;
+  return pb_attn_bwd_main(d, stream_);
 }
 
 #ifdef PB_TRACE

@@ -163,6 +163,10 @@ class Plan:
     def _add(self, name, fn, *args):
         self.ops.append((name, fn, args))
 
+    def join_side(self):
+        """The main stream waits here for everything issued on the side stream so far (see run())."""
+        self.ops.append(('join', None, ()))
+
     def marker(self, *payload):
         """Host-side marker (no launch): run() hands the payload to `on_marker` when it reaches it."""
         self.ops.append(('marker', None, payload))
@@ -188,10 +192,10 @@ class Plan:
                 if pending:
                     main.wait_stream(side_stream)
                     pending = False
-                if on_marker is not None:
+                if name == 'marker' and on_marker is not None:
                     on_marker(*args)
                 continue
-            if use_side and name == 'colsum':
+            if use_side and name in ('colsum', 'attn_prep'):
                 ev = self._side_events[n_side] if n_side < len(self._side_events) else None
                 if ev is None:
                     ev = torch.cuda.Event()
@@ -314,7 +318,13 @@ class Plan:
         a.lse, a.dvec, a.key_keep = lse, dvec or None, keep or None
         a.B, a.H, a.Sq, a.Sk, a.hd, a.causal, a.scale = B, H, Sq, Sk, hd, causal, hd ** -0.5
         self._keep.append(a)
-        if backward:
+        if backward == 'prep':
+            # ('attn_prep' ops go to the side stream in run(); PIANOBART_B200_SIDE_PREP=0 keeps D on the main stream)
+            nm = 'attn_prep' if os.environ.get('PIANOBART_B200_SIDE_PREP', '1') != '0' else 'attn_prep_main'
+            self._add(nm, self.lib.pb_attn_bwd_prep, C.byref(a))
+        elif backward == 'main':
+            self._add('attn_bwd', self.lib.pb_attn_bwd_main, C.byref(a))
+        elif backward:
             self._add('attn_bwd', self.lib.pb_attn_bwd, C.byref(a))
         else:
             self._add('attn_fwd', self.lib.pb_attn_fwd, C.byref(a))
@@ -643,15 +653,21 @@ class BackboneGraph:
                               _ptr(r['stc']), _ptr(r['stc'], M), _ptr(dA), self.G(lp + '.encoder_attn_layer_norm.weight'),
                               self.G(lp + '.encoder_attn_layer_norm.bias'), M, d, dbias=self.G(ca + '.out_proj.bias'),
                               dx_drop=_ptr(dAd), out_drop=self.site(side, l, 2))
-                    bw.wgrad(_ptr(dAd), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
-                    bw.gemm(_ptr(dAd), self.W(ca + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dOc'))
                     # dP = dO V^T ; dV = P^T dO ; dS = softmax'(P, dP) ; dQ = scale dS K ; dK = scale dS^T Q
                     if self.flash:
+                        # dO first, then D = rowsum(dO * O) on the side stream next to the out_proj weight gradient
+                        bw.gemm(_ptr(dAd), self.W(ca + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dOc'))
                         dvec = self.buf('g.dvec', B * H * Smax, dtype=torch.float32)
-                        bw.attn(True, _ptr(r['Qc']), _ptr(r['KVc']), _ptr(r['KVc'], d), _ptr(r['Oc']), d, 2 * d, 2 * d, d,
-                                _ptr(r['lse_c']), _ptr(dvec), _ptr(enc_keep), B, H, S, S_enc, hd, 0, dout=_ptr(dO),
-                                dq=_ptr(dQc), dk=_ptr(dKVc), dv=_ptr(dKVc, d), lddq=d, lddk=2 * d, lddv=2 * d)
+                        aargs = (_ptr(r['Qc']), _ptr(r['KVc']), _ptr(r['KVc'], d), _ptr(r['Oc']), d, 2 * d, 2 * d, d,
+                                 _ptr(r['lse_c']), _ptr(dvec), _ptr(enc_keep), B, H, S, S_enc, hd, 0)
+                        akw = dict(dout=_ptr(dO), dq=_ptr(dQc), dk=_ptr(dKVc), dv=_ptr(dKVc, d), lddq=d, lddk=2 * d, lddv=2 * d)
+                        bw.attn('prep', *aargs, **akw)
+                        bw.wgrad(_ptr(dAd), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
+                        bw.join_side()
+                        bw.attn('main', *aargs, **akw)
                     else:
+                        bw.wgrad(_ptr(dAd), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
+                        bw.gemm(_ptr(dAd), self.W(ca + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dOc'))
                         bw.gemm(_ptr(dO), _ptr(r['KVc'], d), _ptr(scores), S, S_enc, hd, d, 2 * d, S_enc, flags=OUT32,
                                 batch_h=H, batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=S * S_enc,
                                 c_sb=H * S * S_enc, name=ln('dP_c'))
@@ -683,15 +699,21 @@ class BackboneGraph:
                           _ptr(r['st1'], M), _ptr(dA), self.G(lp + '.self_attn_layer_norm.weight'),
                           self.G(lp + '.self_attn_layer_norm.bias'), M, d, dbias=self.G(sa + '.out_proj.bias'),
                           dx_drop=_ptr(dAd), out_drop=self.site(side, l, 1))
-                bw.wgrad(_ptr(dAd), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
-                bw.gemm(_ptr(dAd), self.W(sa + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dO'))
                 QKV, Pm = r['QKV'], r['P']
                 if self.flash:
+                    bw.gemm(_ptr(dAd), self.W(sa + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dO'))
                     dvec = self.buf('g.dvec', B * H * Smax, dtype=torch.float32)
-                    bw.attn(True, _ptr(QKV), _ptr(QKV, d), _ptr(QKV, 2 * d), _ptr(r['O']), 3 * d, 3 * d, 3 * d, d,
-                            _ptr(r['lse']), _ptr(dvec), _ptr(keep), B, H, S, S, hd, cz, dout=_ptr(dO), dq=_ptr(dQKV),
-                            dk=_ptr(dQKV, d), dv=_ptr(dQKV, 2 * d), lddq=3 * d, lddk=3 * d, lddv=3 * d)
+                    aargs = (_ptr(QKV), _ptr(QKV, d), _ptr(QKV, 2 * d), _ptr(r['O']), 3 * d, 3 * d, 3 * d, d,
+                             _ptr(r['lse']), _ptr(dvec), _ptr(keep), B, H, S, S, hd, cz)
+                    akw = dict(dout=_ptr(dO), dq=_ptr(dQKV), dk=_ptr(dQKV, d), dv=_ptr(dQKV, 2 * d), lddq=3 * d, lddk=3 * d,
+                               lddv=3 * d)
+                    bw.attn('prep', *aargs, **akw)
+                    bw.wgrad(_ptr(dAd), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
+                    bw.join_side()
+                    bw.attn('main', *aargs, **akw)
                 else:
+                    bw.wgrad(_ptr(dAd), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
+                    bw.gemm(_ptr(dAd), self.W(sa + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dO'))
                     bw.gemm(_ptr(dO), _ptr(QKV, 2 * d), _ptr(scores), S, S, hd, d, 3 * d, S, flags=OUT32, batch_h=H,
                             batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S * 3 * d, c_sh=S * S, c_sb=H * S * S, causal=cz,
                             name=ln('dP'))
