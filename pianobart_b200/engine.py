@@ -159,6 +159,7 @@ class Plan:
         self.ops = []
         self._keep = []  # keep ctypes structs / arrays alive
         self._side_events = []
+        self._side_names = set()   # GEMM launches that may run on the side stream (weight gradients)
 
     def _add(self, name, fn, *args):
         self.ops.append((name, fn, args))
@@ -174,11 +175,12 @@ class Plan:
     def run(self, stream=None, on_marker=None, profile=None, side_stream=None):
         """profile: optional list; every GEMM launch is then bracketed by CUDA events on the launching
         stream and (name, flops, start_event, end_event) is appended (bench.py roofline).
-        side_stream: a second CUDA stream for the bias-gradient column sums: they are HBM-bound, have no consumer before the
-        optimizer, and otherwise sit serially between tensor-bound GEMMs; each one starts when its producer has finished
-        (event) and runs next to the following GEMMs.  The main stream joins the side stream at every marker (the
-        data-parallel reducer ships the layer's gradients there) and at the end of the plan - always before any later op
-        rewrites a column-sum source (those buffers are reused once per layer, after the layer's marker)."""
+        side_stream: a second CUDA stream for work that has no consumer before the optimizer - the bias-gradient column sums
+        (HBM-bound), D = rowsum(dO*O) of the attention backward, and the weight-gradient GEMMs recorded with side=True.  Each
+        starts when its producer has finished (event) and runs next to the critical chain (dgrad GEMMs, LayerNorm and
+        attention backward): the block scheduler fills the ramp and tail of every kernel with CTAs of the other stream.
+        The main stream joins the side stream at every marker (the data-parallel reducer ships the layer's gradients there),
+        at explicit join_side() points - recorded before every op that rewrites a buffer a side op reads - and at the end."""
         main = torch.cuda.current_stream() if stream is None else None
         s = C.c_void_p(main.cuda_stream if stream is None else stream)
         use_side = side_stream is not None and main is not None and profile is None
@@ -195,7 +197,7 @@ class Plan:
                 if name == 'marker' and on_marker is not None:
                     on_marker(*args)
                 continue
-            if use_side and name in ('colsum', 'attn_prep'):
+            if use_side and (name in ('colsum', 'attn_prep') or name in self._side_names):
                 ev = self._side_events[n_side] if n_side < len(self._side_events) else None
                 if ev is None:
                     ev = torch.cuda.Event()
@@ -246,13 +248,18 @@ class Plan:
         fn = self.lib.pb_gemm_bf16 if self.dtype == PB_BF16 else self.lib.pb_gemm_f32
         self._add(name, fn, C.byref(d))
 
-    def wgrad(self, dy, x, dw, n_out, n_in, M, ld_dy, ld_x, name='wgrad'):
+    def wgrad(self, dy, x, dw, n_out, n_in, M, ld_dy, ld_x, name='wgrad', side=False):
         """dW[n_out, n_in] += dY[M, n_out]^T X[M, n_in]   (fp32 atomic accumulate, split-K)."""
         bn = int(os.environ.get('PIANOBART_B200_WGRAD_BN', '256'))
         pairs = n_out >= 1024 and bn == 256 and os.environ.get('PIANOBART_B200_CG2', '1') != '0'   # library's cta_group::2 rule
         split = choose_split_k(n_out, n_in, M, bn, pairs, _num_sms())
         self.gemm(dy, x, dw, n_out, n_in, M, ld_dy, ld_x, n_in, a_mn=1, b_mn=1,
                   flags=L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC, split_k=split, block_n=bn, name=name)
+        # Measured (profiles/r2_summary.md section 8): running the weight-gradient GEMMs next to the critical chain is SLOWER
+        # (29.5 vs 29.1 ms per step) - two persistent tcgen05 kernels interleaving their CTAs lose more in L2 / shared-memory
+        # locality than the filled ramps and tails give back under the power cap - so it stays an opt-in experiment.
+        if side and os.environ.get('PIANOBART_B200_SIDE_WGRAD', '0') == '1':
+            self._side_names.add(name)
 
     def embed_fwd(self, ids, table, out, M, ntok_arr, err=0):
         self._add('embed_fwd', self.lib.pb_octuple_embed_fwd, C.c_void_p(ids), 0, C.c_void_p(table), C.c_void_p(out),
@@ -468,7 +475,7 @@ class BackboneGraph:
         if self.with_heads:
             self.dlogits = self.buf('dlogits', Mo, VOCAB)
             bw.colsum(_ptr(self.dlogits), self.G('heads.b'), Mo, VOCAB, VOCAB)
-            bw.wgrad(_ptr(self.dlogits), _ptr(self.out), self.G('heads.w'), VOCAB, d, Mo, VOCAB, d, name='dW_heads')
+            bw.wgrad(_ptr(self.dlogits), _ptr(self.out), self.G('heads.w'), VOCAB, d, Mo, VOCAB, d, name='dW_heads', side=True)
             bw.gemm(_ptr(self.dlogits), self.W('heads.w'), _ptr(self.d_out), Mo, d, VOCAB, VOCAB, d, d, b_mn=1,
                     name='dH_heads')
             bw.marker('grads_final', *self.lay.ranges['heads'])
@@ -632,15 +639,16 @@ class BackboneGraph:
                 lp = r['lp']
                 ln = lambda s: '%s.L%d.%s' % (side, l, s)
                 # -- FFN backward
+                bw.join_side()     # (the LayerNorm backward rewrites dAd, which side-stream weight gradients read)
                 bw.ln_bwd(_ptr(dcur), _ptr(r['A2']), self.Pf(lp + '.final_layer_norm.weight'), _ptr(r['st2']),
                           _ptr(r['st2'], M), _ptr(dA), self.G(lp + '.final_layer_norm.weight'),
                           self.G(lp + '.final_layer_norm.bias'), M, d, dbias=self.G(lp + '.fc2.bias'),
                           dx_drop=_ptr(dAd), out_drop=self.site(side, l, 3))
-                bw.wgrad(_ptr(dAd), _ptr(r['G']), self.G(lp + '.fc2.weight'), d, F, M, d, F, name=ln('dW_fc2'))
+                bw.wgrad(_ptr(dAd), _ptr(r['G']), self.G(lp + '.fc2.weight'), d, F, M, d, F, name=ln('dW_fc2'), side=True)
                 bw.gemm(_ptr(dAd), self.W(lp + '.fc2.weight'), _ptr(dZ), M, F, d, d, F, F, b_mn=1,
                         flags=L.PB_GEMM_MUL_AUX, aux=_ptr(r['Z']), ldaux=F, name=ln('dZ'))
                 bw.colsum(_ptr(dZ), self.G(lp + '.fc1.bias'), M, F, F)
-                bw.wgrad(_ptr(dZ), _ptr(r['h_mid']), self.G(lp + '.fc1.weight'), F, d, M, F, d, name=ln('dW_fc1'))
+                bw.wgrad(_ptr(dZ), _ptr(r['h_mid']), self.G(lp + '.fc1.weight'), F, d, M, F, d, name=ln('dW_fc1'), side=True)
                 bw.gemm(_ptr(dZ), self.W(lp + '.fc1.weight'), _ptr(dH1), M, d, F, F, d, d, b_mn=1, residual=_ptr(dA),
                         ldr=d, name=ln('dH_mid'))
                 dmid = dH1
@@ -649,6 +657,7 @@ class BackboneGraph:
                     ca = lp + '.encoder_attn'
                     dQc = self.buf('g.dQc', Mmax, d)
                     dKVc = self.buf('g.dKVc', Mmax, 2 * d)
+                    bw.join_side()
                     bw.ln_bwd(_ptr(dmid), _ptr(r['Ac']), self.Pf(lp + '.encoder_attn_layer_norm.weight'),
                               _ptr(r['stc']), _ptr(r['stc'], M), _ptr(dA), self.G(lp + '.encoder_attn_layer_norm.weight'),
                               self.G(lp + '.encoder_attn_layer_norm.bias'), M, d, dbias=self.G(ca + '.out_proj.bias'),
@@ -662,11 +671,11 @@ class BackboneGraph:
                                  _ptr(r['lse_c']), _ptr(dvec), _ptr(enc_keep), B, H, S, S_enc, hd, 0)
                         akw = dict(dout=_ptr(dO), dq=_ptr(dQc), dk=_ptr(dKVc), dv=_ptr(dKVc, d), lddq=d, lddk=2 * d, lddv=2 * d)
                         bw.attn('prep', *aargs, **akw)
-                        bw.wgrad(_ptr(dAd), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
+                        bw.wgrad(_ptr(dAd), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'), side=True)
                         bw.join_side()
                         bw.attn('main', *aargs, **akw)
                     else:
-                        bw.wgrad(_ptr(dAd), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'))
+                        bw.wgrad(_ptr(dAd), _ptr(r['Oc']), self.G(ca + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_oc'), side=True)
                         bw.gemm(_ptr(dAd), self.W(ca + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dOc'))
                         bw.gemm(_ptr(dO), _ptr(r['KVc'], d), _ptr(scores), S, S_enc, hd, d, 2 * d, S_enc, flags=OUT32,
                                 batch_h=H, batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S_enc * 2 * d, c_sh=S * S_enc,
@@ -682,9 +691,9 @@ class BackboneGraph:
                                 alpha=scale, batch_h=H, batch_b=B, a_sh=S * S_enc, a_sb=H * S * S_enc, b_sh=hd,
                                 b_sb=S * d, c_sh=hd, c_sb=S_enc * 2 * d, name=ln('dK_c'))
                     bw.colsum(_ptr(dQc), self.G(ca + '.q_proj.bias'), M, d, d)
-                    bw.wgrad(_ptr(dQc), _ptr(r['H1']), self.G(ca + '.q_proj.weight'), d, d, M, d, d, name=ln('dW_qc'))
+                    bw.wgrad(_ptr(dQc), _ptr(r['H1']), self.G(ca + '.q_proj.weight'), d, d, M, d, d, name=ln('dW_qc'), side=True)
                     bw.colsum(_ptr(dKVc), self.G(ca + '.bkv'), Me, 2 * d, 2 * d)
-                    bw.wgrad(_ptr(dKVc), _ptr(enc_out), self.G(ca + '.wkv'), 2 * d, d, Me, 2 * d, d, name=ln('dW_kvc'))
+                    bw.wgrad(_ptr(dKVc), _ptr(enc_out), self.G(ca + '.wkv'), 2 * d, d, Me, 2 * d, d, name=ln('dW_kvc'), side=True)
                     bw.gemm(_ptr(dKVc), self.W(ca + '.wkv'), _ptr(d_enc_out), Me, d, 2 * d, 2 * d, d, d, b_mn=1,
                             residual=0 if first_cross else _ptr(d_enc_out), ldr=d, name=ln('dEnc'))
                     first_cross = False
@@ -695,6 +704,7 @@ class BackboneGraph:
                 # -- self attention backward
                 sa = lp + '.self_attn'
                 cz = 1 if is_dec else 0
+                bw.join_side()
                 bw.ln_bwd(_ptr(dmid), _ptr(r['A']), self.Pf(lp + '.self_attn_layer_norm.weight'), _ptr(r['st1']),
                           _ptr(r['st1'], M), _ptr(dA), self.G(lp + '.self_attn_layer_norm.weight'),
                           self.G(lp + '.self_attn_layer_norm.bias'), M, d, dbias=self.G(sa + '.out_proj.bias'),
@@ -708,11 +718,11 @@ class BackboneGraph:
                     akw = dict(dout=_ptr(dO), dq=_ptr(dQKV), dk=_ptr(dQKV, d), dv=_ptr(dQKV, 2 * d), lddq=3 * d, lddk=3 * d,
                                lddv=3 * d)
                     bw.attn('prep', *aargs, **akw)
-                    bw.wgrad(_ptr(dAd), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
+                    bw.wgrad(_ptr(dAd), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'), side=True)
                     bw.join_side()
                     bw.attn('main', *aargs, **akw)
                 else:
-                    bw.wgrad(_ptr(dAd), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'))
+                    bw.wgrad(_ptr(dAd), _ptr(r['O']), self.G(sa + '.out_proj.weight'), d, d, M, d, d, name=ln('dW_o'), side=True)
                     bw.gemm(_ptr(dAd), self.W(sa + '.out_proj.weight'), _ptr(dO), M, d, d, d, d, d, b_mn=1, name=ln('dO'))
                     bw.gemm(_ptr(dO), _ptr(QKV, 2 * d), _ptr(scores), S, S, hd, d, 3 * d, S, flags=OUT32, batch_h=H,
                             batch_b=B, a_sh=hd, a_sb=S * d, b_sh=hd, b_sb=S * 3 * d, c_sh=S * S, c_sb=H * S * S, causal=cz,
@@ -728,13 +738,14 @@ class BackboneGraph:
                             batch_h=H, batch_b=B, a_sh=S * S, a_sb=H * S * S, b_sh=hd, b_sb=S * 3 * d, c_sh=hd,
                             c_sb=S * 3 * d, name=ln('dK'))
                 bw.colsum(_ptr(dQKV), self.G(sa + '.bqkv'), M, 3 * d, 3 * d)
-                bw.wgrad(_ptr(dQKV), _ptr(r['h_in']), self.G(sa + '.wqkv'), 3 * d, d, M, 3 * d, d, name=ln('dW_qkv'))
+                bw.wgrad(_ptr(dQKV), _ptr(r['h_in']), self.G(sa + '.wqkv'), 3 * d, d, M, 3 * d, d, name=ln('dW_qkv'), side=True)
                 bw.gemm(_ptr(dQKV), self.W(sa + '.wqkv'), _ptr(dnext), M, d, 3 * d, 3 * d, d, d, b_mn=1,
                         residual=_ptr(dA), ldr=d, name=ln('dH_in'))
                 dcur, dnext = dnext, dcur
                 bw.marker('grads_final', *self.lay.ranges['%s.layers.%d' % (side, l)])
             # -- front end backward
             dY0 = dA
+            bw.join_side()
             bw.ln_bwd(_ptr(dcur), _ptr(Y0), self.Pf(pre + '.layernorm_embedding.weight'), _ptr(st0), _ptr(st0, M),
                       _ptr(dY0), self.G(pre + '.layernorm_embedding.weight'), self.G(pre + '.layernorm_embedding.bias'),
                       M, d, dbias=0 if custom_dec else self.G('encoder_linear.bias'), in_drop=self.site(side, -1, 0))
@@ -743,7 +754,7 @@ class BackboneGraph:
             if not custom_dec:
                 onehot = self.buf('g.onehot', Mmax, VOCAB)
                 bw.onehot(_ptr(ids), _ptr(onehot), M, self.ntok_arr)
-                bw.wgrad(_ptr(onehot), _ptr(dY0), _ptr(self.Gacc), VOCAB, d, M, VOCAB, d, name=nm('dG'))
+                bw.wgrad(_ptr(onehot), _ptr(dY0), _ptr(self.Gacc), VOCAB, d, M, VOCAB, d, name=nm('dG'), side=True)
             else:
                 self.d_dec_in = dY0      # gradient wrt the caller's decoder input embeddings
             bw.marker('grads_final', *self.lay.ranges['%s.front' % side])

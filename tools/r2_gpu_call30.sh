@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+nvidia-smi -L
+( timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5 ) > gpurun_out/r2_pytest_2gpu_b.log 2>&1
+cat gpurun_out/r2_pytest_2gpu_b.log
+( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 40 --warmup 5 --no-cpu-baseline --no-decode ) > gpurun_out/r2_bench_2gpu_b.log 2>&1
+tail -1 gpurun_out/r2_bench_2gpu_b.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['achieved'], d['clocks'])"
+( timeout 600 python bench.py --gpus 1 --steps 40 --warmup 5 --no-cpu-baseline --no-decode ) > gpurun_out/r2_bench_1gpu_b.log 2>&1
+tail -1 gpurun_out/r2_bench_1gpu_b.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['achieved'], d['clocks'])"
