@@ -130,7 +130,9 @@ class PretrainStep:
         self.loss_mask = torch.empty(M * 8, dtype=torch.float32, device=dev)
         # stats: [0:8] loss numerators, [8:16] correct counts, [16:24] mask sums (denominators)
         self.stats = torch.zeros(24, dtype=torch.float32, device=dev)
-        self.h_stats = torch.zeros(24, dtype=torch.float32).pin_memory()
+        self.h_stats2 = [torch.zeros(24, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._stats_ev = [torch.cuda.Event() for _ in range(2)]
+        self._stats_slot = 0
         self.pad = (C.c_int * 8)(*[int(x) for x in pb.pad_word_np])
         self.mask = (C.c_int * 8)(*[int(x) for x in pb.mask_word_np])
         self.sos = (C.c_int * 8)(*[int(x) for x in pb.sos_word_np])
@@ -244,22 +246,35 @@ class PretrainStep:
         self.launches += n
         return n
 
-    def fetch_stats(self):
-        """D2H of the 24 step scalars; returns (total_loss, losses[8], accs[8]) like pretrain.py:171-189."""
+    def queue_stats(self):
+        """Queues the D2H copy of the step's 24 scalars (behind the step, on the current stream) into one of two pinned
+        slots and returns a ticket for collect_stats(): the trainer reads step i back only after step i + 1 has been
+        launched, so the device never idles between steps waiting for the host."""
         st = self.stats
         if self.world > 1:
             import torch.distributed as dist
             st = self.stats.clone()
             dist.all_reduce(st[0:16], group=self.pg)
-        self.h_stats.copy_(st, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        v = self.h_stats.numpy().astype(np.float64)
+        k = self._stats_slot
+        self._stats_slot ^= 1
+        self.h_stats2[k].copy_(st, non_blocking=True)
+        self._stats_ev[k].record()
+        return k
+
+    def collect_stats(self, ticket):
+        """-> (total_loss, losses[8], accs[8]) like pretrain.py:171-189, for the step queue_stats() was called after."""
+        self._stats_ev[ticket].synchronize()
+        v = self.h_stats2[ticket].numpy().astype(np.float64)
         num, cor, den = v[0:8], v[8:16], v[16:24]
         with np.errstate(divide='ignore', invalid='ignore'):
             losses = num / den
             accs = cor / den
         total = float(np.sum(losses * np.array(self.loss_weights)) / self.loss_norm)
         return total, losses, accs
+
+    def fetch_stats(self):
+        """D2H of the 24 step scalars + synchronisation; returns (total_loss, losses[8], accs[8])."""
+        return self.collect_stats(self.queue_stats())
 
 
 class PlanPrefetcher:
@@ -405,21 +420,31 @@ class Pretrainer:
             st = self._step(ori.shape[0], ori.shape[1])
             st.upload(ori, plan=plan)
             return st
-        st = stage(next(it, None))
-        while st is not None:
-            st.noise()
-            st.run(train=train)
-            # one step ahead: the next batch (its plan was drawn by the prefetch thread) is staged and its H2D copies
-            # are queued while the GPU still executes this step; only then the step's scalars are read back (sync)
-            nxt = stage(next(it, None))
-            total, losses, accs = st.fetch_stats()
+        def collect(pending):
+            nonlocal total_losses, total_acc, nb
+            total, losses, accs = pending[0].collect_stats(pending[1])
             if self.verbose:
                 sys.stdout.write('Loss: {:06f} | loss: {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}\n'.format(total, *losses))
                 sys.stdout.write('Acc: {:06f} | acc: {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}, {:03f}\n'.format(np.average(accs), *accs))
             total_losses += total
             total_acc += accs
             nb += 1
-            st = nxt
+        st = stage(next(it, None))
+        pending = None
+        while st is not None:
+            st.noise()
+            st.run(train=train)
+            ticket = st.queue_stats()
+            # Software pipeline, two steps deep: step i is on the device; the host now reads back the scalars of step i - 1
+            # (its wait ends while step i still runs, so the device never idles between steps), then stages batch i + 1 (plan
+            # drawn by the prefetch thread; the pinned set it reuses was last read by the copies of batch i - 1, complete by
+            # then) and queues its H2D copies behind step i.
+            if pending is not None:
+                collect(pending)
+            pending = (st, ticket)
+            st = stage(next(it, None))
+        if pending is not None:
+            collect(pending)
         nb = max(nb, 1)
         return round(total_losses / nb, 3), [round(float(x) / nb, 3) for x in total_acc]
 
