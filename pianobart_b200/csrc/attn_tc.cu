@@ -11,13 +11,13 @@
 // P, dS (and their transposes) never touch shared memory: the softmax warps write them back (bf16, packed) over the
 // TMEM columns of the S / dP values they were derived from, and the next MMA reads them as its A operand from TMEM.
 //
-//   attn_fwd     CTA = (b, h, 128 queries)  loop over 128-key blocks:  S=QK^T -> online softmax -> O += P V ; LSE out
+//   attn_fwd3    CTA = (b, h, 2 x 128 queries) loop over 128-key blocks: S=QK^T -> online softmax -> O += P V ; LSE out
+//                (the production forward kernel; attn_fwd is its one-tile predecessor, PIANOBART_B200_ATTN_FWD=1)
 //   attn_bwd_dkv CTA = (b, h, 128 keys)     loop over 64-query blocks: S^T, dP^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q
 //   attn_bwd_dq  CTA = (b, h, 128 queries)  loop over 128-key blocks:  S, dP -> dS -> dQ += dS K
 //   attn_bwd_prep                           D = rowsum(dO * O)
-// Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax / epilogue:
-// thread <-> (TMEM lane = tile row, 64-column half), two warps per scheduler so that the dependent ALU chains of
-// one warp hide behind the other (a single warp per scheduler left the kernel latency-bound, profiles/).
+// Warp roles per CTA of the backward kernels and attn_fwd (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9
+// softmax / epilogue: thread <-> (TMEM lane = tile row, 64-column half), two warps per scheduler.
 // Measured facts the pipelines are built around (tools/micro/mma_bench.cu, -DPB_TRACE phase traces): one tcgen05.mma
 // (M=128, K=16) holds the tensor pipe for max(~72, N/2) cycles whatever the operand source; a TMA tile refill takes
 // 1500-2300 cycles under load; the MUFU pipe (ex2) is what bounds the softmax.  Outputs leave through bulk tensor
@@ -502,223 +502,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
   if (threadIdx.x == 64) PB_TR(0, 63, 4);
-}
-
-// ===================================================================================== forward, two CTAs per SM
-// Same arithmetic as attn_fwd_kernel with the opposite trade: every resource is single-buffered (Q, one K tile, one V tile =
-// 96 KB of shared memory; S/P + O = 256 TMEM columns; 192 threads) so that TWO CTAs are resident per SM, and the overlap of
-// tensor pipe, MUFU pipe and TMA comes from the two CTAs running out of phase instead of from look-ahead inside one CTA:
-// while one CTA's softmax warps exponentiate block j (MUFU-bound, ~1000 cycles per 128 x 128 block) the other CTA's S / P V
-// products own the tensor pipe, and a CTA's prologue (Q / K TMA latency, key bitmap) and epilogue (O store) hide behind its
-// neighbour's steady state - a one-tile CTA of the look-ahead kernel spends a third of its life there (profiles/r1_summary).
-// A softmax thread owns a whole row (4 warps, no row-max exchange between threads).  Within a CTA every barrier alternates
-// strictly (S(j) -> softmax(j) -> P V(j) -> S(j+1), in-order tensor pipe), so no parity wait can alias a later phase:
-// s_full(j) is committed after P V(j-1), which is why the O rescale needs no barrier of its own.
-constexpr int F2_THREADS = 64 + 128;
-
-__global__ void __launch_bounds__(F2_THREADS, 2)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
-                 const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  if (threadIdx.x == 64) PB_TR(0, 63, 0);
-  __shared__ __align__(8) uint64_t q_full, k_full, k_empty, v_full, v_empty, s_full, p_full, o_full, mma_drain;
-  __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t s_keep[FWD_MAX_SK / 32];
-  Smem4 sm;
-  carve(smem_raw, sm, 3);  // 0 Q, 1 K, 2 V
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qb * AT;
-  int nkb = (p.Sk + AT - 1) / AT;
-  if (p.causal) nkb = min(nkb, qb + 1);
-
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); }
-  if (warp == 1 && lane == 0) {
-    mbar_init(&q_full, 1); mbar_init(&k_full, 1); mbar_init(&k_empty, 1); mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
-    mbar_init(&s_full, 1); mbar_init(&p_full, 128); mbar_init(&o_full, 1); mbar_init(&mma_drain, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
-  pdl_launch_dependents();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  pdl_wait();
-  if (threadIdx.x == 64) PB_TR(0, 63, 1);
-  const uint32_t tmem = tmem_base_smem;
-  const uint32_t tS = tmem, tO = tmem + AT;
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(&q_full, TILE_BYTES);
-      load_tile(sm.t[0], &tq, &q_full, q0, h, b);
-      // release order of the slots is K(j) [after S(j-1)], V(j) [after P V(j-1)], K(j+1) [after S(j)], ...: one thread
-      // waiting in that order never holds a ready load back
-      for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&k_empty, ((uint32_t)j & 1) ^ 1);
-        chaos_delay(p.dbg_delay >> 2, 2 * j);
-        mbar_expect_tx(&k_full, TILE_BYTES);
-        load_tile(sm.t[1], &tk, &k_full, j * AT, h, b);
-        mbar_wait(&v_empty, ((uint32_t)j & 1) ^ 1);
-        chaos_delay(p.dbg_delay, 2 * j + 1);
-        mbar_expect_tx(&v_full, TILE_BYTES);
-        load_tile(sm.t[2], &tv, &v_full, j * AT, h, b);
-      }
-      // producer tail
-      mbar_wait(&k_empty, ((uint32_t)nkb & 1) ^ 1);
-      mbar_wait(&v_empty, ((uint32_t)nkb & 1) ^ 1);
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc_pv = make_idesc_bf16(AT, AT, 0, 1);
-      mbar_wait(&q_full, 0);
-      for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&k_full, (uint32_t)j & 1);
-        tc_fence_after();
-        PB_TR(0, j, 0);
-        // S(j) overwrites P(j-1): P V(j-1) precedes it in the in-order tensor pipe
-        mma_tile<false, false>(tS, sm.a[0], sm.a[1], false);
-        umma_commit(&s_full);
-        umma_commit(&k_empty);
-        PB_TR(0, j, 1);
-        mbar_wait(&p_full, (uint32_t)j & 1);
-        mbar_wait(&v_full, (uint32_t)j & 1);
-        tc_fence_after();
-        PB_TR(0, j, 2);
-        // O += P V: A = P from TMEM (packed bf16, 64 columns), B = V tile as MN-major operand
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_ts(tO, tS + kk * 8, desc_mnmajor(sm.a[2], kk), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&v_empty);
-        PB_TR(0, j, 3);
-      }
-      umma_commit(&o_full);
-      umma_commit(&mma_drain);
-      mbar_wait(&mma_drain, 0);
-    }
-  } else {
-    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-    const int r = quad * 32 + lane;          // tile row = TMEM lane
-    const int tid = threadIdx.x - 64;        // 0..127
-    const int qg = q0 + r;
-    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const float sl2 = p.scale * LOG2E;
-    const bool causal = p.causal != 0;
-    float m_used = -INFINITY, l = 0.f;
-    const int trole = (lane == 0 && (warp == 2 || warp == 4)) ? (warp == 2 ? 1 : 2) : -1;
-    for (int k0 = 0; k0 < nkb * AT; k0 += 128) {
-      const int kc = k0 + tid;
-      bool kp = kc < p.Sk;
-      if (kp && p.key_keep) kp = p.key_keep[(long long)b * p.Sk + kc] != 0;
-      const uint32_t w = __ballot_sync(0xffffffffu, kp);
-      if (lane == 0) s_keep[kc >> 5] = w;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int j = 0; j < nkb; ++j) {
-      uint32_t msk[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) msk[c] = chunk_mask(s_keep[j * 4 + c], causal, qg, j * AT + c * 32);
-      if (trole > 0) PB_TR(trole, j, 0);
-      mbar_wait(&s_full, (uint32_t)j & 1);
-      tc_fence_after();
-      if (trole > 0) PB_TR(trole, j, 1);
-      // pass 1: masked row maximum
-      float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        if (msk[c] == 0xffffffffu) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) { bm0 = fmaxf(bm0, __uint_as_float(v[i])); bm1 = fmaxf(bm1, __uint_as_float(v[i + 1])); }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            bm0 = fmaxf(bm0, ((msk[c] >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
-            bm1 = fmaxf(bm1, ((msk[c] >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : -INFINITY);
-          }
-        }
-      }
-      const float m_blk = fmaxf(bm0, bm1) * sl2;
-      if (trole > 0) PB_TR(trole, j, 2);
-      // lazy rescale: keep the old reference unless the maximum grew by more than 2^8
-      float f = 1.0f;
-      bool need = false;
-      if (m_used == -INFINITY) {
-        m_used = m_blk;
-      } else if (m_blk > m_used + RESCALE_THRESHOLD) {
-        f = ex2(m_used - m_blk);
-        m_used = m_blk;
-        need = true;
-      }
-      if (__any_sync(0xffffffffu, need)) {     // (P V(j-1) has retired: s_full(j) was committed after it)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tO + lane_addr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-          tmem_st32(tO + lane_addr + c * 32, v);
-        }
-        l *= f;
-      }
-      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
-      if (trole > 0) PB_TR(trole, j, 3);
-      // pass 2: exponentials; P chunk c (32 keys = 16 packed columns) lands on S columns already consumed
-      float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld32(tS + lane_addr + c * 32, sv);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        const bool all = msk[c] == 0xffffffffu;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x0 = __uint_as_float(sv[2 * i]), x1 = __uint_as_float(sv[2 * i + 1]);
-          if (!all) {
-            x0 = ((msk[c] >> (2 * i)) & 1u) ? x0 : -INFINITY;
-            x1 = ((msk[c] >> (2 * i + 1)) & 1u) ? x1 : -INFINITY;
-          }
-          const float e0 = ex2(fmaf(x0, sl2, neg_m)), e1 = ex2(fmaf(x1, sl2, neg_m));
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
-          rs0 += e0;
-          rs1 += e1;
-        }
-        tmem_st16(tS + lane_addr + c * 16, pk);
-      }
-      l += rs0 + rs1;
-      tmem_st_wait();
-      if (trole > 0) PB_TR(trole, j, 4);
-      tc_fence_before();
-      mbar_arrive(&p_full);
-      if (trole > 0) PB_TR(trole, j, 5);
-    }
-    mbar_wait(&o_full, 0);
-    tc_fence_after();
-    if (threadIdx.x == 64) PB_TR(0, 63, 2);
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    // O rows -> the Q tile (every S MMA has retired) -> two bulk tensor stores
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tO + lane_addr + c * 32, v);
-      tmem_ld_wait();
-      stage_row_chunk(sm.t[0], r, c >> 1, c & 1, v, inv);
-    }
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (tid == 0) { store_tile_tma(&to, sm.t[0], q0, h, b); bulk_wait_read<0>(); }
-    if (qg < p.Sq) p.lse[((long long)b * p.H + h) * p.Sq + qg] = (l > 0.f) ? (m_used + log2f(l)) : INFINITY;
-    if (threadIdx.x == 64) PB_TR(0, 63, 3);
-    tc_fence_before();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 256);
 }
 
 // ===================================================================================== forward, two Q tiles per CTA
@@ -1567,7 +1350,8 @@ extern "C" int pb_attn_fwd(const pb_attn_desc* d, void* stream_) {
   AttnParams p;
   fill_params(p, d);
   dim3 grid((d->Sq + AT - 1) / AT, d->H, d->B);
-  // PIANOBART_B200_ATTN_FWD: 3 (default) two Q tiles per CTA; 2 single-buffered CTAs, two per SM; 1 one-tile look-ahead kernel
+  // PIANOBART_B200_ATTN_FWD: 3 (default) two Q tiles per CTA; 1 the round-1 one-tile look-ahead kernel (kept as the baseline of
+  // profiles/r2_summary.md section 7 and for tools/attn_late_tile_demo.py)
   static const int variant = []() { const char* e = getenv("PIANOBART_B200_ATTN_FWD"); return e ? atoi(e) : 3; }();
   if (variant == 3) {
     static bool attr3 = false;
@@ -1576,18 +1360,6 @@ extern "C" int pb_attn_fwd(const pb_attn_desc* d, void* stream_) {
     dim3 grid3((d->Sq + 2 * AT - 1) / (2 * AT), d->H, d->B);
     PB_LAUNCH(attn_fwd3_kernel, grid3, F3_THREADS, smem3, stream, tq, tk, tv, to, p);
     return pb_check_launch("attn_fwd3_kernel");
-  }
-  if (variant == 2) {
-    // single-buffered CTAs, two resident per SM (96 KB of shared memory and 256 TMEM columns each)
-    static bool attr2 = false;
-    const int smem2 = 3 * TILE_BYTES + 1024;
-    if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      if (e != cudaSuccess) return pb_set_cuda_error("cudaFuncSetAttribute(attn_fwd2 carveout)", e);
-    }
-    if (set_smem(attn_fwd2_kernel, smem2, attr2)) return -1;
-    PB_LAUNCH(attn_fwd2_kernel, grid, F2_THREADS, smem2, stream, tq, tk, tv, to, p);
-    return pb_check_launch("attn_fwd2_kernel");
   }
   static bool attr = false;
   const int smem = 6 * TILE_BYTES + 1024;

@@ -14,7 +14,7 @@ nb = 8
 print('MMA thread (two-tile kernel): [loop top, P_a + V ok, PV_a + S_a(j+1) issued, P_b ok, PV_b + S_b(j+1) issued]   (cycles since CTA entry)')
 for j in range(nb):
     print(j, [int(x - t0) if x > 0 else -1 for x in t[0, j, :5]])
-for role in (1, 2):
+for role in (1, 2):  # (fwd4: warps 2 and 10)
     print('softmax warp %d: [loop top, s_full ok, pass 1 done, rescale done, pass 2 done, arrived]' % role)
     for j in range(nb):
         print(j, [int(x - t0) if x > 0 else -1 for x in t[role, j, :6]])
