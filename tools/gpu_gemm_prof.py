@@ -41,7 +41,7 @@ def main():
         step.run(train=True, profile=prof)
         torch.cuda.synchronize()
         for name, flops, e0, e1 in prof:
-            key = re.sub(r'\d+', '#', name)
+            key = re.sub(r'L\d+', 'L#', name)
             a = agg[key]
             a[0] += 1; a[1] += flops; a[2] += e0.elapsed_time(e1)
     rows = sorted(agg.items(), key=lambda kv: -kv[1][2])
