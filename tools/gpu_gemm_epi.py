@@ -71,3 +71,7 @@ case('out_proj bn=256 no pairs', 1024, 1024, bias=True, drop=True, res=True, blo
 case('fc1 N=2048: bias+gelu+dgelu', 2048, 1024, bias=True, flags=L.PB_GEMM_GELU | L.PB_GEMM_AUX_DGELU, aux=True)
 case('fc2 K=2048: bias+dropout+residual', 1024, 2048, bias=True, drop=True, res=True)
 case('fc2 K=2048 bn=128', 1024, 2048, bias=True, drop=True, res=True, block_n=128)
+case('plain N=2048', 2048, 1024)
+case('bias N=2048', 2048, 1024, bias=True)
+case('N=2048: bias+gelu (no second output)', 2048, 1024, bias=True, flags=L.PB_GEMM_GELU)
+case('N=2048: bias+preact aux store only', 2048, 1024, bias=True, flags=L.PB_GEMM_AUX_PREACT, aux=True)
