@@ -30,6 +30,7 @@ class Generator:
         if pb.pb_dtype != E.PB_BF16:
             raise L.PBError('KV-cache decode is implemented for the bf16 production mode only')
         self.lm, self.pb = lm, pb
+        self._pack_gen = pb._pack_gen
         self.B, self.Se = B, S_enc
         self.S = S_max or S_enc
         self.use_graph = use_graph
@@ -360,6 +361,7 @@ class Generator:
     # ------------------------------------------------------------------
     def start(self, input_ids_encoder, encoder_attention_mask, uniforms=None, forced=None):
         pb = self.pb
+        pb.check_pack_generation(self._pack_gen, 'Generator')
         pb._sync_weights()
         pb._live_graph = None
         if (forced is None) != (self.forced is None) or forced is not None:
@@ -443,7 +445,8 @@ def generate(lm, input_ids_encoder, encoder_attention_mask=None, check_every=32)
     """Drop-in for `PianoBartLM.forward(..., generate=True)`; consumes numpy's global RNG like the reference
     (8 uniforms per executed step, attribute order)."""
     B, S = input_ids_encoder.shape[0], input_ids_encoder.shape[1]
-    key = (id(lm), B, S)
+    lm.pianobart._ensure_packed()
+    key = (id(lm), B, S, lm.pianobart._pack_gen)
     gen = _GEN_CACHE.get(key)
     if gen is None:
         _GEN_CACHE.clear()

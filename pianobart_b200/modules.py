@@ -193,6 +193,7 @@ class PianoBart(nn.Module):
         self._wver = None
         self._anchor = None
         self._drop_seed = None
+        self._pack_gen = 0      # bumped by every _repack(): objects holding raw pointers into the buffers check it
 
     # ------------------------------------------------------------------ flat storage
     def _named_flat_params(self):
@@ -219,6 +220,15 @@ class PianoBart(nn.Module):
         self._live_graph = None
         self._wver = None
         self._anchor = torch.zeros(1, device=device, requires_grad=True)
+        self._pack_gen += 1
+
+    def check_pack_generation(self, gen, what):
+        """Launch plans record raw device pointers into the flat buffers: an object built before the module was moved
+        (.to / .cuda / .float) or before extra parameters were attached must not run on the old memory."""
+        self._ensure_packed()
+        if gen != self._pack_gen:
+            raise L.PBError('%s was built for an earlier layout of the parameter buffers (the module was moved or re-packed '
+                            'since); build a new one' % what)
 
     def _apply(self, fn, *a, **kw):
         r = super()._apply(fn, *a, **kw)

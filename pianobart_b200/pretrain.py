@@ -108,6 +108,7 @@ class PretrainStep:
         self.dev = dev
         self.lib = L.lib()
         self.graph = pb._graph(B, S, S, True, True, dropout)
+        self._pack_gen = pb._pack_gen
         # north-star fusion 3 (bf16 mode): MLM heads + masked CE in one kernel (csrc/heads_ce_tc.cu)
         self.fused_ce = (pb.pb_dtype == E.PB_BF16 and self.graph.d % 64 == 0
                          and os.environ.get('PIANOBART_B200_FUSED_CE', '1') != '0')
@@ -196,6 +197,7 @@ class PretrainStep:
         g, lib, s = self.graph, self.lib, L.stream_ptr()
         pb = self.pb
         P = C.c_void_p
+        pb.check_pack_generation(self._pack_gen, 'PretrainStep')
         pb._sync_weights()
         pb._live_graph = None  # the fused step owns the graph buffers; autograd must not reuse them
         self.stats.zero_()

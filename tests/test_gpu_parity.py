@@ -607,3 +607,51 @@ def test_training_mode_dropout_matches_oracle_with_same_masks():
     st.run(train=True)
     total2, _, _ = st.fetch_stats()
     assert abs(total2 - total) > 1e-6
+
+
+def test_objects_built_before_a_repack_refuse_to_run():
+    """A launch plan holds raw pointers into the flat parameter buffers; moving / re-packing the module afterwards must be
+    detected, not silently run on freed memory (advisor finding, generate.py / pretrain.py)."""
+    from oracle import params as P
+    from pianobart_b200 import _lib as L
+    from pianobart_b200.pretrain import FusedAdamW, PretrainStep
+    cfg = (64, 2, 2, 4, 128, 32)
+    pb, lm = build_cuda_model(cfg, 3, 'bf16')
+    step = PretrainStep(lm, 2, 32, FusedAdamW(pb, lr=1e-4), 0.15)
+    random.seed(1); np.random.seed(1)
+    step.upload(P.synth_ids(2, 32, 11, padded=True))
+    step.noise()
+    step.run(train=True)
+    lm.float()                      # nn.Module._apply: storage may move -> the next use re-packs the flat buffers
+    with pytest.raises(L.PBError, match='earlier layout'):
+        step.run(train=True)
+    step2 = PretrainStep(lm, 2, 32, FusedAdamW(pb, lr=1e-4), 0.15)
+    step2.upload(P.synth_ids(2, 32, 11, padded=True))
+    step2.noise()
+    step2.run(train=True)
+    assert np.isfinite(step2.fetch_stats()[0])
+
+
+def test_side_stream_work_is_transparent(monkeypatch):
+    """Bias-gradient column sums, D = rowsum(dO*O) and the gradient zeroing run on a side stream (engine.Plan.run): the
+    gradients of a training step must not depend on it (same masks, same inputs; fp32 atomics reorder sums only)."""
+    from oracle import params as P
+    from pianobart_b200.pretrain import PretrainStep
+    cfg = (128, 2, 2, 1, 256, 64)          # head_dim 128: the tcgen05 attention path incl. the split backward
+    grads = []
+    for side in ('1', '0'):
+        monkeypatch.setenv('PIANOBART_B200_SIDE_COLSUM', side)
+        pb, lm = build_cuda_model(cfg, 7, 'bf16', dropout=0.1)
+        lm.train()
+        torch.manual_seed(5)
+        pb._drop_seed = None
+        step = PretrainStep(lm, 2, 64, None, 0.15)
+        random.seed(2); np.random.seed(2)
+        step.upload(P.synth_ids(2, 64, 21, padded=True))
+        for _ in range(3):                 # repeated runs: the zeroing of step i + 1 must wait for the readers of step i
+            step.noise()
+            step.run(train=True)
+        torch.cuda.synchronize()
+        grads.append(pb._grad.detach().clone())
+    scale = float(grads[1].abs().max())
+    assert float((grads[0] - grads[1]).abs().max()) <= 2e-5 * scale
