@@ -1,5 +1,5 @@
 import ctypes as C, sys, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pianobart_b200 import _lib as L
 lib = L.lib(); dev = 'cuda:0'
