@@ -744,7 +744,9 @@ class BackboneGraph:
                 dcur, dnext = dnext, dcur
                 bw.marker('grads_final', *self.lay.ranges['%s.layers.%d' % (side, l)])
             # -- front end backward
-            dY0 = dA
+            # (the gradient wrt caller-provided decoder input embeddings outlives this stream's backward: it gets its own
+            # buffer - the shared scratch dA is rewritten by the encoder stream's backward that follows)
+            dY0 = self.buf('g.d_dec_in', M, d) if custom_dec else dA
             bw.join_side()
             bw.ln_bwd(_ptr(dcur), _ptr(Y0), self.Pf(pre + '.layernorm_embedding.weight'), _ptr(st0), _ptr(st0, M),
                       _ptr(dY0), self.G(pre + '.layernorm_embedding.weight'), self.G(pre + '.layernorm_embedding.bias'),

@@ -64,7 +64,7 @@ def test_token_classification_matches_reference(cn):
 
 
 @pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
-@pytest.mark.parametrize('task', ['seqcls', 'tokcls4'])
+@pytest.mark.parametrize('task', ['seqcls', 'tokcls4', 'tokcls8'])
 def test_finetune_training_gradients_match_reference(task, dtype):
     """Rows A14 / A15: loss and gradients of one finetune step (backbone through the kernel path, head parameters included)
     against the executed reference (cls_tiny.npz: reference SequenceClassification / TokenClassification + the loss of
@@ -82,6 +82,21 @@ def test_finetune_training_gradients_match_reference(task, dtype):
         m.eval()
         y = torch.from_numpy(g['seqcls_labels']).cuda()
         loss = torch.nn.functional.cross_entropy(m(ids, mask), y, reduction='none').sum() / ids.shape[0]
+    elif task == 'tokcls8':
+        # class_num >= 5: label embedding + decoder_linear replace the decoder front end (finetune.py:194-198); the gradient
+        # wrt those decoder input embeddings leaves the backbone through its own buffer
+        m = TokenClassification(pb, class_num=8, hs=d).cuda()
+        _load_extra(m, 'tokcls8.', ['classifier.1.weight', 'classifier.1.bias', 'classifier.3.weight', 'classifier.3.bias',
+                                    'pianobart.decoder_emb.lut.weight', 'pianobart.decoder_linear.weight',
+                                    'pianobart.decoder_linear.bias'], 9)
+        m.eval()
+        y = torch.from_numpy(g['tokcls8_labels']).cuda()
+        y_shift = torch.from_numpy(g['tokcls8_dec_in'].astype(np.int64)).cuda()
+        attn_shift = torch.zeros_like(mask)
+        attn_shift[:, 1:] = mask[:, :-1]
+        attn_shift[:, 0] = mask[:, 0]
+        lg = m(ids, y_shift, mask, attn_shift)
+        loss = (torch.nn.functional.cross_entropy(lg.permute(0, 2, 1), y, reduction='none') * mask).sum() / mask.sum()
     else:
         m = TokenClassification(pb, class_num=4, hs=d).cuda()
         _load_extra(m, 'tokcls4.', ['classifier.1.weight', 'classifier.1.bias', 'classifier.3.weight', 'classifier.3.bias'], 9)
@@ -107,6 +122,75 @@ def test_finetune_training_gradients_match_reference(task, dtype):
                 assert cos > 0.99 and _rel(got, want) < 0.2, (name, cos, _rel(got, want))
             n += 1
     assert n >= 8
+
+
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+@pytest.mark.parametrize('task', ['seqcls', 'tokcls8'])
+def test_default_model_finetune_step_matches_reference(task, dtype):
+    """BASELINE configs[3] / [4] at the default model size (d 1024, 8 + 8 layers, S 1024, batch 2): logits, loss and
+    gradients of the composer sequence task (8 classes) and the velocity token task (class_num 8: label embedding +
+    decoder_linear as the decoder front end, shifted labels, finetune.py:194-198) against the executed reference
+    (tests/golden/cls_default.npz, tools/make_golden.py::golden_cls_default) - the trainer's own loss path
+    (FinetuneTrainer._loss -> pb_heads_ce) included."""
+    from pianobart_b200 import heads
+    from pianobart_b200.modules import SequenceClassification, TokenClassification
+    g = load_golden('cls_default')
+    d = int(g['cfg'][0])
+    pb, _ = build_cuda_model(g['cfg'], int(g['seed']), dtype, lm=False)
+    ids = torch.from_numpy(g['ids'].astype(np.int64)).cuda()
+    mask = (ids[:, :, 0] != pb.bar_pad_word).float()
+    if task == 'seqcls':
+        m = SequenceClassification(pb, class_num=8, hs=d).cuda()
+        _load_extra(m, 'seqcls.', ['attention.ws1.weight', 'attention.ws2.weight', 'classifier.1.weight', 'classifier.1.bias',
+                                   'classifier.3.weight', 'classifier.3.bias'], 12)
+        m.eval()
+        y = torch.from_numpy(g['seqcls_labels']).cuda()
+        logits = m(ids, mask)
+        loss, correct, am = heads.masked_ce(logits, y, None)
+        want_logits, got_logits = g['seqcls_logits'], logits.detach().cpu().numpy()
+    else:
+        m = TokenClassification(pb, class_num=8, hs=d).cuda()
+        _load_extra(m, 'tokcls8.', ['classifier.1.weight', 'classifier.1.bias', 'classifier.3.weight', 'classifier.3.bias',
+                                    'pianobart.decoder_emb.lut.weight', 'pianobart.decoder_linear.weight',
+                                    'pianobart.decoder_linear.bias'], 12)
+        m.eval()
+        y = torch.from_numpy(g['tokcls8_labels'].astype(np.int64)).cuda()
+        y_shift = torch.from_numpy(g['tokcls8_dec_in'].astype(np.int64)).cuda()
+        attn_shift = torch.zeros_like(mask)
+        attn_shift[:, 1:] = mask[:, :-1]
+        attn_shift[:, 0] = mask[:, 0]
+        logits = m(ids, y_shift, mask, attn_shift)
+        M = logits.shape[0] * logits.shape[1]
+        loss, correct, am = heads.masked_ce(logits.reshape(M, -1), y.reshape(M), mask.reshape(M))
+        want_logits, got_logits = g['tokcls8_logits'], logits.detach().cpu().numpy()[:, ::8]
+    m.zero_grad()
+    loss.backward()
+    ref = float(g[task + '_loss'])
+    assert abs(loss.item() - ref) / ref < (1e-5 if dtype == 'fp32' else 1e-2)
+    assert _rel(got_logits, want_logits) < (2e-4 if dtype == 'fp32' else 5e-2)
+    sd = dict(m.named_parameters())
+    n = 0
+    for k in g.files:
+        if k.startswith(task + '_grad:'):
+            name = k.split(':', 1)[1]
+            got, want = sd[name].grad.cpu().numpy().astype(np.float64), g[k].astype(np.float64)
+            wmax = float(np.abs(want).max())
+            if wmax < 1e-4:
+                # The pooling-attention weights: with these weights the sequence softmax is nearly uniform and the decoder
+                # outputs of neighbouring positions nearly equal, so p * (dp - sum p dp) cancels to ~1e-6 of its terms - the
+                # reference's own value is rounding noise of the backbone output (our pooling kernels agree with fp64 to 1e-6
+                # on well-conditioned inputs, tests/test_gpu_heads.py).  Require the right order of magnitude only.
+                assert float(np.abs(got).max()) < 50 * wmax + 1e-7, (name, float(np.abs(got).max()), wmax)
+            elif dtype == 'fp32':
+                # (5e-3 of the largest entry: a ReLU pre-activation within rounding distance of zero flips its gate)
+                assert float(np.abs(got - want).max()) < 5e-3 * wmax + 1e-8, (name, _rel(got, want))
+            else:
+                # bf16 through 16 layers: direction and scale.  (Batch 2: one ReLU gate of the pooled classifier flipping under
+                # bf16 noise switches a whole row of classifier.1.weight's gradient on or off - hence the loose max-norm bound)
+                cos = float((got * want).sum() / (np.linalg.norm(got) * np.linalg.norm(want) + 1e-30))
+                assert cos > 0.98 and _rel(got, want) < 0.5, (name, cos, _rel(got, want))
+            n += 1
+    assert n >= 6
 
 
 def test_generation_finetune_loss_matches_oracle():

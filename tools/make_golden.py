@@ -447,6 +447,22 @@ def golden_cls():
             else:
                 res = tc(ids, ids, mask, mask)
             out['tokcls%d_logits' % cn] = res.numpy()
+        if cn == 8:
+            # training gradients through the replacement decoder front end (label embedding + decoder_linear, shifted labels)
+            tc.zero_grad()
+            attn_shift = torch.zeros_like(mask)
+            attn_shift[:, 1:] = mask[:, :-1]
+            attn_shift[:, 0] = mask[:, 0]
+            lg = tc(ids, y_shift, mask, attn_shift)
+            l = torch.nn.functional.cross_entropy(lg.permute(0, 2, 1), labels, reduction='none') * mask
+            loss = l.sum() / mask.sum()
+            loss.backward()
+            out['tokcls8_labels'] = labels.numpy()
+            out['tokcls8_loss'] = np.float64(loss.item())
+            for k, v in tc.named_parameters():
+                if k in GRAD_KEYS or k.startswith('classifier') or k.startswith('pianobart.decoder_'):
+                    if v.grad is not None:
+                        out['tokcls8_grad:' + k] = v.grad.numpy().copy()
         if cn == 4:
             # training gradients of the token task (finetune.py:125-130,233-235: CE masked by encoder non-pad / sum(mask))
             y_tok = torch.from_numpy(np.random.RandomState(8).randint(0, cn, size=(B, S))).long()
@@ -463,8 +479,79 @@ def golden_cls():
     np.savez_compressed(os.path.join(OUT, 'cls_tiny.npz'), **out)
 
 
+def golden_cls_default():
+    """BASELINE configs[3] / [4] at the DEFAULT model size (d 1024, 8 + 8 layers, S 1024; batch 2 to keep the CPU run and the
+    fixture small): sequence classification with 8 classes (composer) and token classification with class_num = 8 (velocity:
+    7 + 1, the replacement decoder front end on shifted labels) - logits, training loss and a handful of gradients from the
+    reference's own modules (model.py:165-272) and loss expressions (finetune.py:125-132)."""
+    cfg = (1024, 8, 8, 8, 2048, 1024)
+    d = cfg[0]
+    S, B = 1024, 2
+    out = dict(cfg=np.array(cfg), seed=12)
+    ids = torch.from_numpy(P.synth_ids(B, S, 77, padded=True))
+    out['ids'] = ids.numpy().astype(np.int16)
+    BACKBONE = ('pianobart.encoder_linear.bias', 'pianobart.bart.decoder.layers.7.final_layer_norm.weight',
+                'pianobart.bart.encoder.layers.0.self_attn.q_proj.bias')
+    pb, _ = build_ref(cfg, 12)
+    mask = (ids[:, :, 0] != pb.bar_pad_word).float()
+    sc = ref_model.SequenceClassification(pb, class_num=8, hs=d)
+    extra = {'attention.ws1.weight': (128, d), 'attention.ws2.weight': (4, 128), 'classifier.1.weight': (256, d * 4),
+             'classifier.1.bias': (256,), 'classifier.3.weight': (8, 256), 'classifier.3.bias': (8,)}
+    sd = sc.state_dict()
+    for k, shp in extra.items():
+        sd[k] = torch.from_numpy(P.gen_tensor('seqcls.' + k, shp, 12))
+    sc.load_state_dict(sd)
+    sc.eval()
+    y_seq = torch.from_numpy(np.random.RandomState(16).randint(0, 8, size=(B,))).long()
+    sc.zero_grad()
+    logits = sc(ids, mask)
+    loss = torch.nn.functional.cross_entropy(logits, y_seq, reduction='none').sum() / B
+    loss.backward()
+    out['seqcls_logits'] = logits.detach().numpy()
+    out['seqcls_labels'] = y_seq.numpy()
+    out['seqcls_loss'] = np.float64(loss.item())
+    for k, v in sc.named_parameters():
+        if k in BACKBONE or k.startswith('classifier') or k.startswith('attention'):
+            out['seqcls_grad:' + k] = v.grad.numpy().copy()
+    del sc, pb
+    # token classification, class_num = 8 (>= 5: label embedding + its Linear replace the decoder front end)
+    cn = 8
+    pb, _ = build_ref(cfg, 12)
+    tc = ref_model.TokenClassification(pb, class_num=cn, hs=d)
+    sd = tc.state_dict()
+    extra = {'classifier.1.weight': (256, d), 'classifier.1.bias': (256,), 'classifier.3.weight': (cn, 256),
+             'classifier.3.bias': (cn,), 'pianobart.decoder_emb.lut.weight': (cn, 64),
+             'pianobart.decoder_linear.weight': (d, 64), 'pianobart.decoder_linear.bias': (d,)}
+    for k, shp in extra.items():
+        assert tuple(sd[k].shape) == shp, (k, sd[k].shape, shp)
+        sd[k] = torch.from_numpy(P.gen_tensor('tokcls%d.' % cn + k, shp, 12))
+    tc.load_state_dict(sd)
+    tc.eval()
+    labels = torch.from_numpy(np.random.RandomState(14).randint(0, cn - 1, size=(B, S))).long()
+    y_shift = torch.zeros_like(labels)
+    y_shift[:, 1:] = labels[:, :-1]
+    y_shift[:, 0] = cn - 1
+    attn_shift = torch.zeros_like(mask)
+    attn_shift[:, 1:] = mask[:, :-1]
+    attn_shift[:, 0] = mask[:, 0]
+    tc.zero_grad()
+    lg = tc(ids, y_shift, mask, attn_shift)
+    l = torch.nn.functional.cross_entropy(lg.permute(0, 2, 1), labels, reduction='none') * mask
+    loss = l.sum() / mask.sum()
+    loss.backward()
+    out['tokcls8_dec_in'] = y_shift.numpy().astype(np.int16)
+    out['tokcls8_labels'] = labels.numpy().astype(np.int16)
+    out['tokcls8_logits'] = lg.detach().numpy()[:, ::8].copy()          # every 8th position
+    out['tokcls8_loss'] = np.float64(loss.item())
+    keep = BACKBONE[:2] + ('pianobart.decoder_emb.lut.weight', 'pianobart.decoder_linear.bias')
+    for k, v in tc.named_parameters():
+        if k in keep or k.startswith('classifier'):
+            out['tokcls8_grad:' + k] = v.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, 'cls_default.npz'), **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['tiny', 'mid', 'default', 'noising', 'generate', 'cls', 'generate_default', 'genft', 'truncate']
+    which = sys.argv[1:] or ['tiny', 'mid', 'default', 'noising', 'generate', 'cls', 'generate_default', 'genft', 'truncate', 'cls_default']
     if 'tiny' in which:
         golden_forward('fwd_tiny', (64, 2, 2, 4, 128, 32), 1, 5, 32, True,
                        ['encoder_linear.bias', 'word_emb.3.lut.weight', 'bart.decoder.layers.1.encoder_attn.k_proj.weight',
@@ -490,3 +577,5 @@ if __name__ == '__main__':
         golden_genft()
     if 'truncate' in which:
         golden_truncate()
+    if 'cls_default' in which:
+        golden_cls_default()
