@@ -655,3 +655,39 @@ def test_side_stream_work_is_transparent(monkeypatch):
         grads.append(pb._grad.detach().clone())
     scale = float(grads[1].abs().max())
     assert float((grads[0] - grads[1]).abs().max()) <= 2e-5 * scale
+
+
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_backbone_outputs_and_encoder_only_forward_vs_reference(dtype):
+    """PianoBart.forward (PianoBart.py:56-80): `.last_hidden_state` / `.encoder_last_hidden_state` of the full model and the
+    encoder-only call (input_ids_decoder=None -> bart.encoder) against the executed reference's hidden states; the
+    encoder-only path also has to be differentiable (it is what a user fine-tuning an encoder head would call)."""
+    g = load_golden('fwd_tiny')
+    pb, _ = build_cuda_model(g['cfg'], int(g['seed']), dtype, lm=False)
+    pb.eval()
+    enc, dec, ori, lmask, em, dm = golden_inputs(g)
+    tol = 2e-5 if dtype == 'fp32' else 4e-2
+    with torch.no_grad():
+        full = pb(enc, dec, em, dm)
+        only = pb(enc, None, em)
+    assert float((full.encoder_last_hidden_state.cpu() - torch.from_numpy(g['enc_hidden'])).abs().max()) < tol * max(1.0, float(np.abs(g['enc_hidden']).max()))
+    assert float((full.last_hidden_state.cpu() - torch.from_numpy(g['last_hidden'])).abs().max()) < tol * max(1.0, float(np.abs(g['last_hidden']).max()))
+    assert float((only.last_hidden_state.cpu() - torch.from_numpy(g['enc_hidden'])).abs().max()) < tol * max(1.0, float(np.abs(g['enc_hidden']).max()))
+    # gradient through the encoder-only graph: d/dtheta of sum(h * w) against finite differences of one bias
+    w = torch.randn(only.last_hidden_state.shape, generator=torch.Generator().manual_seed(3)).cuda()
+    pb.zero_grad()
+    out = pb(enc, None, em).last_hidden_state
+    (out * w).sum().backward()
+    bias = dict(pb.named_parameters())['bart.encoder.layers.0.fc1.bias']
+    assert bias.grad is not None and torch.isfinite(bias.grad).all() and float(bias.grad.abs().max()) > 0
+    if dtype == 'fp32':
+        j = int(bias.grad.abs().argmax())
+        eps = 1e-2
+        with torch.no_grad():
+            bias[j] += eps
+            fp = float((pb(enc, None, em).last_hidden_state * w).sum())
+            bias[j] -= 2 * eps
+            fm = float((pb(enc, None, em).last_hidden_state * w).sum())
+            bias[j] += eps
+        fd = (fp - fm) / (2 * eps)
+        assert abs(fd - float(bias.grad[j])) < 2e-2 * abs(fd) + 1e-4, (fd, float(bias.grad[j]))
