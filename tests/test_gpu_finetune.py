@@ -310,3 +310,43 @@ def test_pretrainer_iteration_prefetch_and_pipelining_are_transparent():
         st.upload(batch); st.noise(); st.run(train=False)
         tot += st.fetch_stats()[0]
     assert round(tot / len(data), 3) == out[0][0]
+
+
+TINY = ['--max_seq_len', '64', '--hs', '64', '--layers', '1', '--ffn_dims', '128', '--heads', '4', '--num_workers', '0',
+        '--dtype', 'bf16', '--nopretrain']
+
+
+@pytest.mark.parametrize('task', ['composer', 'velocity', 'melody'])
+def test_finetune_entry_point_runs(task, tmp_path, monkeypatch):
+    """main.finetune() mirror (reference main.py:103-211) on synthetic data with a small model: the three task shapes - sequence
+    labels (composer), token labels through the label-embedding decoder front end (velocity: class_num 7 + 1) and token
+    labels with decoder ids = encoder ids (melody with --class_num 3) - train, validate, test and checkpoint."""
+    from pianobart_b200 import main as M
+    monkeypatch.chdir(tmp_path)
+    extra = ['--class_num', '3'] if task == 'melody' else []
+    tr = M.finetune(['--task', task, '--dataset', 'Pianist8', '--synthetic', '16', '--epochs', '2', '--batch_size', '4',
+                     '--lr', '1e-3', '--name', 't'] + TINY + extra)
+    ck = torch.load(tmp_path / 'result' / 'finetune' / (task + '_t') / 'model.ckpt', map_location='cpu', weights_only=False)
+    assert {'epoch', 'state_dict', 'valid_acc', 'valid_loss', 'train_loss', 'train_acc', 'optimizer'} <= set(ck.keys())
+    assert np.isfinite(ck['train_loss']) and np.isfinite(ck['valid_loss'])
+    log = (tmp_path / 'result' / 'finetune' / (task + '_t') / 'log').read_text()
+    assert 'Epoch 2' in log
+    if task == 'velocity':
+        assert any(k.startswith('pianobart.decoder_emb') for k in ck['state_dict'])
+
+
+def test_generation_entry_points_run(tmp_path, monkeypatch):
+    """main.finetune_generation() (reference main.py:214-321) then main.eval_generation() (eval_generation.py:49-115) on the
+    checkpoint it wrote: the .npy has the reference's shape / dtype, rows after the stop step are <PAD>, and the truncated
+    copy obeys the Octuple2Midi rules."""
+    from pianobart_b200 import main as M
+    monkeypatch.chdir(tmp_path)
+    M.finetune_generation(['--synthetic', '8', '--epochs', '1', '--batch_size', '4', '--lr', '1e-3', '--name', 'g'] + TINY)
+    ck_path = tmp_path / 'result' / 'finetune' / 'generation_g' / 'model.ckpt'
+    assert ck_path.exists()
+    args = [a for a in TINY if a != '--nopretrain']
+    out = M.eval_generation(['--ckpt', str(ck_path), '--synthetic', '3', '--batch_size', '1', '--output', 'gen.npy', '--truncate'] + args)
+    arr = np.load(tmp_path / 'gen.npy')
+    assert arr.shape == (3, 64, 8) and arr.dtype == np.float32 and np.array_equal(arr, out.numpy())
+    trunc, lens = np.load(tmp_path / 'gen.trunc.npy'), np.load(tmp_path / 'gen.len.npy')
+    assert trunc.shape == (3, 64, 8) and lens.shape == (3,) and (lens >= 0).all() and (lens < 64).all()
