@@ -172,7 +172,7 @@ class Plan:
         """Host-side marker (no launch): run() hands the payload to `on_marker` when it reaches it."""
         self.ops.append(('marker', None, payload))
 
-    def run(self, stream=None, on_marker=None, profile=None, side_stream=None):
+    def run(self, stream=None, on_marker=None, profile=None, side_stream=None, on_op=None):
         """profile: optional list; every GEMM launch is then bracketed by CUDA events on the launching
         stream and (name, flops, start_event, end_event) is appended (bench.py roofline).
         side_stream: a second CUDA stream for work that has no consumer before the optimizer - the bias-gradient column sums
@@ -197,6 +197,8 @@ class Plan:
                 if name == 'marker' and on_marker is not None:
                     on_marker(*args)
                 continue
+            if on_op is not None and name == 'attn_bwd':
+                on_op(name)     # (data-parallel reducer: launch the armed gradient buckets next to this attention backward)
             if use_side and (name in ('colsum', 'attn_prep') or name in self._side_names):
                 ev = self._side_events[n_side] if n_side < len(self._side_events) else None
                 if ev is None:

@@ -7,7 +7,17 @@ denominators (mask sums, pretrain.py:117) are all-reduced BEFORE backward, summi
 exactly the gradient of the reference's full-batch loss.
 
 `BucketReducer` is device-agnostic (CUDA + NCCL in production, CPU + gloo in the tests).
+
+Where the all-reduce kernels run matters more than when they are issued: the tcgen05 GEMMs are persistent kernels with a static
+tile schedule, so a GEMM CTA whose SM is held by an NCCL CTA starts late and the whole GEMM waits for it (round 1: 1.6 of the
+2.0 ms lost at 8 GPUs was GEMM time), while the attention backward kernels are ordinary grids of 1024 CTAs that simply flow
+around occupied SMs.  A bucket that is complete is therefore only ARMED at its marker and launched when the main stream
+reaches the next attention backward (`on_attention`, called by engine.Plan.run), i.e. next to ~0.25-0.5 ms of attention
+kernels; what is still armed at the end of the backward pass is launched by finish().  PIANOBART_B200_COMM_ALIGN=0 launches at
+the markers instead.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -21,8 +31,22 @@ class BucketReducer:
         self.pending = None          # (lo, hi) contiguous range whose gradients are final but not yet reduced
         self.issued = []             # ranges handed to all_reduce, in order
         self.works = []
+        self.armed = []              # complete buckets waiting for the next attention backward
+        self.align = comm_stream is not None and os.environ.get('PIANOBART_B200_COMM_ALIGN', '1') != '0'
 
     def _issue(self, lo, hi):
+        if self.align:
+            self.armed.append((lo, hi))
+        else:
+            self._launch(lo, hi)
+
+    def on_attention(self, name=None):
+        """Plan.run hook, called right before an attention backward is launched on the main stream."""
+        armed, self.armed = self.armed, []
+        for lo, hi in armed:
+            self._launch(lo, hi)
+
+    def _launch(self, lo, hi):
         self.issued.append((lo, hi))
         view = self.g[lo:hi]
         if self.comm_stream is not None:
@@ -53,6 +77,7 @@ class BucketReducer:
         if self.pending is not None:
             self._issue(*self.pending)
             self.pending = None
+        self.on_attention()
         for w in self.works:
             w.wait()
         self.works = []

@@ -238,7 +238,7 @@ class PretrainStep:
             if self.world > 1:
                 from .parallel import BucketReducer
                 red = BucketReducer(pb._grad, self.pg, comm_stream=self.comm_stream)
-                n += g.bwd.run(on_marker=red.on_final, profile=profile, side_stream=g.side_stream())
+                n += g.bwd.run(on_marker=red.on_final, profile=profile, side_stream=g.side_stream(), on_op=red.on_attention)
                 red.finish()
             else:
                 n += g.bwd.run(profile=profile, side_stream=g.side_stream())

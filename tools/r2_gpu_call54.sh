@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+( timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -2 )
+for rep in 1 2; do
+for cfg in "PIANOBART_B200_COMM_ALIGN=1" "PIANOBART_B200_COMM_ALIGN=0"; do
+  echo "== $cfg"
+  ( env $cfg timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2953$rep bench.py --gpus 2 --steps 40 --warmup 5 --no-cpu-baseline --no-decode 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['achieved'], d['clocks']['sm_mhz'])" )
+done
+done
+( timeout 600 python bench.py --gpus 1 --steps 40 --warmup 5 --no-cpu-baseline --no-decode 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['achieved'], d['clocks']['sm_mhz'])" )
