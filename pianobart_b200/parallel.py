@@ -23,7 +23,9 @@ import torch.distributed as dist
 
 
 class BucketReducer:
-    def __init__(self, flat_grad, group=None, target_bytes=48 << 20, comm_stream=None):
+    def __init__(self, flat_grad, group=None, target_bytes=None, comm_stream=None):
+        if target_bytes is None:
+            target_bytes = int(os.environ.get('PIANOBART_B200_BUCKET_MB', '32')) << 20
         self.g = flat_grad
         self.group = group
         self.target = max(1, target_bytes // flat_grad.element_size())
