@@ -400,6 +400,9 @@ typedef struct pb_decode_batch_desc {
   int* error_flag;
   long long* trace;                                    /* developer hook (NULL in production): clock64 before / after every
                                                           grid barrier of the launch's last token, [gridDim][2 * 80]     */
+  float* part; int* part_cnt;                          /* cross-attention units of the last, partial round are cut into two
+                                                          key halves: partial results [gridDim][132] fp32 and zero-initialised
+                                                          pair counters [gridDim / 2]; both NULL = whole units only        */
 } pb_decode_batch_desc;
 int pb_decode_batch_run(const pb_decode_batch_desc* d, int n_steps, const int* seg_sizes_host, const float* temp_host,
                         const float* top_p_host, const int* pad_host, void* stream);

@@ -78,7 +78,8 @@ class DecodeBatchDesc(C.Structure):
                 [(n, C.c_void_p) for n in (
                     'emb_table', 'w_in', 'b_in', 'pos_table', 'lne_g', 'lne_b', 'w_heads', 'b_heads', 'enc_keep',
                     't_dev', 'cur_tok', 'result', 'sampled', 'done', 'n_written', 'uniforms', 'forced', 'logits',
-                    'xemb', 'raw0', 'raw1', 'raw2', 'hn', 'qkv', 'qc', 'ob', 'f1', 'stats', 'barrier', 'error_flag', 'trace')])
+                    'xemb', 'raw0', 'raw1', 'raw2', 'hn', 'qkv', 'qc', 'ob', 'f1', 'stats', 'barrier', 'error_flag', 'trace',
+                    'part', 'part_cnt')])
 
 
 class PBError(RuntimeError):

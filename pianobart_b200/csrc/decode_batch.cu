@@ -29,6 +29,7 @@ constexpr int KVRING = 4;                    // K / V ring of the attention phas
 constexpr int KCH = 128;                     // keys per K / V chunk (one contiguous 32 KB bulk copy)
 constexpr int KVSLOT = 2 * WSLOT;
 constexpr int MAXKEYS = PB_DECODE_NSPLIT * PB_DECODE_NSLOT;   // 1026 >= 1024
+constexpr int PART_STRIDE = 132;             // floats per partial attention result: max, sum, o[128] (+ pad)
 
 struct BShared {
   alignas(1024) uint8_t x[BM * XSTRIDE];     // staged activations [64][1024] bf16 (padded rows); reduction scratch afterwards
@@ -285,7 +286,10 @@ __device__ __forceinline__ void proj_phase(BCtx& cx, const bf16* xsrc, int ldx, 
 // ---------------------------------------------------------------------------------------------- attention phase
 // one (sequence b, head h) unit: nk cached keys streamed as K chunks then V chunks (+ the new key of this step for self
 // attention); keep: encoder key-padding flags of the sequence or null.  Result -> out[b, h*128 .. +128) bf16.
-__device__ __forceinline__ void attn_unit(BCtx& cx, int nk, bool has_new, const uint8_t* keep, bf16* out) {
+// part >= 0: this call covers only a key range of the unit (the caller offsets `keep`; the producer streams that range): the
+// unnormalised result (max, sum, o[128]) goes to P.part[part] and the second of the two halves to arrive (atomic counter, no
+// waiting) merges both and writes `out`.
+__device__ __forceinline__ void attn_unit(BCtx& cx, int nk, bool has_new, const uint8_t* keep, bf16* out, int part = -1) {
   BShared* sm = cx.sm;
   const int nkc = (nk + KCH - 1) / KCH;
   const float4 q4 = *reinterpret_cast<const float4*>(&sm->q[cx.lane * 4]);
@@ -379,10 +383,60 @@ __device__ __forceinline__ void attn_unit(BCtx& cx, int nk, bool has_new, const 
 #pragma unroll
     for (int gg = 0; gg < 8; ++gg) { o0 += sm->po[gg][2 * cx.tid]; o1 += sm->po[gg][2 * cx.tid + 1]; }
     if (has_new) { o0 += sm->sc[nk] * sm->vnew[2 * cx.tid]; o1 += sm->sc[nk] * sm->vnew[2 * cx.tid + 1]; }
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
-    *reinterpret_cast<uint32_t*>(out + 2 * cx.tid) = pack_bf16x2(o0 * inv, o1 * inv);
+    if (part < 0) {
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      *reinterpret_cast<uint32_t*>(out + 2 * cx.tid) = pack_bf16x2(o0 * inv, o1 * inv);
+    } else {
+      float* gp = cx.p->part + (size_t)part * PART_STRIDE;
+      if (cx.tid == 0) { gp[0] = m; gp[1] = l; }
+      gp[2 + 2 * cx.tid] = o0;
+      gp[3 + 2 * cx.tid] = o1;
+      __threadfence();
+    }
   }
   cons_sync();
+  if (part >= 0) {
+    if (cx.tid == 0) sm->tok[0] = atomicAdd(cx.p->part_cnt + (part >> 1), 1);
+    cons_sync();
+    const int old = sm->tok[0];
+    cons_sync();
+    if (old == 1) {                                        // both halves are in global memory: merge them
+      __threadfence();
+      if (cx.tid < HD / 2) {
+        const float* g0 = cx.p->part + (size_t)(part & ~1) * PART_STRIDE;
+        const float* g1 = g0 + PART_STRIDE;
+        const float m0 = __ldcg(g0), l0 = __ldcg(g0 + 1), m1 = __ldcg(g1), l1 = __ldcg(g1 + 1);
+        const float mm = fmaxf(m0, m1);
+        const float w0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mm), w1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mm);
+        const float ll = l0 * w0 + l1 * w1;
+        const float inv = ll > 0.f ? 1.0f / ll : 0.f;
+        const float o0 = __ldcg(g0 + 2 + 2 * cx.tid) * w0 + __ldcg(g1 + 2 + 2 * cx.tid) * w1;
+        const float o1 = __ldcg(g0 + 3 + 2 * cx.tid) * w0 + __ldcg(g1 + 3 + 2 * cx.tid) * w1;
+        *reinterpret_cast<uint32_t*>(out + 2 * cx.tid) = pack_bf16x2(o0 * inv, o1 * inv);
+      }
+      if (cx.tid == 0) cx.p->part_cnt[part >> 1] = 0;      // next use: the next cross-attention phase, grid barriers away
+    }
+  }
+}
+
+// Work list of an attention phase: CTA c takes units c, c + G, ... while whole rounds last; the units of the last, partial
+// round are cut into two key halves (chunk-aligned) when that gives every CTA at most one piece - 512 units on 148 CTAs:
+// 3 whole units + one half instead of 4 units for 68 CTAs and 3 for the rest (a quarter of the phase was idle time).
+struct AttnItem { int ui, k_lo, k_n, part; };
+__device__ __forceinline__ int attn_items(int c, int G, int nunits, int nk, bool can_split, AttnItem (&it)[8]) {
+  const int nfull = nunits / G, rem = nunits - nfull * G;
+  const int nkc = (nk + KCH - 1) / KCH;
+  int n = 0;
+  for (int i = 0; i < nfull && n < 7; ++i) it[n++] = AttnItem{c + i * G, 0, nk, -1};
+  if (can_split && rem > 0 && 2 * rem <= G && nkc >= 2) {
+    if (c < 2 * rem) {
+      const int h0 = ((nkc + 1) / 2) * KCH, half = c & 1;
+      it[n++] = AttnItem{nfull * G + (c >> 1), half ? h0 : 0, half ? nk - h0 : h0, c};
+    }
+  } else if (c < rem) {
+    it[n++] = AttnItem{nfull * G + c, 0, nk, -1};
+  }
+  return n;
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -404,6 +458,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const __grid_
   const int t0 = *P.t_dev;
   n_steps = max(0, min(n_steps, Smax - t0));
   const int nunits = BM * H;                               // (sequence, head) attention units; unit i -> b = i / 8, h = i % 8
+  const bool split_ok = P.part != nullptr && P.part_cnt != nullptr;   // scratch for the halves of the last, partial round
 
   if (warp == NCW) {
     // ============================================================ producer: weights and K / V chunks, static schedule
@@ -431,14 +486,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const __grid_
       };
       // attention streams K (all chunks) then V (all chunks) per unit: interleave per unit
       uint32_t kk = 0, na = 0;
-      auto attn = [&](const void* kb, const void* vb, int row_cap, int nk) {
+      auto attn = [&](const void* kb, const void* vb, int row_cap, int nk_all, bool can_split) {
         // the consumers have left the projection phase that used x (their arrival follows its closing grid barrier)
         mbar_wait_to(&sm->x_free, na & 1u, err);
         ++na;
-        const int nkc = (nk + KCH - 1) / KCH;
-        for (int ui = c; ui < nunits; ui += G) {
+        AttnItem items[8];
+        const int nit = attn_items(c, G, nunits, nk_all, can_split, items);
+        for (int ii = 0; ii < nit; ++ii) {
+          const int ui = items[ii].ui, nk = items[ii].k_n;
+          const int nkc = (nk + KCH - 1) / KCH;
           for (int pass = 0; pass < 2; ++pass) {
-            const bf16* ub = reinterpret_cast<const bf16*>(pass == 0 ? kb : vb) + (size_t)ui * row_cap * HD;
+            const bf16* ub = reinterpret_cast<const bf16*>(pass == 0 ? kb : vb) + ((size_t)ui * row_cap + items[ii].k_lo) * HD;
             for (int j = 0; j < nkc; ++j) {
               const uint32_t slot = kk % KVRING;
               if (kk >= KVRING) mbar_wait_to(&sm->kv_empty[slot], ((kk / KVRING) & 1u) ^ 1u, err);
@@ -456,10 +514,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const __grid_
         for (int l = 0; l < nl; ++l) {
           const pb_decode_layer& L = P.layer[l];
           proj(L.wqkv, 3 * D, 1);
-          attn(L.self_k, L.self_v, Smax, t);
+          attn(L.self_k, L.self_v, Smax, t, false);
           proj(L.wo, D, 1);
           proj(L.wqc, D, 1);
-          attn(L.cross_k, L.cross_v, Se, Se);
+          attn(L.cross_k, L.cross_v, Se, Se, split_ok);
           proj(L.woc, D, 1);
           proj(L.w1, F, 1);
           proj(L.w2, D, 2);
@@ -537,15 +595,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const __grid_
       if (c == 0 && tid < 2 * BM) st1[tid] = 0.f;
       // ---- cross attention over the encoder keys
       cx.attn_begin();
-      for (int ui = c; ui < nunits; ui += G) {
-        const int b = ui >> 3, h = ui & 7;
-        if (tid < HD / 2) {
-          const float2 f = unpack_bf16x2(__ldcg(reinterpret_cast<const unsigned*>(qcb + (size_t)b * D + h * HD) + tid));
-          sm->q[2 * tid] = f.x * qscale;
-          sm->q[2 * tid + 1] = f.y * qscale;
+      {
+        AttnItem items[8];
+        const int nit = attn_items(c, G, nunits, Se, split_ok, items);
+        for (int ii = 0; ii < nit; ++ii) {
+          const int ui = items[ii].ui, b = ui >> 3, h = ui & 7;
+          if (tid < HD / 2) {
+            const float2 f = unpack_bf16x2(__ldcg(reinterpret_cast<const unsigned*>(qcb + (size_t)b * D + h * HD) + tid));
+            sm->q[2 * tid] = f.x * qscale;
+            sm->q[2 * tid + 1] = f.y * qscale;
+          }
+          cons_sync();
+          attn_unit(cx, items[ii].k_n, false, P.enc_keep ? P.enc_keep + (size_t)b * Se + items[ii].k_lo : nullptr,
+                    ob + (size_t)b * D + h * HD, items[ii].part);
         }
-        cons_sync();
-        attn_unit(cx, Se, false, P.enc_keep ? P.enc_keep + (size_t)b * Se : nullptr, ob + (size_t)b * D + h * HD);
       }
       cx.grid_sync();
       proj_phase(cx, ob, D, 1, D, nullptr, nullptr, nullptr, nullptr, L.boc, false, hn, nullptr, raw2, nullptr, D, st2);

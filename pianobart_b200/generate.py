@@ -250,6 +250,11 @@ class Generator:
         for k, t in self.act.items():
             setattr(D, k, E._ptr(t))
         D.barrier, D.error_flag, D.stats = E._ptr(self.barrier), E._ptr(self.err_flag), E._ptr(self.ln_stats)
+        if os.environ.get('PIANOBART_B200_DECODE_SPLIT', '1') != '0':
+            # scratch for the key halves of the cross-attention units of the last, partial round (csrc/decode_batch.cu)
+            self.attn_part = torch.zeros(160 * 132, device=dev, dtype=torch.float32)
+            self.attn_part_cnt = torch.zeros(80, device=dev, dtype=torch.int32)
+            D.part, D.part_cnt = E._ptr(self.attn_part), E._ptr(self.attn_part_cnt)
         self.pdesc = D
         self.launches_per_step = 1
         self._steps_issued = 0
