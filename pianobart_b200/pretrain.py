@@ -203,9 +203,17 @@ class PretrainStep:
         self.stats.zero_()
         M = self.M
         L.check(lib.pb_mask_sums(P(self.loss_mask.data_ptr()), P(self.stats.data_ptr() + 64), C.c_longlong(M), 8, s), 'mask_sums')
+        den_ready = None
         if self.world > 1:
+            # global denominators (pretrain.py:117 on the full batch): the all-reduce runs on the comm stream during the
+            # forward pass - only the loss kernel at its end needs them (on the main stream its latency sat between steps)
             import torch.distributed as dist
-            dist.all_reduce(self.stats[16:24], group=self.pg)  # global denominators (pretrain.py:117 on the full batch)
+            cur = torch.cuda.current_stream()
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(self.stats[16:24], group=self.pg)
+                den_ready = torch.cuda.Event()
+                den_ready.record()
         side = g.side_stream() if train else None
         if side is not None:
             # the 695 MB gradient buffer is cleared on the side stream while the forward pass runs (nothing reads or writes
@@ -214,6 +222,8 @@ class PretrainStep:
             with torch.cuda.stream(side):
                 L.check(lib.pb_fill_zero(P(pb._grad.data_ptr()), C.c_longlong(pb._grad.numel() * 4), L.stream_ptr()), 'fill_zero')
         n = g.fwd.run(profile=profile)
+        if den_ready is not None:
+            torch.cuda.current_stream().wait_event(den_ready)
         if self.fused_ce:
             # heads GEMM + masked CE + accuracy + dlogits in one tcgen05 kernel: the fp32 logits never reach HBM
             L.check(lib.pb_heads_ce_fused(P(g.out.data_ptr()), C.c_longlong(g.d), P(g.W('heads.w')), P(g.Pf('heads.b')),
@@ -252,14 +262,20 @@ class PretrainStep:
         """Queues the D2H copy of the step's 24 scalars (behind the step, on the current stream) into one of two pinned
         slots and returns a ticket for collect_stats(): the trainer reads step i back only after step i + 1 has been
         launched, so the device never idles between steps waiting for the host."""
-        st = self.stats
-        if self.world > 1:
-            import torch.distributed as dist
-            st = self.stats.clone()
-            dist.all_reduce(st[0:16], group=self.pg)
         k = self._stats_slot
         self._stats_slot ^= 1
-        self.h_stats2[k].copy_(st, non_blocking=True)
+        if self.world > 1:
+            # numerators / correct counts summed over the ranks on the comm stream: the next step does not wait for it
+            import torch.distributed as dist
+            st = self.stats.clone()
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(st[0:16], group=self.pg)
+                self.h_stats2[k].copy_(st, non_blocking=True)
+                self._stats_ev[k].record()
+            st.record_stream(self.comm_stream)
+            return k
+        self.h_stats2[k].copy_(self.stats, non_blocking=True)
         self._stats_ev[k].record()
         return k
 
