@@ -32,6 +32,11 @@ from .modules import PianoBart, PianoBartLM
 LOSS_WEIGHTS = [262, 134, 262, 134, 38, 135, 55, 260]
 
 
+# kernels executed by replaying captured step graphs (the library's launch counter only sees direct API calls); bench.py adds
+# this to pb_launch_count() for its gpu_launches figure
+GRAPH_REPLAYED_LAUNCHES = [0]
+
+
 class FusedAdamW:
     """HF-semantics AdamW (transformers 4.29 `AdamW(lr, weight_decay=0.01)`: betas (0.9, 0.999), eps 1e-6,
     bias correction folded in the step size, decay after the update) over the flat parameter buffer,
@@ -109,6 +114,7 @@ class PretrainStep:
         self.lib = L.lib()
         self.graph = pb._graph(B, S, S, True, True, dropout)
         self._pack_gen = pb._pack_gen
+        self._cg, self._cg_n, self._graph_ok, self._eager_runs = None, 0, True, 0
         # north-star fusion 3 (bf16 mode): MLM heads + masked CE in one kernel (csrc/heads_ce_tc.cu)
         self.fused_ce = (pb.pb_dtype == E.PB_BF16 and self.graph.d % 64 == 0
                          and os.environ.get('PIANOBART_B200_FUSED_CE', '1') != '0')
@@ -194,12 +200,47 @@ class PretrainStep:
 
     # -- stage 2: forward + loss (+ backward + optimizer)
     def run(self, train=True, profile=None):
-        g, lib, s = self.graph, self.lib, L.stream_ptr()
         pb = self.pb
-        P = C.c_void_p
         pb.check_pack_generation(self._pack_gen, 'PretrainStep')
         pb._sync_weights()
         pb._live_graph = None  # the fused step owns the graph buffers; autograd must not reuse them
+        # The ~330 launches of forward + loss + backward (incl. the side-stream fork / joins) replay as ONE CUDA graph once the
+        # step is warm (single GPU, training mode): same kernels, same order, programmatic-dependent-launch edges kept.
+        # The optimizer stays outside (its bias-correction scalars change every step).  PIANOBART_B200_STEP_GRAPH=0: eager.
+        if (train and profile is None and self.world == 1 and self._graph_ok
+                and os.environ.get('PIANOBART_B200_STEP_GRAPH', '1') != '0'):
+            if self._cg is None and self._eager_runs >= 2:
+                try:
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg):
+                        self._cg_n = self._enqueue(True, None)
+                    self._cg = cg
+                except Exception as e:            # capture unsupported for some node: keep launching eagerly (same kernels)
+                    self._graph_ok = False
+                    torch.cuda.synchronize()
+                    sys.stderr.write('pianobart_b200: step graph capture failed (%s); launching eagerly\n' % (str(e)[:200],))
+            if self._cg is not None:
+                self._cg.replay()
+                n = self._cg_n
+                GRAPH_REPLAYED_LAUNCHES[0] += n
+                if self.opt is not None:
+                    self.opt.step()
+                    n += 3
+                self.launches += n
+                return n
+        self._eager_runs += 1
+        n = self._enqueue(train, profile)
+        if train and self.opt is not None:
+            self.opt.step()
+            n += 3
+        self.launches += n
+        return n
+
+    def _enqueue(self, train, profile):
+        """Queues forward + loss (+ backward) of one step on the current stream (and the graph's side / comm streams)."""
+        g, lib, s = self.graph, self.lib, L.stream_ptr()
+        pb = self.pb
+        P = C.c_void_p
         self.stats.zero_()
         M = self.M
         L.check(lib.pb_mask_sums(P(self.loss_mask.data_ptr()), P(self.stats.data_ptr() + 64), C.c_longlong(M), 8, s), 'mask_sums')
@@ -230,7 +271,8 @@ class PretrainStep:
                                           P(self.targets.data_ptr()), P(self.loss_mask.data_ptr()),
                                           P(self.stats.data_ptr() + 64), P(self.stats.data_ptr()),
                                           P(self.stats.data_ptr() + 32), P(g.dlogits.data_ptr()) if train else P(None),
-                                          P(None), C.c_longlong(M), g.d, 8, self.seg, self.w, C.c_float(self.grad_scale), s),
+                                          P(None), C.c_longlong(M), g.d, 8, self.seg, self.w, C.c_float(self.grad_scale),
+                                          L.stream_ptr()),
                     'heads_ce_fused')
             n += 1
         else:
@@ -238,7 +280,7 @@ class PretrainStep:
             L.check(lib.pb_heads_ce(P(g.logits.data_ptr()), P(self.targets.data_ptr()), P(self.loss_mask.data_ptr()),
                                     P(self.stats.data_ptr() + 64), P(self.stats.data_ptr()), P(self.stats.data_ptr() + 32),
                                     P(g.dlogits.data_ptr()) if train else P(None), P(None), C.c_longlong(M), 8, self.seg,
-                                    self.w, C.c_float(self.grad_scale), pb.pb_dtype, s), 'heads_ce')
+                                    self.w, C.c_float(self.grad_scale), pb.pb_dtype, L.stream_ptr()), 'heads_ce')
             n += 2
         if train:
             if side is not None:
@@ -252,10 +294,6 @@ class PretrainStep:
                 red.finish()
             else:
                 n += g.bwd.run(profile=profile, side_stream=g.side_stream())
-            if self.opt is not None:
-                self.opt.step()
-                n += 3
-        self.launches += n
         return n
 
     def queue_stats(self):
