@@ -152,3 +152,35 @@ def test_plan_prefetcher_preserves_rng_order():
     for a, (o, b) in zip(seq, got):
         assert np.array_equal(a.src, b.src) and np.array_equal(a.loss, b.loss) and np.array_equal(a.loss_mode, b.loss_mode)
         assert a.rand_tok == b.rand_tok or np.array_equal(np.array(a.rand_tok), np.array(b.rand_tok))
+
+
+def test_bucket_reducer_arms_buckets_until_the_next_attention_backward():
+    """parallel.BucketReducer with aligned launches: a complete bucket is held until engine.Plan.run reaches the next attention
+    backward (on_attention) or the end of the pass (finish); every element is still reduced exactly once, in marker order."""
+    import numpy as np
+    import torch
+    from pianobart_b200.engine import ParamLayout
+    from pianobart_b200.parallel import BucketReducer
+    lay = ParamLayout(64, 2, 2, 128, 32, True)
+    g = torch.zeros(lay.size)
+    red = BucketReducer(g, None, target_bytes=64 * 1024)
+    red.align = True                       # (normally: CUDA comm stream present and PIANOBART_B200_COMM_ALIGN != 0)
+    launched = []
+    red._launch = lambda lo, hi: launched.append((lo, hi)) or red.issued.append((lo, hi))
+    order = ['heads', 'decoder.layers.1', 'decoder.layers.0', 'decoder.front', 'encoder.layers.1', 'encoder.layers.0',
+             'encoder.front', 'front']
+    seen_at_attention = []
+    for k in order:
+        if 'layers' in k:                  # each layer's backward contains attention backward launches before its marker
+            red.on_attention('attn_bwd')
+            seen_at_attention.append(len(launched))
+        n_before = len(launched)
+        red.on_final('grads_final', *lay.ranges[k])
+        assert len(launched) == n_before   # markers only arm
+    assert len(red.armed) >= 1             # the last bucket waits for finish()
+    issued = red.finish()
+    cover = np.zeros(lay.size, dtype=np.int32)
+    for lo, hi in issued:
+        cover[lo:hi] += 1
+    assert (cover == 1).all() and issued == launched and not red.armed
+    assert seen_at_attention[-1] >= 1      # earlier buckets went out next to an attention backward, not at the end
