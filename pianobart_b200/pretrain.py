@@ -207,6 +207,8 @@ class PretrainStep:
         # The ~330 launches of forward + loss + backward (incl. the side-stream fork / joins) replay as ONE CUDA graph once the
         # step is warm (single GPU, training mode): same kernels, same order, programmatic-dependent-launch edges kept.
         # The optimizer stays outside (its bias-correction scalars change every step).  PIANOBART_B200_STEP_GRAPH=0: eager.
+        # (Data parallel steps stay eager: capturing the NCCL all-reduces works and is 0.3 ms faster at 2 GPUs, but the
+        # processes then hang in teardown until killed - profiles/r2_summary.md section 12.)
         if (train and profile is None and self.world == 1 and self._graph_ok
                 and os.environ.get('PIANOBART_B200_STEP_GRAPH', '1') != '0'):
             if self._cg is None and self._eager_runs >= 2:
