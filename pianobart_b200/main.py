@@ -486,10 +486,133 @@ def eval_generation(argv=None):
     return output
 
 
+# ----------------------------------------------------------------------------------- demo (demo.py:34-170)
+def get_args_demo(argv=None):
+    p = argparse.ArgumentParser(description='')
+    p.add_argument('--dict_file', type=str, default='./Data/Octuple.pkl')
+    p.add_argument('--ckpt', default='result/pretrain/pianobart/model_best.ckpt')
+    p.add_argument('--input', default='./Data/POP909/POP909/001/001.mid')
+    p.add_argument('--output', default='./output.mid')
+    p.add_argument('--num_workers', type=int, default=5)
+    p.add_argument('--max_seq_len', type=int, default=1024)
+    p.add_argument('--hs', type=int, default=1024)
+    p.add_argument('--layers', type=int, default=8)
+    p.add_argument('--ffn_dims', type=int, default=2048)
+    p.add_argument('--heads', type=int, default=8)
+    p.add_argument('--nopretrain', action='store_true')
+    p.add_argument('--cpu', action='store_true')
+    p.add_argument('--cuda_devices', type=int, nargs='+', default=[0])
+    p.add_argument('--dtype', type=str, default='bf16', choices=['bf16'])
+    return p.parse_args(argv)
+
+
+def demo(argv=None):
+    """reference demo.py: MIDI file -> Octuple prompt (Midi2Octuple) -> KV-cache generation -> truncation + Octuple -> MIDI file
+    (Octuple2Midi).  MIDI I/O and the codec are pianobart_b200/codec.py (no miditoolkit needed)."""
+    from .modules import PianoBartLM
+    from .postprocess import midi_to_octuple, octuple_to_midi
+    args = get_args_demo(argv)
+    if args.cpu or not torch.cuda.is_available():
+        raise SystemExit('pianobart_b200 demo has no CPU path (sm_100a kernels only)')
+    e2w, w2e = _load_vocab(args.dict_file)
+    pianobart = _build_pianobart(args, e2w, w2e)
+    model = PianoBartLM(pianobart)
+    if not args.nopretrain and os.path.exists(args.ckpt):
+        model.load_state_dict(torch.load(args.ckpt, map_location='cpu')['state_dict'], strict=False)
+    device = torch.device('cuda', args.cuda_devices[0] if args.cuda_devices else 0)
+    model = model.to(device)
+    model.eval()
+    x = midi_to_octuple(args.input, device=device)
+    if x.shape[1] != args.max_seq_len:
+        raise SystemExit('the codec pads prompts to 1024 rows: --max_seq_len must be 1024')
+    x = x.long()
+    attn_encoder = (x[:, :, 0] != pianobart.bar_pad_word).float()
+    with torch.no_grad():
+        y = model(input_ids_encoder=x, encoder_attention_mask=attn_encoder, generate=True)
+    written = octuple_to_midi(y, [args.output])
+    print('Saved to %s' % args.output if written[0] else 'Generate Fail! (empty)')
+    return x, y
+
+
+# ----------------------------------------------------------------------------------- dataset builder (convert.py:583-650)
+def get_args_convert(argv=None):
+    p = argparse.ArgumentParser(description='MIDI files -> (N, 1024, 8) Octuple .npy blocks (reference Data/data_generation/convert.py)')
+    p.add_argument('--input', type=str, required=True, help='directory scanned recursively for .mid / .midi files')
+    p.add_argument('--output', type=str, required=True, help='output directory')
+    p.add_argument('--dataset', type=str, default='dataset')
+    p.add_argument('--task', choices=['pretrain', 'generate', 'melody', 'velocity', 'emotion'], default='pretrain')
+    p.add_argument('--nopad', action='store_true', help="pretrain only: concatenate the pieces and cut 1024-row blocks")
+    p.add_argument('--seed', type=int, default=None)
+    return p.parse_args(argv)
+
+
+def convert(argv=None):
+    """The reference's dataset builder: 80 / 10 / 10 split of the shuffled file list, every piece encoded, cut at the 255-bar
+    limit, padded (or packed) to 1024-row blocks; `<dataset>_<split>.npy` (+ `_ans.npy` for the labelled tasks).  Duplicate
+    pieces (same (program, pitch) sequence, convert.py:118-122,352-368) are skipped."""
+    import hashlib
+    import random
+    from . import codec
+    args = get_args_convert(argv)
+    if args.seed is not None:
+        random.seed(args.seed)
+    files = sorted(os.path.join(r, f) for r, _, fs in os.walk(args.input) for f in fs if f.lower().endswith(('.mid', '.midi')))
+    random.shuffle(files)
+    os.makedirs(args.output, exist_ok=True)
+    n = len(files)
+    splits = {'train': files[:80 * n // 100], 'valid': files[80 * n // 100:90 * n // 100], 'test': files[90 * n // 100:]}
+    pad = not args.nopad if args.task == 'pretrain' else args.task not in ('melody', 'velocity')
+    seen, ok, stats = {}, 0, {}
+    for sp in ('test', 'train', 'valid'):
+        out, ans = [], []
+        for path in splits[sp]:
+            try:
+                rows = codec.score_to_octuple(codec.read_midi(path), args.task)
+                if not rows:
+                    print('ERROR(BLANK): ' + path)
+                    continue
+                digest = hashlib.md5(str(tuple((r[2], r[3]) for r in rows)).encode('ascii')).hexdigest()
+                if digest in seen:
+                    print('ERROR(DUPLICATED): %s %s == %s' % (digest, path, seen[digest]))
+                    continue
+                seen[digest] = path
+                label = int(os.path.basename(path)[1]) - 1 if args.task == 'emotion' else None
+                for item in codec.segments_for_task(rows, args.task, pad=pad, label=label):
+                    if args.task == 'pretrain':
+                        out.append(item) if pad else out.extend(item)
+                    elif args.task == 'generate':
+                        out.append(item[0])
+                        ans.append(item[1])
+                    elif pad:
+                        out.append(item[0])
+                        ans.append(item[1])
+                    else:
+                        out.extend(item[0])
+                        ans.extend(item[1])
+                ok += 1
+                print('SUCCESS: ' + path)
+            except Exception as ex:                      # (the reference logs and skips a file it cannot process)
+                print('ERROR(PROCESS): %s %s' % (path, ex))
+        arr = np.array(out)
+        if args.task == 'pretrain' and not pad and len(out):
+            arr = codec.pack_rows(arr)
+        elif args.task in ('melody', 'velocity') and len(out):
+            other = codec.MELODY_MAP['OTHER'] if args.task == 'melody' else codec.VELOCITY_MAP['OTHER']
+            arr = codec.pack_rows(arr)
+            ans = codec.pack_rows(np.array(ans), other, 1)
+        if len(out):
+            np.save(os.path.join(args.output, '%s_%s.npy' % (args.dataset, sp)), arr)
+        if len(ans):
+            np.save(os.path.join(args.output, '%s_%s_ans.npy' % (args.dataset, sp)), np.array(ans))
+        stats[sp] = (len(splits[sp]), tuple(arr.shape))
+    print('%d/%d MIDI files successfully processed' % (ok, n))
+    return stats
+
+
 if __name__ == '__main__':
     import sys
     cmds = {'pretrain': pretrain, 'finetune': finetune, 'finetune_generation': finetune_generation,
-            'eval_generation': eval_generation}
+            'eval_generation': eval_generation, 'demo': demo, 'convert': convert}
     if len(sys.argv) > 1 and sys.argv[1] in cmds:
         cmds[sys.argv[1]](sys.argv[2:])
     else:

@@ -1,6 +1,7 @@
-"""Generation post-processing on the device: the truncation rules of reference `Octuple2Midi`
-(demo.py:72-102) for a batch of generated sequences, up to (not including) the MIDI writer, which needs `miditoolkit` and is
-out of scope."""
+"""Generation post-processing: the truncation rules of reference `Octuple2Midi` (demo.py:72-102) for a batch of
+generated sequences on the device, then - on the host - the Octuple -> MIDI decoder and a Standard MIDI File writer
+(codec.py; the reference uses `miditoolkit`, absent from this image) and the matching MIDI -> prompt direction
+(`Midi2Octuple`, demo.py:60-67)."""
 import ctypes as C
 
 import torch
@@ -29,3 +30,32 @@ def octuple_truncate(octuple):
                                         C.c_void_p(out.data_ptr()), C.c_void_p(ln.data_ptr()), B, S, pad, L.stream_ptr()),
             'octuple_truncate')
     return (out[0], ln) if squeeze else (out, ln)
+
+
+def octuple_to_midi(octuple, midi_paths):
+    """demo.py:72-105 (`Octuple2Midi`) for a batch: truncate on the device, decode every non-empty sequence with
+    codec.octuple_to_score and write it as a Standard MIDI File.  midi_paths: one path per sequence (a str for a single
+    sequence).  Returns the list of written paths (None where the reference prints "Generate Fail! (empty)")."""
+    from . import codec
+    trunc, lens = octuple_truncate(octuple)
+    if trunc.dim() == 2:
+        trunc, midi_paths = trunc.unsqueeze(0), [midi_paths]
+    rows, lens = trunc.cpu().numpy(), lens.cpu().numpy()
+    written = []
+    for b, path in enumerate(midi_paths):
+        n = int(lens[b])
+        if n == 0:
+            written.append(None)
+            continue
+        codec.write_midi(codec.octuple_to_score(rows[b, :n].tolist()), path)
+        written.append(path)
+    return written
+
+
+def midi_to_octuple(midi_path, device='cuda'):
+    """demo.py:60-67 (`Midi2Octuple`): a MIDI file as a (1, 1024, 8) int32 prompt - its LAST 1023 notes + <EOS> when it is
+    longer than the window, <PAD>-filled otherwise."""
+    from . import codec
+    rows = codec.score_to_octuple(codec.read_midi(midi_path), task='pretrain')
+    rows = codec.pad_segment(rows, window=1024, last=True)
+    return torch.tensor([rows], dtype=torch.int32, device=device)

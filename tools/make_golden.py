@@ -550,8 +550,117 @@ def golden_cls_default():
     np.savez_compressed(os.path.join(OUT, 'cls_default.npz'), **out)
 
 
+def _import_reference_convert():
+    """reference Data/data_generation/convert.py with `miditoolkit` (absent from this image) replaced by plain containers of the
+    same attribute names - the codec functions only read / build those attributes."""
+    import importlib.util
+    import types
+
+    class _Obj:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+    class _MidiFile(_Obj):
+        def __init__(self, *a, **kw):
+            super().__init__(ticks_per_beat=480, instruments=[], time_signature_changes=[], tempo_changes=[])
+            self.__dict__.update(kw)
+
+    mt = types.ModuleType('miditoolkit')
+    mt.midi = types.ModuleType('miditoolkit.midi')
+    mt.midi.parser = types.ModuleType('miditoolkit.midi.parser')
+    mt.midi.parser.MidiFile = _MidiFile
+    mt.containers = types.ModuleType('miditoolkit.containers')
+    mt.containers.Instrument = lambda program=0, is_drum=False, name='': _Obj(program=program, is_drum=is_drum, name=name, notes=[])
+    mt.containers.Note = lambda start, end, pitch, velocity: _Obj(start=start, end=end, pitch=pitch, velocity=velocity)
+    mt.containers.TimeSignature = lambda numerator, denominator, time: _Obj(numerator=numerator, denominator=denominator, time=time)
+    mt.containers.TempoChange = lambda tempo, time: _Obj(tempo=tempo, time=time)
+    for k in ('miditoolkit', 'miditoolkit.midi', 'miditoolkit.midi.parser', 'miditoolkit.containers'):
+        sys.modules[k] = {'miditoolkit': mt, 'miditoolkit.midi': mt.midi, 'miditoolkit.midi.parser': mt.midi.parser,
+                          'miditoolkit.containers': mt.containers}[k]
+    spec = importlib.util.spec_from_file_location('ref_convert', os.path.join(REF, 'Data', 'data_generation', 'convert.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, mt
+
+
+def golden_codec():
+    """Row N4: the reference's MIDI_to_encoding / encoding_to_MIDI / padding / data_split executed on synthetic scores (several
+    instruments incl. drums, time-signature and tempo changes, long pieces that cross the 255-bar limit)."""
+    cv, mt = _import_reference_convert()
+    out = {}
+    cases = []
+    for ci, (seed, tpb, n_notes, n_bars, sigs) in enumerate([
+            (1, 480, 400, 40, [(4, 4)]), (2, 384, 900, 80, [(3, 4), (6, 8), (4, 4)]), (3, 480, 1500, 300, [(4, 4), (2, 4)]),
+            (4, 96, 250, 30, [(5, 4), (7, 8), (9, 16), (12, 8)]), (5, 480, 60, 6, [(4, 4)])]):
+        rs = np.random.RandomState(seed)
+        midi = mt.midi.parser.MidiFile()
+        midi.ticks_per_beat = tpb
+        # time signature changes at bar boundaries
+        t, changes = 0, []
+        per_sig = max(1, n_bars // len(sigs))
+        for (num, den) in sigs:
+            changes.append((t, num, den))
+            t += per_sig * num * 4 * tpb // den
+        total_ticks = t
+        midi.time_signature_changes = [mt.containers.TimeSignature(numerator=n, denominator=d, time=tt) for tt, n, d in changes]
+        tempo_times = np.sort(rs.randint(0, total_ticks, size=rs.randint(1, 6)))
+        tempo_times[0] = 0 if ci % 2 == 0 else tempo_times[0]
+        midi.tempo_changes = [mt.containers.TempoChange(tempo=float(rs.choice([40, 72.5, 120, 133.3, 200, 300])), time=int(tt))
+                              for tt in tempo_times]
+        names = ['MELODY', 'BRIDGE', 'PIANO', 'x']
+        insts = []
+        for k in range(rs.randint(1, 4)):
+            ins = mt.containers.Instrument(program=int(rs.randint(0, 128)), is_drum=False, name=names[k % 4])
+            insts.append(ins)
+        if ci in (1, 3):
+            insts.append(mt.containers.Instrument(program=0, is_drum=True, name='drums'))
+        for _ in range(n_notes):
+            ins = insts[rs.randint(0, len(insts))]
+            st = int(rs.randint(0, total_ticks))
+            if rs.rand() < 0.5:
+                st = st // (tpb // 4) * (tpb // 4)
+            du = int(rs.choice([tpb // 8, tpb // 4, tpb // 2, tpb, 2 * tpb, 7 * tpb, 40 * tpb, 1]))
+            ins.notes.append(mt.containers.Note(start=st, end=st + du, pitch=int(rs.randint(21, 109)),
+                                                velocity=int(rs.randint(1, 128))))
+        midi.instruments = insts
+        # inputs, flat
+        out['c%d_tpb' % ci] = np.int64(tpb)
+        out['c%d_ts' % ci] = np.array(changes, dtype=np.int64)
+        out['c%d_tempo_t' % ci] = np.array([c.time for c in midi.tempo_changes], dtype=np.int64)
+        out['c%d_tempo_v' % ci] = np.array([c.tempo for c in midi.tempo_changes], dtype=np.float64)
+        out['c%d_inst' % ci] = np.array([[i.program, int(i.is_drum), names.index(i.name) if i.name in names else -1] for i in insts],
+                                        dtype=np.int64)
+        out['c%d_notes' % ci] = np.array([[k, n.start, n.end, n.pitch, n.velocity] for k, i in enumerate(insts) for n in i.notes],
+                                         dtype=np.int64)
+        for task in ('pretrain', 'melody', 'velocity'):
+            enc = cv.MIDI_to_encoding(midi, task)
+            out['c%d_enc_%s' % (ci, task)] = np.array(enc, dtype=np.int64)
+        enc = cv.MIDI_to_encoding(midi, 'pretrain')
+        # decoder (encoding_to_MIDI): drop the rows the encoder wrote for drums? - no: feed everything, the reference drops them
+        back = cv.encoding_to_MIDI(enc)
+        out['c%d_dec_notes' % ci] = np.array([[int(i.name), int(i.is_drum), i.program, n.start, n.end, n.pitch, n.velocity]
+                                              for i in back.instruments for n in i.notes], dtype=np.int64)
+        out['c%d_dec_ts' % ci] = np.array([[c.time, c.numerator, c.denominator] for c in back.time_signature_changes], dtype=np.int64)
+        out['c%d_dec_tempo_t' % ci] = np.array([c.time for c in back.tempo_changes], dtype=np.int64)
+        out['c%d_dec_tempo_v' % ci] = np.array([c.tempo for c in back.tempo_changes], dtype=np.float64)
+        # dataset blocks: the bar-limit windows of F (re-stated from convert.py:420-445 by running F's own loop is not possible
+        # without its file I/O; padding / data_split are executed directly)
+        out['c%d_pad' % ci] = np.array(cv.padding('x', list(enc[:1500])), dtype=np.int64)
+        out['c%d_pad_last' % ci] = np.array(cv.padding('x', list(enc[:1500]), last=True), dtype=np.int64)
+        out['c%d_split' % ci] = cv.data_split(np.array(enc, dtype=np.int64))
+        cases.append(ci)
+    out['n_cases'] = np.int64(len(cases))
+    # scalar code tables
+    out['tab_d2e'] = np.array([cv.d2e(x) for x in range(0, 5000, 7)], dtype=np.int64)
+    out['tab_e2d'] = np.array([cv.e2d(x) for x in range(0, 140)], dtype=np.int64)
+    out['tab_b2e'] = np.array([cv.b2e(x) for x in np.linspace(5, 400, 300)], dtype=np.int64)
+    out['tab_e2b'] = np.array([cv.e2b(x) for x in range(0, 49)], dtype=np.float64)
+    out['tab_tsr'] = np.array([cv.time_signature_reduce(n, d) for n in range(1, 40) for d in (1, 2, 4, 8, 16, 32, 64, 128)], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, 'codec.npz'), **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['tiny', 'mid', 'default', 'noising', 'generate', 'cls', 'generate_default', 'genft', 'truncate', 'cls_default']
+    which = sys.argv[1:] or ['tiny', 'mid', 'default', 'noising', 'generate', 'cls', 'generate_default', 'genft', 'truncate', 'cls_default', 'codec']
     if 'tiny' in which:
         golden_forward('fwd_tiny', (64, 2, 2, 4, 128, 32), 1, 5, 32, True,
                        ['encoder_linear.bias', 'word_emb.3.lut.weight', 'bart.decoder.layers.1.encoder_attn.k_proj.weight',
@@ -579,3 +688,5 @@ if __name__ == '__main__':
         golden_truncate()
     if 'cls_default' in which:
         golden_cls_default()
+    if 'codec' in which:
+        golden_codec()
