@@ -148,6 +148,12 @@ int pb_octuple_front_fwd(const void* ids, int ids_int64, const void* table_proj,
 /* one-hot rows of the Octuple ids: out[m, off_a + ids[m,a]] = 1 (a = 0..7), 0 elsewhere; out [M, sum(n_tokens)] in `dtype`.
  * Backward of the fused front end: G = onehot^T dy0 as one GEMM replaces the scatter-add of pb_octuple_embed_bwd. */
 int pb_octuple_onehot(const void* ids, int ids_int64, void* out, long long M, const int* n_tokens_host, int dtype, void* stream);
+/* Block-diagonal copy of the fused embedding table: out[off_a + r, emb_dim a + c] = emb[off_a + r, c]; out is
+ * [sum(n_tokens), 8 emb_dim] in `dtype`, its off-diagonal blocks must have been zeroed once by the caller.  Turns the eight
+ * per-attribute products of PianoBart.py:60-71 (tables x in_linear slices) and their weight gradients into single GEMMs. */
+int pb_octuple_blockdiag(const void* emb, void* out, int emb_dim, const int* n_tokens_host, int dtype, void* stream);
+/* g_emb[off_a + r, c] += alpha * dfull[off_a + r, emb_dim a + c]   (fp32; dfull = G W_in, [sum(n_tokens), 8 emb_dim]) */
+int pb_octuple_blockdiag_grad(const float* dfull, float* g_emb, int emb_dim, const int* n_tokens_host, float alpha, void* stream);
 /* stream-ordered memset(ptr, 0, bytes) */
 int pb_fill_zero(void* ptr, long long bytes, void* stream);
 

@@ -159,6 +159,15 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
       : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 // 2^y for a pair of log2-domain arguments on the FMA / integer pipes (no MUFU): round-to-nearest split y = k + f with the
 // magic-number trick, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16
 // rounding of P), k added into the exponent field.  Arguments below -120 give 2^-120 (0 after the bf16 P V product).  The
@@ -180,6 +189,19 @@ __device__ __forceinline__ float2 exp2_poly2(float2 y) {
   e.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
   e.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
   return e;
+}
+// Backward softmax of an unmasked pair: P = 2^(S sl2 + negL), dS = P (dP scale + negDs), in packed fp32; POLY sends the two
+// exponentials to the FMA pipe (exp2_poly2) instead of MUFU.
+#ifndef PB_BWD_POLY_MASK
+#define PB_BWD_POLY_MASK 0        // measured (profiles/r2_attn_bwd_poly.log, B16 H8 S1024): scalar 0.284 ms, packed 0.278,
+                                  // packed + 5/16 polynomial 0.279, + 8/16 0.283 - the backward kernels are not MUFU-bound
+#endif
+template <bool POLY>
+__device__ __forceinline__ void bwd_pair(uint32_t s0, uint32_t s1, uint32_t d0, uint32_t d1, float2 sl2v, float2 negL,
+                                         float2 scv, float2 negDs, float2& e, float2& ds) {
+  const float2 y = ffma2(make_float2(__uint_as_float(s0), __uint_as_float(s1)), sl2v, negL);
+  if (POLY) { e = exp2_poly2(y); } else { e.x = ex2(y.x); e.y = ex2(y.y); }
+  ds = fmul2(e, ffma2(make_float2(__uint_as_float(d0), __uint_as_float(d1)), scv, negDs));
 }
 // bit i of the result = column (c0 + i) of this key block may be attended by query qg:
 // key-padding bitmap word AND (causal: kg0 + c0 + i <= qg)
@@ -974,25 +996,44 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       tmem_ld32(tS0 + st * QB + lane_addr + hf * 32, sv);
       tmem_ld32(tdP0 + st * QB + lane_addr + hf * 32, dv);
       tmem_ld_wait();
-      float pr[32], ds[32];
+      // P^T / dS^T of this thread's 32 queries: 16 packed columns over the S^T / dP^T columns it has just consumed
+      uint32_t pp[16], pd[16];
       const float4* L4 = reinterpret_cast<const float4*>(&s_L[st][hf * 32]);
       const float4* D4 = reinterpret_cast<const float4*>(&s_D[st][hf * 32]);
+      if (msk == 0xffffffffu) {
+        // unmasked chunk (the common case): packed fp32 arithmetic, a share of the exponentials on the FMA pipe
+        const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(p.scale, p.scale);
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 l4 = L4[g], d4 = D4[g];
-        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+        for (int g = 0; g < 8; ++g) {
+          const float4 l4 = L4[g], d4 = D4[g];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int i = g * 4 + t;
-          float pv = ex2(fmaf(__uint_as_float(sv[i]), sl2, lv[t]));
-          if (msk != 0xffffffffu) pv = ((msk >> i) & 1u) ? pv : 0.f;
-          pr[i] = pv;
-          ds[i] = pv * fmaf(__uint_as_float(dv[i]), p.scale, dd[t]);
+          for (int t = 0; t < 2; ++t) {
+            const int i = g * 2 + t;         // pair index: queries 2i, 2i+1 of the chunk
+            const float2 nl = t == 0 ? make_float2(l4.x, l4.y) : make_float2(l4.z, l4.w);
+            const float2 nd = t == 0 ? make_float2(d4.x, d4.y) : make_float2(d4.z, d4.w);
+            float2 e, dsv;
+            if ((PB_BWD_POLY_MASK >> i) & 1) bwd_pair<true>(sv[2 * i], sv[2 * i + 1], dv[2 * i], dv[2 * i + 1], sl2v, nl, scv, nd, e, dsv);
+            else bwd_pair<false>(sv[2 * i], sv[2 * i + 1], dv[2 * i], dv[2 * i + 1], sl2v, nl, scv, nd, e, dsv);
+            const __nv_bfloat162 a2 = __floats2bfloat162_rn(e.x, e.y);
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(dsv.x, dsv.y);
+            pp[i] = *reinterpret_cast<const uint32_t*>(&a2);
+            pd[i] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
         }
-      }
-      {
-        // P^T / dS^T of this thread's 32 queries: 16 packed columns over the S^T / dP^T columns it has just consumed
-        uint32_t pp[16], pd[16];
+      } else {
+        float pr[32], ds[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 l4 = L4[g], d4 = D4[g];
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int i = g * 4 + t;
+            const float pv = ((msk >> i) & 1u) ? ex2(fmaf(__uint_as_float(sv[i]), sl2, lv[t])) : 0.f;
+            pr[i] = pv;
+            ds[i] = pv * fmaf(__uint_as_float(dv[i]), p.scale, dd[t]);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const __nv_bfloat162 a2 = __floats2bfloat162_rn(pr[2 * i], pr[2 * i + 1]);
@@ -1000,10 +1041,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           pp[i] = *reinterpret_cast<const uint32_t*>(&a2);
           pd[i] = *reinterpret_cast<const uint32_t*>(&b2);
         }
-        tmem_st16(tS0 + st * QB + lane_addr + hf * 32, pp);
-        tmem_st16(tdP0 + st * QB + lane_addr + hf * 32, pd);
-        tmem_st_wait();
       }
+      tmem_st16(tS0 + st * QB + lane_addr + hf * 32, pp);
+      tmem_st16(tdP0 + st * QB + lane_addr + hf * 32, pd);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&pds_full[st]);
     }
@@ -1208,16 +1249,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         tmem_ld32(tS0 + st * AT + lane_addr + hf * 64 + c * 32, sv);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (msk[c] == 0xffffffffu) {
+          // unmasked chunk (the common case): packed fp32 arithmetic, a share of the exponentials on the FMA pipe
+          const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(p.scale, p.scale);
+          const float2 nl = make_float2(negL, negL), nd = make_float2(nDs, nDs);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, negL)), p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, negL));
-          if (msk[c] != 0xffffffffu) {
-            p0 = ((msk[c] >> (2 * i)) & 1u) ? p0 : 0.f;
-            p1 = ((msk[c] >> (2 * i + 1)) & 1u) ? p1 : 0.f;
+          for (int i = 0; i < 16; ++i) {
+            float2 e, dsv;
+            if ((PB_BWD_POLY_MASK >> i) & 1) bwd_pair<true>(sv[2 * i], sv[2 * i + 1], dv[c][2 * i], dv[c][2 * i + 1], sl2v, nl, scv, nd, e, dsv);
+            else bwd_pair<false>(sv[2 * i], sv[2 * i + 1], dv[c][2 * i], dv[c][2 * i + 1], sl2v, nl, scv, nd, e, dsv);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(dsv.x, dsv.y);
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
           }
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0 * fmaf(__uint_as_float(dv[c][2 * i]), p.scale, nDs),
-                                                          p1 * fmaf(__uint_as_float(dv[c][2 * i + 1]), p.scale, nDs));
-          pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ((msk[c] >> (2 * i)) & 1u) ? ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, negL)) : 0.f;
+            const float p1 = ((msk[c] >> (2 * i + 1)) & 1u) ? ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, negL)) : 0.f;
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0 * fmaf(__uint_as_float(dv[c][2 * i]), p.scale, nDs),
+                                                            p1 * fmaf(__uint_as_float(dv[c][2 * i + 1]), p.scale, nDs));
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
         }
         if (c == 0 && trole > 0) PB_TR(trole, j, 3);
         // dS chunk (32 keys = 16 packed columns) over the S columns this thread has already consumed

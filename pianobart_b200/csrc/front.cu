@@ -180,6 +180,46 @@ __global__ void __launch_bounds__(256) octuple_onehot_kernel(const I* __restrict
   }
 }
 
+// Block-diagonal form of the eight embedding tables: out[off_a + r, E a + c] = emb[off_a + r, c]   ([V, 8 E], zero elsewhere -
+// the off-diagonal blocks are cleared once by the caller and never written).  With it the eight table products of the front
+// end become ONE GEMM  T = Ebd W_in^T  (the zero blocks add exact zeros to the fp32 accumulators, so T is bit-identical to
+// the per-attribute products), and the eight weight-gradient products ONE:  dW_in += G^T Ebd.
+template <typename T>
+__global__ void __launch_bounds__(256) octuple_blockdiag_kernel(const T* __restrict__ emb, T* __restrict__ out, int V, int E,
+                                                                FrontMeta meta) {
+  pdl_entry();
+  constexpr int N = Pk<T>::N;
+  typedef typename Pk<T>::raw Raw;
+  const int packs = E / N;
+  const int total = V * packs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / packs, c = (i - r * packs) * N;
+    int a = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) a += (r >= meta.row_off[k]) ? 1 : 0;
+    *reinterpret_cast<Raw*>(out + (long long)r * (8 * E) + a * E + c) = *reinterpret_cast<const Raw*>(emb + (long long)r * E + c);
+  }
+}
+
+// Gradient of the tables from the full product dEbd = G W_in ([V, 8 E] fp32): g_emb[off_a + r, c] += alpha dEbd[off_a + r, E a + c]
+__global__ void __launch_bounds__(256) octuple_blockdiag_grad_kernel(const float* __restrict__ dfull, float* __restrict__ g_emb,
+                                                                     int V, int E, float alpha, FrontMeta meta) {
+  pdl_entry();
+  const int packs = E / 4;
+  const int total = V * packs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / packs, c = (i - r * packs) * 4;
+    int a = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) a += (r >= meta.row_off[k]) ? 1 : 0;
+    const float4 v = *reinterpret_cast<const float4*>(dfull + (long long)r * (8 * E) + a * E + c);
+    float4* g = reinterpret_cast<float4*>(g_emb + (long long)r * E + c);
+    float4 o = *g;
+    o.x += alpha * v.x; o.y += alpha * v.y; o.z += alpha * v.z; o.w += alpha * v.w;
+    *g = o;
+  }
+}
+
 FrontMeta make_meta(const int* n_tokens_host, int& total) {
   FrontMeta m;
   int off = 0;
@@ -253,6 +293,28 @@ extern "C" int pb_octuple_onehot(const void* ids, int ids_int64, void* out, long
     else { PB_LAUNCH((octuple_onehot_kernel<float, int>), grid, 256, 0, st, (const int*)ids, (float*)out, M, total, meta); }
   }
   return pb_check_launch("octuple_onehot");
+}
+
+extern "C" int pb_octuple_blockdiag(const void* emb, void* out, int emb_dim, const int* n_tokens_host, int dtype, void* stream) {
+  int total;
+  const FrontMeta meta = make_meta(n_tokens_host, total);
+  const int n = dtype == PB_DTYPE_BF16 ? 8 : 4;
+  if (emb_dim <= 0 || emb_dim % n != 0) return pb_set_error("octuple_blockdiag: emb_dim must be a multiple of the 16-byte pack");
+  cudaStream_t st = PB_STREAM(stream);
+  const int grid = grid_rows((long long)total * (emb_dim / n), 256, 4);
+  if (dtype == PB_DTYPE_BF16) { PB_LAUNCH((octuple_blockdiag_kernel<bf16>), grid, 256, 0, st, (const bf16*)emb, (bf16*)out, total, emb_dim, meta); }
+  else { PB_LAUNCH((octuple_blockdiag_kernel<float>), grid, 256, 0, st, (const float*)emb, (float*)out, total, emb_dim, meta); }
+  return pb_check_launch("octuple_blockdiag");
+}
+
+extern "C" int pb_octuple_blockdiag_grad(const float* dfull, float* g_emb, int emb_dim, const int* n_tokens_host, float alpha,
+                                         void* stream) {
+  int total;
+  const FrontMeta meta = make_meta(n_tokens_host, total);
+  if (emb_dim <= 0 || emb_dim % 4 != 0) return pb_set_error("octuple_blockdiag_grad: emb_dim must be a multiple of 4");
+  const int grid = grid_rows((long long)total * (emb_dim / 4), 256, 4);
+  PB_LAUNCH(octuple_blockdiag_grad_kernel, grid, 256, 0, PB_STREAM(stream), dfull, g_emb, total, emb_dim, alpha, meta);
+  return pb_check_launch("octuple_blockdiag_grad");
 }
 
 extern "C" int pb_fill_zero(void* ptr, long long bytes, void* stream) {

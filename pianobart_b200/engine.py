@@ -274,6 +274,13 @@ class Plan:
                   C.c_void_p(mean), C.c_void_p(rstd), C.c_longlong(M), d, ntok_arr, C.c_float(1e-5), self._site(drop),
                   self.dtype, C.c_void_p(err or None))
 
+    def blockdiag(self, emb, out, ntok_arr):
+        self._add('front.expand', self.lib.pb_octuple_blockdiag, C.c_void_p(emb), C.c_void_p(out), 256, ntok_arr, self.dtype)
+
+    def blockdiag_grad(self, dfull, g_emb, ntok_arr, alpha):
+        self._add('front.dE_diag', self.lib.pb_octuple_blockdiag_grad, C.c_void_p(dfull), C.c_void_p(g_emb), 256, ntok_arr,
+                  C.c_float(alpha))
+
     def onehot(self, ids, out, M, ntok_arr):
         self._add('onehot', self.lib.pb_octuple_onehot, C.c_void_p(ids), 0, C.c_void_p(out), C.c_longlong(M), ntok_arr, self.dtype)
 
@@ -440,14 +447,18 @@ class BackboneGraph:
 
         if self.drop_p > 0.0:
             f.add_u64(self.drop_seed.data_ptr(), 1)   # new masks every forward; backward re-reads the same seed
-        # ---- fused front end (csrc/front.cu): T[off_a + r] = 16 E_a[r] W_a^T, tabulated once per forward for both streams
+        # ---- fused front end (csrc/front.cu): T[off_a + r] = 16 E_a[r] W_a^T, tabulated once per forward for both streams.
+        # The tables are first copied into their block-diagonal form Ebd [1280, 2048] (zero off-diagonal blocks, cleared once
+        # here) so that T = Ebd W_in^T is ONE GEMM instead of eight latency-bound sub-GFLOP launches; the zero blocks add exact
+        # zeros to the accumulators, T is bit-identical to the per-attribute products.
         es = self.es
         self.Tproj = self.buf('front.T', VOCAB, d)
-        off = 0
-        for a, n in enumerate(N_TOKENS):
-            f.gemm(self.W('emb') + off * 256 * es, self.W('encoder_linear.weight') + a * 256 * es,
-                   _ptr(self.Tproj, off * d), n, d, 256, 256, 2048, d, name='front.T%d' % a)
-            off += n
+        self.Ebd = self.buf('front.Ebd', VOCAB, 2048)
+        self.Ebd.zero_()
+        if self.Ebd.is_cuda:
+            torch.cuda.current_stream().synchronize()   # plans may replay on another stream
+        f.blockdiag(self.W('emb'), _ptr(self.Ebd), self.ntok_arr)
+        f.gemm(_ptr(self.Ebd), self.W('encoder_linear.weight'), _ptr(self.Tproj), VOCAB, d, 2048, 2048, 2048, d, name='front.T')
         if bw is not None:
             # G = sum over tokens of onehot(m)^T dY0[m]  ([1280, d] fp32, both streams accumulate into it)
             self.Gacc = self.buf('front.G', VOCAB, d, dtype=torch.float32)
@@ -487,17 +498,17 @@ class BackboneGraph:
             enc_back(d_enc_out, None)
         else:
             enc_back(self.d_out, None)
-        # ---- front-end parameter gradients from G:  dE_a = 16 G_a W_a ,  dW_a = G_a^T (16 E_a)   (tiny GEMMs)
+        # ---- front-end parameter gradients from G:  dW_in += G^T Ebd  (Ebd holds 16 E_a on its diagonal blocks) is one
+        # weight-gradient GEMM straight into in_linear's [d, 2048] gradient;  dE_a = 16 G_a W_a  is the diagonal of one product
+        # G W_in [1280, 2048] (8x the needed flops, 5 GFLOP) folded into the table gradients by a small kernel: 3 launches
+        # instead of 16 (each 17-23 us of launch / pipeline-fill latency for < 1 GFLOP)
         Gb = self.buf('front.Gb', VOCAB, d)
         bw.cast_from_f32(_ptr(self.Gacc), _ptr(Gb), VOCAB * d)
-        ACC = L.PB_GEMM_OUT_F32 | L.PB_GEMM_ATOMIC_ACC
-        off = 0
-        for a, n in enumerate(N_TOKENS):
-            bw.gemm(_ptr(Gb, off * d), self.W('encoder_linear.weight') + a * 256 * es, self.G('emb') + off * 256 * 4,
-                    n, 256, d, d, 2048, 256, b_mn=1, flags=ACC, alpha=16.0, name='front.dE%d' % a)
-            bw.gemm(_ptr(Gb, off * d), self.W('emb') + off * 256 * es, self.G('encoder_linear.weight') + a * 256 * 4,
-                    d, 256, n, d, 256, 2048, a_mn=1, b_mn=1, flags=ACC, name='front.dW%d' % a)
-            off += n
+        bw.wgrad(_ptr(Gb), _ptr(self.Ebd), self.G('encoder_linear.weight'), d, 2048, VOCAB, d, 2048, name='front.dW')
+        dEfull = self.buf('front.dEfull', VOCAB, 2048, dtype=torch.float32)
+        bw.gemm(_ptr(Gb), self.W('encoder_linear.weight'), _ptr(dEfull), VOCAB, 2048, d, d, 2048, 2048, b_mn=1,
+                flags=L.PB_GEMM_OUT_F32, name='front.dE')
+        bw.blockdiag_grad(_ptr(dEfull), self.G('emb'), self.ntok_arr, 16.0)
         bw.marker('grads_final', *self.lay.ranges['front'])
 
     def _stream(self, side, ids, keep, S, enc_out, enc_keep, S_enc):
