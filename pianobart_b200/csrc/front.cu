@@ -7,13 +7,13 @@
 //   in_linear(cat_a e_a) = sum_a  e_a W_a^T + b,      W_a = W[:, 256 a : 256 a + 256],
 // and because the Octuple vocabulary is tiny (1280 rows over the 8 attributes) the products are tabulated once per step:
 //   T[off_a + r] = 16 E_a[r] W_a^T                      ([1280, d] in the activation dtype: 2.6 MB bf16, L2-resident)
-// (8 small tcgen05 GEMMs recorded in the forward plan).  One kernel then gathers 8 rows of T per token, adds bias and the
+// (one tcgen05 GEMM over the block-diagonal copy of the tables, octuple_blockdiag_kernel below).  One kernel then gathers 8 rows of T per token, adds bias and the
 // position row, writes the pre-LayerNorm sum (LayerNorm's backward input) and the normalised, dropped-out output: one warp
 // per token, the row lives in registers, 16-byte accesses.  HBM traffic per token and stream: 8 ids in, 2 x d x 2 B out
 // (the 8 x d x 2 B of table rows come from L2), instead of the 2 x 4 KB round trip of X plus a [M,2048] x [2048,d] GEMM.
 //
 // Backward (engine.py): with G = sum_m onehot(m)^T dy0[m] ([1280, d], one tcgen05 GEMM against the one-hot matrix built by
-// octuple_onehot_kernel),  dE_a = 16 G_a W_a  and  dW_a = G_a^T (16 E_a)  are again tiny GEMMs - the [M,2048] gradient of
+// octuple_onehot_kernel),  dE_a = 16 G_a W_a  and  dW_a = G_a^T (16 E_a)  are two more GEMMs (block-diagonal form) - the [M,2048] gradient of
 // X, the [M,2048] x [d,2048] weight-gradient product and the scatter-add of round 1 (4.5 % of HBM peak) disappear.
 #include "pb_internal.h"
 #include "dropout.cuh"
