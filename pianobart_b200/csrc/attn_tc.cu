@@ -237,6 +237,22 @@ __device__ __forceinline__ void build_keep_bits(uint32_t* s_bits, const AttnPara
   }
 }
 
+// Tile coordinates of this CTA.  Causal problems have tiles of very different length (1..Sk/128 key blocks); CTAs are
+// dispatched in linear block order, so the tile index along the sequence is made the SLOWEST coordinate there: all heads'
+// longest tiles are issued first, the shortest last (longest-processing-time order; with the sequence index fastest the
+// last wave mixed long and short tiles).  xt counts from the longest tile for the caller to map.
+#ifndef PB_ATTN_LPT
+#define PB_ATTN_LPT 1
+#endif
+__device__ __forceinline__ void tile_coords(bool causal, int& xt, int& h, int& b) {
+  if (!PB_ATTN_LPT || !causal) { xt = blockIdx.x; h = blockIdx.y; b = blockIdx.z; return; }
+  const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const int hb = gridDim.y * gridDim.z;
+  xt = lin / hb;
+  const int r = lin - xt * hb;
+  b = r / gridDim.y;
+  h = r - b * gridDim.y;
+}
 struct Smem4 { uint8_t* t[6]; uint32_t a[6]; };
 __device__ __forceinline__ void carve(uint8_t* raw, Smem4& s, int n) {
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
@@ -283,7 +299,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   carve(smem_raw, sm, 6);  // 0 Q, 1-3 K ring, 4-5 V ring
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // causal: query blocks near the end of the sequence visit the most key blocks - schedule them first
-  const int qb = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  int xt, h, b;
+  tile_coords(p.causal != 0, xt, h, b);
+  const int qb = p.causal ? (int)gridDim.x - 1 - xt : xt;
   const int q0 = qb * AT;
   int nkb = (p.Sk + AT - 1) / AT;
   if (p.causal) nkb = min(nkb, qb + 1);
@@ -554,7 +572,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
   carve(smem_raw, sm, 6);  // 0-1 Q_a Q_b, 2-3 K ring, 4-5 V ring
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // causal: query tiles near the end of the sequence visit the most key blocks - schedule them first
-  const int qp = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  int xt, h, b;
+  tile_coords(p.causal != 0, xt, h, b);
+  const int qp = p.causal ? (int)gridDim.x - 1 - xt : xt;
   const int q0 = qp * 2 * AT;
   const int nkb_all = (p.Sk + AT - 1) / AT;
   int nk[2];
@@ -860,7 +880,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const uint32_t aK = base, aV = base + TILE_BYTES, aQ = base + 2 * TILE_BYTES, adO = aQ + NQ * QT_BYTES;
   uint8_t* gK = gen; uint8_t* gV = gen + TILE_BYTES; uint8_t* gQ = gen + 2 * TILE_BYTES; uint8_t* gdO = gQ + NQ * QT_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  int kb, h, b;
+  tile_coords(p.causal != 0, kb, h, b);     // key block 0 sees every query block: longest first
   const int k0 = kb * AT;
   const int nqb = (p.Sq + QB - 1) / QB;
   const int qb0 = p.causal ? (k0 / QB) : 0;   // causal: first 64-query block that can see key k0
@@ -1108,7 +1129,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const uint32_t aV = sm.a[5];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // causal: query blocks near the end of the sequence visit the most key blocks - schedule them first
-  const int qb = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  int xt, h, b;
+  tile_coords(p.causal != 0, xt, h, b);
+  const int qb = p.causal ? (int)gridDim.x - 1 - xt : xt;
   const int q0 = qb * AT;
   int nkb = (p.Sk + AT - 1) / AT;
   if (p.causal) nkb = min(nkb, qb + 1);
