@@ -288,6 +288,65 @@ def test_octuple_embed_bwd_vs_index_add():
         assert (tab - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
 
 
+def test_octuple_blockdiag_forms():
+    """pb_octuple_blockdiag / pb_octuple_blockdiag_grad (the block-diagonal table form that turns the eight per-attribute
+    products of PianoBart.py:60-71 into single GEMMs): exact copies into / out of the diagonal blocks, nothing else touched,
+    and T = Ebd W^T equals the per-attribute products bit for bit."""
+    from pianobart_b200.vocab import build_octuple_vocab
+    L, lib = _lib()
+    dev = 'cuda:0'
+    e2w, _ = build_octuple_vocab()
+    ntok = [len(e2w[k]) for k in e2w]
+    V = sum(ntok)
+    arr = (C.c_int * 8)(*ntok)
+    P = C.c_void_p
+    torch.manual_seed(9)
+    for dtype, code in ((torch.bfloat16, 1), (torch.float32, 0)):
+        emb = torch.randn(V, 256, device=dev).to(dtype)
+        out = torch.full((V, 2048), 7.0, device=dev, dtype=dtype)
+        L.check(lib.pb_octuple_blockdiag(P(emb.data_ptr()), P(out.data_ptr()), 256, arr, code, L.stream_ptr()), 'blockdiag')
+        ref = torch.full((V, 2048), 7.0, device=dev, dtype=dtype)
+        off = 0
+        for a, n in enumerate(ntok):
+            ref[off:off + n, a * 256:(a + 1) * 256] = emb[off:off + n]
+            off += n
+        assert torch.equal(out, ref)
+    dfull = torch.randn(V, 2048, device=dev)
+    g = torch.randn(V, 256, device=dev)
+    g0 = g.clone()
+    L.check(lib.pb_octuple_blockdiag_grad(P(dfull.data_ptr()), P(g.data_ptr()), 256, arr, C.c_float(16.0), L.stream_ptr()), 'bd_grad')
+    ref = g0.clone()
+    off = 0
+    for a, n in enumerate(ntok):
+        ref[off:off + n] += 16.0 * dfull[off:off + n, a * 256:(a + 1) * 256]
+        off += n
+    assert torch.equal(g, ref)
+    # T = Ebd W^T against the eight per-attribute products, through the tcgen05 GEMM
+    d = 1024
+    emb = (torch.randn(V, 256, device=dev) * 0.3).bfloat16()
+    W = (torch.randn(d, 2048, device=dev) * 0.05).bfloat16()
+    Ebd = torch.zeros(V, 2048, device=dev, dtype=torch.bfloat16)
+    L.check(lib.pb_octuple_blockdiag(P(emb.data_ptr()), P(Ebd.data_ptr()), 256, arr, 1, L.stream_ptr()), 'blockdiag')
+
+    def gemm(a, b, c, M, N, K, lda, ldb, ldc):
+        g_ = L.GemmDesc()
+        g_.a, g_.b, g_.c = a, b, c
+        g_.M, g_.N, g_.K, g_.lda, g_.ldb, g_.ldc = M, N, K, lda, ldb, ldc
+        g_.batch_h = g_.batch_b = 1
+        g_.alpha, g_.split_k = 1.0, 1
+        L.check(lib.pb_gemm_bf16(C.byref(g_), L.stream_ptr()), 'gemm')
+
+    T1 = torch.zeros(V, d, device=dev, dtype=torch.bfloat16)
+    T8 = torch.zeros(V, d, device=dev, dtype=torch.bfloat16)
+    gemm(Ebd.data_ptr(), W.data_ptr(), T1.data_ptr(), V, d, 2048, 2048, 2048, d)
+    off = 0
+    for a, n in enumerate(ntok):
+        gemm(emb.data_ptr() + off * 256 * 2, W.data_ptr() + a * 256 * 2, T8.data_ptr() + off * d * 2, n, d, 256, 256, 2048, d)
+        off += n
+    torch.cuda.synchronize()
+    assert torch.equal(T1, T8)
+
+
 # --------------------------------------------------------------------------- single kernels vs torch fp32
 @pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
 def test_layernorm_fwd_bwd(dtype):
