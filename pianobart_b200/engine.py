@@ -172,7 +172,7 @@ class Plan:
         """Host-side marker (no launch): run() hands the payload to `on_marker` when it reaches it."""
         self.ops.append(('marker', None, payload))
 
-    def run(self, stream=None, on_marker=None, profile=None, side_stream=None, on_op=None):
+    def run(self, stream=None, on_marker=None, profile=None, side_stream=None, on_op=None, norm_partials=None):
         """profile: optional list; every GEMM launch is then bracketed by CUDA events on the launching
         stream and (name, flops, start_event, end_event) is appended (bench.py roofline).
         side_stream: a second CUDA stream for work that has no consumer before the optimizer - the bias-gradient column sums
@@ -180,7 +180,11 @@ class Plan:
         starts when its producer has finished (event) and runs next to the critical chain (dgrad GEMMs, LayerNorm and
         attention backward): the block scheduler fills the ramp and tail of every kernel with CTAs of the other stream.
         The main stream joins the side stream at every marker (the data-parallel reducer ships the layer's gradients there),
-        at explicit join_side() points - recorded before every op that rewrites a buffer a side op reads - and at the end."""
+        at explicit join_side() points - recorded before every op that rewrites a buffer a side op reads - and at the end.
+        norm_partials: the squared-norm partials recorded behind every 'grads_final' marker (ops 'gnorm', 'gnorm_zero'; they
+        give the clip norm of the fused optimizer without a separate pass over the gradient buffer) - None: skipped,
+        'local': launched (side stream), 'zero_only': only the accumulator is cleared (data parallel: the reducer adds
+        the partial of each bucket behind its all-reduce)."""
         main = torch.cuda.current_stream() if stream is None else None
         s = C.c_void_p(main.cuda_stream if stream is None else stream)
         use_side = side_stream is not None and main is not None and profile is None
@@ -197,9 +201,13 @@ class Plan:
                 if name == 'marker' and on_marker is not None:
                     on_marker(*args)
                 continue
+            if name == 'gnorm' and norm_partials != 'local':
+                continue
+            if name == 'gnorm_zero' and norm_partials is None:
+                continue
             if on_op is not None and name == 'attn_bwd':
                 on_op(name)     # (data-parallel reducer: launch the armed gradient buckets next to this attention backward)
-            if use_side and (name in ('colsum', 'attn_prep') or name in self._side_names):
+            if use_side and (name in ('colsum', 'attn_prep', 'gnorm') or name in self._side_names):
                 ev = self._side_events[n_side] if n_side < len(self._side_events) else None
                 if ev is None:
                     ev = torch.cuda.Event()
@@ -283,6 +291,13 @@ class Plan:
 
     def onehot(self, ids, out, M, ntok_arr):
         self._add('onehot', self.lib.pb_octuple_onehot, C.c_void_p(ids), 0, C.c_void_p(out), C.c_longlong(M), ntok_arr, self.dtype)
+
+    def grads_final(self, lo, hi, grad_base, gnorm):
+        """Gradients of flat[lo:hi] are final here: marker for the data-parallel reducer + (optional, see run()) the partial
+        of the clip norm over that range (norm partials fused with the gradient buckets)."""
+        self.marker('grads_final', lo, hi)
+        if gnorm and hi > lo:
+            self._add('gnorm', self.lib.pb_sumsq, C.c_void_p(grad_base + lo * 4), C.c_longlong(hi - lo), C.c_void_p(gnorm))
 
     def fill_zero(self, ptr, nbytes):
         self._add('fill_zero', self.lib.pb_fill_zero, C.c_void_p(ptr), C.c_longlong(nbytes))
@@ -463,6 +478,10 @@ class BackboneGraph:
             # G = sum over tokens of onehot(m)^T dY0[m]  ([1280, d] fp32, both streams accumulate into it)
             self.Gacc = self.buf('front.G', VOCAB, d, dtype=torch.float32)
             bw.fill_zero(_ptr(self.Gacc), VOCAB * d * 4)
+            # squared gradient norm accumulated range by range behind the 'grads_final' markers (Plan.run(norm_partials=...))
+            self.gnorm = self.buf('gnorm', 8, dtype=torch.float32)
+            self.G_base = self.g_f32.data_ptr()
+            bw._add('gnorm_zero', bw.lib.pb_fill_zero, C.c_void_p(_ptr(self.gnorm)), C.c_longlong(4))
         # ---- encoder stream
         Me = B * self.Se
         enc_out, enc_back = self._stream('encoder', self.enc_ids, self.enc_keep, self.Se, None, None, 0)
@@ -491,7 +510,7 @@ class BackboneGraph:
             bw.wgrad(_ptr(self.dlogits), _ptr(self.out), self.G('heads.w'), VOCAB, d, Mo, VOCAB, d, name='dW_heads', side=True)
             bw.gemm(_ptr(self.dlogits), self.W('heads.w'), _ptr(self.d_out), Mo, d, VOCAB, VOCAB, d, d, b_mn=1,
                     name='dH_heads')
-            bw.marker('grads_final', *self.lay.ranges['heads'])
+            bw.grads_final(*self.lay.ranges['heads'], self.G_base, _ptr(self.gnorm))
         if self.has_dec:
             d_enc_out = self.buf('d_enc_out', Me, d)
             dec_back(self.d_out, d_enc_out)
@@ -509,7 +528,7 @@ class BackboneGraph:
         bw.gemm(_ptr(Gb), self.W('encoder_linear.weight'), _ptr(dEfull), VOCAB, 2048, d, d, 2048, 2048, b_mn=1,
                 flags=L.PB_GEMM_OUT_F32, name='front.dE')
         bw.blockdiag_grad(_ptr(dEfull), self.G('emb'), self.ntok_arr, 16.0)
-        bw.marker('grads_final', *self.lay.ranges['front'])
+        bw.grads_final(*self.lay.ranges['front'], self.G_base, _ptr(self.gnorm))
 
     def _stream(self, side, ids, keep, S, enc_out, enc_keep, S_enc):
         """Records forward ops of one stack (front end + layers); returns (output tensor,
@@ -755,7 +774,7 @@ class BackboneGraph:
                 bw.gemm(_ptr(dQKV), self.W(sa + '.wqkv'), _ptr(dnext), M, d, 3 * d, 3 * d, d, d, b_mn=1,
                         residual=_ptr(dA), ldr=d, name=ln('dH_in'))
                 dcur, dnext = dnext, dcur
-                bw.marker('grads_final', *self.lay.ranges['%s.layers.%d' % (side, l)])
+                bw.grads_final(*self.lay.ranges['%s.layers.%d' % (side, l)], self.G_base, _ptr(self.gnorm))
             # -- front end backward
             # (the gradient wrt caller-provided decoder input embeddings outlives this stream's backward: it gets its own
             # buffer - the shared scratch dA is rewritten by the encoder stream's backward that follows)
@@ -772,7 +791,7 @@ class BackboneGraph:
                 bw.wgrad(_ptr(onehot), _ptr(dY0), _ptr(self.Gacc), VOCAB, d, M, VOCAB, d, name=nm('dG'), side=True)
             else:
                 self.d_dec_in = dY0      # gradient wrt the caller's decoder input embeddings
-            bw.marker('grads_final', *self.lay.ranges['%s.front' % side])
+            bw.grads_final(*self.lay.ranges['%s.front' % side], self.G_base, _ptr(self.gnorm))
 
         return out, record_backward
 

@@ -23,13 +23,14 @@ import torch.distributed as dist
 
 
 class BucketReducer:
-    def __init__(self, flat_grad, group=None, target_bytes=None, comm_stream=None):
+    def __init__(self, flat_grad, group=None, target_bytes=None, comm_stream=None, after_reduce=None):
         if target_bytes is None:
             target_bytes = int(os.environ.get('PIANOBART_B200_BUCKET_MB', '32')) << 20
         self.g = flat_grad
         self.group = group
         self.target = max(1, target_bytes // flat_grad.element_size())
         self.comm_stream = comm_stream
+        self.after_reduce = after_reduce   # called as after_reduce(lo, hi) on the comm stream behind each bucket's all-reduce
         self.pending = None          # (lo, hi) contiguous range whose gradients are final but not yet reduced
         self.issued = []             # ranges handed to all_reduce, in order
         self.works = []
@@ -57,6 +58,8 @@ class BucketReducer:
             self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(view, group=self.group)
+                if self.after_reduce is not None:
+                    self.after_reduce(lo, hi)
         else:
             self.works.append(dist.all_reduce(view, group=self.group, async_op=True))
 

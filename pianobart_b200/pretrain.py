@@ -57,14 +57,19 @@ class FusedAdamW:
             self.v = torch.zeros_like(pb._flat)
             self.gnorm_sq = torch.zeros(1, device=pb._flat.device, dtype=torch.float32)
 
-    def step(self, grad_scale=1.0):
+    def step(self, grad_scale=1.0, gnorm=None):
+        """gnorm: a device fp32 scalar that already holds the squared norm of the (all-reduced) gradient buffer - the
+        partials the training step accumulates range by range during backward (engine.Plan.grads_final); None: one pass
+        over the buffer here."""
         self._ensure()
         pb, lib, s = self.pb, L.lib(), L.stream_ptr()
         lay = pb.layout
         n = lay.size
         self.step_count += 1
-        self.gnorm_sq.zero_()
-        L.check(lib.pb_sumsq(C.c_void_p(pb._grad.data_ptr()), C.c_longlong(n), C.c_void_p(self.gnorm_sq.data_ptr()), s), 'sumsq')
+        if gnorm is None:
+            gnorm = self.gnorm_sq
+            gnorm.zero_()
+            L.check(lib.pb_sumsq(C.c_void_p(pb._grad.data_ptr()), C.c_longlong(n), C.c_void_p(gnorm.data_ptr()), s), 'sumsq')
         bf16 = pb.pb_dtype == E.PB_BF16
         for lo, hi, scale in ((0, lay.emb_end, 16.0), (lay.emb_end, n, 1.0)):
             wp = C.c_void_p(pb._wact.data_ptr() + lo * 2) if bf16 else C.c_void_p(None)
@@ -72,7 +77,7 @@ class FusedAdamW:
                                  C.c_void_p(self.v.data_ptr() + lo * 4), C.c_void_p(pb._grad.data_ptr() + lo * 4), wp,
                                  C.c_longlong(hi - lo), C.c_float(self.lr), C.c_float(self.betas[0]),
                                  C.c_float(self.betas[1]), C.c_float(self.eps), C.c_float(self.wd), self.step_count,
-                                 C.c_void_p(self.gnorm_sq.data_ptr()), C.c_float(self.max_grad_norm),
+                                 C.c_void_p(gnorm.data_ptr()), C.c_float(self.max_grad_norm),
                                  C.c_float(grad_scale), C.c_float(scale), s), 'adamw')
         if not bf16:
             pb.mark_weights_dirty()
@@ -115,6 +120,13 @@ class PretrainStep:
         self.graph = pb._graph(B, S, S, True, True, dropout)
         self._pack_gen = pb._pack_gen
         self._cg, self._cg_n, self._graph_ok, self._eager_runs = None, 0, True, 0
+        # clip norm from partials accumulated behind the 'grads_final' markers of the backward plan / the all-reduce of each
+        # gradient bucket instead of a separate pass over the 0.7 GB gradient buffer after backward - only when
+        # those ranges tile the whole flat buffer exactly once.  Measured (profiles/r2_summary.md section 16): data parallel
+        # 29.85 vs 29.91 ms per step (on), single GPU 28.69 vs 28.62 ms (the partials on the side stream compete with the
+        # power-capped GEMMs for as long as the separate pass takes) - so the default is on for world > 1 only;
+        # PIANOBART_B200_NORM_PARTIALS=1|0 forces it.
+        self._norm_partials = False
         # north-star fusion 3 (bf16 mode): MLM heads + masked CE in one kernel (csrc/heads_ce_tc.cu)
         self.fused_ce = (pb.pb_dtype == E.PB_BF16 and self.graph.d % 64 == 0
                          and os.environ.get('PIANOBART_B200_FUSED_CE', '1') != '0')
@@ -150,6 +162,15 @@ class PretrainStep:
         # the kernel normalises by sum(w); rescale when the caller's normaliser differs
         self.grad_scale = sum(self.loss_weights) / self.loss_norm
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        if self.graph.bwd is not None and os.environ.get('PIANOBART_B200_NORM_PARTIALS', '1' if self.world > 1 else '0') != '0':
+            rng = sorted((a[1], a[2]) for name, fn, a in self.graph.bwd.ops if name == 'marker' and a and a[0] == 'grads_final')
+            pos = 0
+            for lo, hi in rng:
+                if lo != pos:
+                    break
+                pos = hi
+            else:
+                self._norm_partials = (pos == pb.layout.size and hasattr(self.graph, 'gnorm'))
         self.launches = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 24 * 4
@@ -226,15 +247,13 @@ class PretrainStep:
                 n = self._cg_n
                 GRAPH_REPLAYED_LAUNCHES[0] += n
                 if self.opt is not None:
-                    self.opt.step()
-                    n += 3
+                    n += self._opt_step()
                 self.launches += n
                 return n
         self._eager_runs += 1
         n = self._enqueue(train, profile)
         if train and self.opt is not None:
-            self.opt.step()
-            n += 3
+            n += self._opt_step()
         self.launches += n
         return n
 
@@ -291,12 +310,24 @@ class PretrainStep:
                 pb._grad.zero_()
             if self.world > 1:
                 from .parallel import BucketReducer
-                red = BucketReducer(pb._grad, self.pg, comm_stream=self.comm_stream)
-                n += g.bwd.run(on_marker=red.on_final, profile=profile, side_stream=g.side_stream(), on_op=red.on_attention)
+                red = BucketReducer(pb._grad, self.pg, comm_stream=self.comm_stream,
+                                    after_reduce=self._bucket_norm if self._norm_partials else None)
+                n += g.bwd.run(on_marker=red.on_final, profile=profile, side_stream=g.side_stream(), on_op=red.on_attention,
+                               norm_partials='zero_only' if self._norm_partials else None)
                 red.finish()
             else:
-                n += g.bwd.run(profile=profile, side_stream=g.side_stream())
+                n += g.bwd.run(profile=profile, side_stream=g.side_stream(),
+                               norm_partials='local' if self._norm_partials else None)
         return n
+
+    def _bucket_norm(self, lo, hi):
+        """Data parallel: squared norm of an all-reduced bucket, queued behind its all-reduce on the comm stream."""
+        L.check(self.lib.pb_sumsq(C.c_void_p(self.pb._grad.data_ptr() + lo * 4), C.c_longlong(hi - lo),
+                                  C.c_void_p(self.graph.gnorm.data_ptr()), L.stream_ptr()), 'sumsq')
+
+    def _opt_step(self):
+        self.opt.step(gnorm=self.graph.gnorm) if self._norm_partials else self.opt.step()
+        return 2 if self._norm_partials else 3
 
     def queue_stats(self):
         """Queues the D2H copy of the step's 24 scalars (behind the step, on the current stream) into one of two pinned
