@@ -61,7 +61,7 @@ class BucketReducer:
                 if self.after_reduce is not None:
                     self.after_reduce(lo, hi)
         else:
-            self.works.append(dist.all_reduce(view, group=self.group, async_op=True))
+            self.works.append((dist.all_reduce(view, group=self.group, async_op=True), lo, hi))
 
     def on_final(self, tag, lo, hi):
         """Plan marker callback: gradients of flat[lo:hi] will not be touched again by this backward."""
@@ -83,8 +83,10 @@ class BucketReducer:
             self._issue(*self.pending)
             self.pending = None
         self.on_attention()
-        for w in self.works:
+        for w, lo, hi in self.works:
             w.wait()
+            if self.after_reduce is not None:
+                self.after_reduce(lo, hi)
         self.works = []
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)

@@ -24,7 +24,11 @@ def _worker_buckets(rank, world, port, out):
     from pianobart_b200.parallel import BucketReducer
     lay = ParamLayout(64, 2, 2, 128, 32, True)
     g = torch.full((lay.size,), float(rank + 1))
-    red = BucketReducer(g, None, target_bytes=64 * 1024)
+    norm_sq = [0.0]
+
+    def partial(lo, hi):     # the clip-norm partial of an all-reduced bucket (pretrain.PretrainStep._bucket_norm on the GPU)
+        norm_sq[0] += float((g[lo:hi].double() ** 2).sum())
+    red = BucketReducer(g, None, target_bytes=64 * 1024, after_reduce=partial)
     # marker order of the backward plan: heads, decoder layers (last first), decoder front, encoder layers, encoder front, front
     order = ['heads', 'decoder.layers.1', 'decoder.layers.0', 'decoder.front', 'encoder.layers.1', 'encoder.layers.0',
              'encoder.front', 'front']
@@ -35,6 +39,7 @@ def _worker_buckets(rank, world, port, out):
     for lo, hi in issued:
         cover[lo:hi] += 1
     ok = bool((cover == 1).all()) and bool((g == sum(range(1, world + 1))).all()) and len(issued) < len(order)
+    ok = ok and abs(norm_sq[0] - float((g.double() ** 2).sum())) <= 1e-9 * norm_sq[0]   # partials = norm of the reduced buffer
     out[rank] = ok
     dist.destroy_process_group()
 

@@ -108,6 +108,19 @@ def test_param_layout_fused_groups_are_contiguous():
         assert b == c
 
 
+def test_param_layout_ranges_tile_the_flat_buffer():
+    """The 'grads_final' ranges of the backward plan (gradient buckets, clip-norm partials) must cover the flat parameter
+    buffer exactly once - PretrainStep checks the same property on the recorded plan before it trusts the partial norms."""
+    from pianobart_b200.engine import ParamLayout
+    for args in ((64, 2, 2, 128, 32, True), (1024, 8, 8, 2048, 1024, True), (128, 1, 3, 256, 64, False)):
+        lay = ParamLayout(*args)
+        pos = 0
+        for lo, hi in sorted(lay.ranges.values()):
+            assert lo == pos and hi > lo
+            pos = hi
+        assert pos == lay.size
+
+
 def test_wgrad_split_k_wave_model():
     """engine.choose_split_k picks the split measured fastest on a 148-SM B200 (tools/gpu_wgrad_split.py) and never
     exceeds a quarter of the k-blocks."""
