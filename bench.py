@@ -425,7 +425,7 @@ def main():
             line['decode'] = decode_bench(lm, pb, dev, peaks)
         except Exception as e:  # the headline metric must still be printed
             line['decode'] = {'error': repr(e)[:200]}
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:     # (rank 0 at N = 1 only: the other ranks of a multi-GPU run have left by now)
         cb = cpu_baseline(batch=2, steps=2, warmup=1)
         line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     print(json.dumps(line))
