@@ -368,8 +368,14 @@ def _read_varlen(buf, i):
 
 
 def read_midi(path):
-    """Minimal SMF reader: notes (per track / channel / program, FIFO note-off pairing), set-tempo and time-signature meta
-    events, channel 10 as drums.  Enough to feed score_to_octuple without miditoolkit."""
+    """Minimal SMF reader (format 0 / 1): what `miditoolkit.midi.parser.MidiFile(path)` gives convert.py:336 / demo.py:62 -
+    ticks_per_beat, instruments with notes in ticks, set-tempo and time-signature changes.  miditoolkit is absent from this
+    image (and unpinned by the reference), so its published loading rule - the one it shares with pretty_midi - is restated:
+    a note-off (or note-on with velocity 0) closes EVERY open note-on of its (channel, pitch) that started on an earlier
+    tick, note-ons of the same tick stay open if something was closed (else they are dropped with the key); a note belongs
+    to the channel's program at its note-OFF; instruments are keyed (program, channel, track) in order of their first closed
+    note, channel 10 is drums, the track name is the instrument name.  Running status, sysex and unknown meta events are
+    skipped over.  (Parity with the library itself is unpinned: no copy of it exists here.)"""
     with open(path, 'rb') as f:
         buf = f.read()
     if buf[:4] != b'MThd':
@@ -388,7 +394,7 @@ def read_midi(path):
         t, status = 0, 0
         program = [0] * 16
         open_notes = {}
-        insts = {}
+        insts = {}           # (program, channel) -> Instrument, insertion-ordered (one track at a time)
         name = ''
         while j < end:
             dt, j = _read_varlen(buf, j)
@@ -408,6 +414,8 @@ def read_midi(path):
                     score.time_signature_changes.append(TimeSignature(numerator=data[0], denominator=2 ** data[1], time=t))
                 elif kind == 0x03:
                     name = data.decode('latin1')
+                    for inst in insts.values():
+                        inst.name = name
                 continue
             if status in (0xf0, 0xf7):
                 ln, j = _read_varlen(buf, j)
@@ -422,18 +430,22 @@ def read_midi(path):
             d1, d2 = buf[j], buf[j + 1]
             j += 2
             if hi == 0x90 and d2 > 0:
-                open_notes.setdefault((ch, d1), []).append((t, d2, program[ch]))
+                open_notes.setdefault((ch, d1), []).append((t, d2))
             elif hi == 0x80 or (hi == 0x90 and d2 == 0):
                 q = open_notes.get((ch, d1))
-                if q:
-                    t0, vel, prog = q.pop(0)
-                    key = (ch, prog)
-                    if key not in insts:
-                        insts[key] = Instrument(program=prog, is_drum=(ch == 9), name=name)
-                    insts[key].notes.append(Note(start=t0, end=max(t, t0 + 1), pitch=d1, velocity=vel))
-        for key in sorted(insts):
-            insts[key].notes.sort(key=lambda n: (n.start, n.pitch))
-            score.instruments.append(insts[key])
+                if q is not None:
+                    close = [(t0, vel) for t0, vel in q if t0 != t]
+                    keep = [(t0, vel) for t0, vel in q if t0 == t]
+                    for t0, vel in close:
+                        key = (program[ch], ch)
+                        if key not in insts:
+                            insts[key] = Instrument(program=program[ch], is_drum=(ch == 9), name=name)
+                        insts[key].notes.append(Note(start=t0, end=t, pitch=d1, velocity=vel))
+                    if close and keep:
+                        open_notes[(ch, d1)] = keep
+                    else:
+                        del open_notes[(ch, d1)]
+        score.instruments.extend(insts.values())
     score.tempo_changes.sort(key=lambda c: c.time)
     score.time_signature_changes.sort(key=lambda c: c.time)
     return score

@@ -101,7 +101,7 @@ def test_midi_file_round_trip(tmp_path):
         assert again.ticks_per_beat == 480
         # a decoded score is already on the codec's grid: onsets, programs, pitches, velocities and time signatures survive the
         # file exactly.  (Durations do not always: when two notes of one pitch overlap on a channel a MIDI file cannot say
-        # which note-off ends which note - the reader pairs first-in first-out.)
+        # which note-off ends which note - the reader closes every open note of the pitch at the first note-off, like miditoolkit.)
         e1, e2 = K.score_to_octuple(decoded), K.score_to_octuple(again)
         assert [r[:4] + r[5:7] for r in e1] == [r[:4] + r[5:7] for r in e2]
         assert max(abs(a[7] - b[7]) for a, b in zip(e1, e2)) <= 1              # tempo passes through microseconds per beat
@@ -155,3 +155,56 @@ def test_convert_entry_point_builds_dataset_blocks(task, tmp_path):
             assert y.shape == x.shape[:2] + (1,) and y.max() <= 6
         else:
             assert y.shape == (x.shape[0],) and set(y.tolist()) <= {0, 1, 2, 3}
+
+def _smf(fmt, div, tracks):
+    import struct
+    return b'MThd' + struct.pack('>IHHH', 6, fmt, len(tracks), div) + b''.join(
+        b'MTrk' + struct.pack('>I', len(t)) + t for t in tracks)
+
+
+def test_midi_reader_on_hand_built_files(tmp_path):
+    """Bytes written by hand (not by write_midi): running status, note-on velocity 0 as note-off, multi-byte delta times, sysex
+    and unknown meta events, programs, channel 10, and the miditoolkit / pretty_midi pairing rule for same-pitch overlaps."""
+    conductor = bytes([0x00, 0xff, 0x58, 0x04, 3, 2, 24, 8,                       # 3/4 at tick 0
+                       0x00, 0xff, 0x51, 0x03, 0x07, 0xa1, 0x20,                  # 500000 us per beat = 120 bpm
+                       0x00, 0xff, 0x7f, 0x02, 0x01, 0x02,                        # sequencer-specific meta: skipped
+                       0x87, 0x40, 0xff, 0x51, 0x03, 0x0f, 0x42, 0x40,            # delta 960 (two-byte varlen): 60 bpm
+                       0x00, 0xff, 0x2f, 0x00])
+    piano = bytes([0x00, 0xff, 0x03, 0x05]) + b'Right' + bytes([
+        0x00, 0xc0, 0x05,                                                          # program 5 on channel 0
+        0x00, 0xf0, 0x03, 0x7e, 0x7f, 0xf7,                                        # sysex: skipped
+        0x00, 0x90, 60, 100,                                                       # t=0    C4 on
+        0x00, 64, 90,                                                              #        E4 on   (running status)
+        0x78, 60, 0,                                                               # t=120  C4 off as note-on velocity 0 (running)
+        0x00, 60, 80,                                                              # t=120  C4 on again on the same tick
+        0x3c, 60, 70,                                                              # t=180  C4 on: overlaps the previous C4
+        0x3c, 0x80, 60, 0,                                                         # t=240  ONE note-off closes BOTH open C4s
+        0x00, 64, 0,                                                               # t=240  E4 off (running status 0x80)
+        0x00, 0xc0, 0x07,                                                          # program change to 7 ...
+        0x00, 0x90, 67, 50,                                                        # t=240  G4 on
+        0x00, 0xc0, 0x09,                                                          # ... and to 9 before its note-off
+        0x1e, 0x80, 67, 0,                                                         # t=270  G4 off: the note belongs to program 9
+        0x00, 0x80, 72, 0,                                                         # spurious note-off: ignored
+        0x00, 0xff, 0x2f, 0x00])
+    drums = bytes([0x00, 0x99, 36, 110, 0x1e, 0x89, 36, 0, 0x00, 0xff, 0x2f, 0x00])   # channel 10
+    path = str(tmp_path / 'hand.mid')
+    open(path, 'wb').write(_smf(1, 480, [conductor, piano, drums]))
+    sc = K.read_midi(path)
+    assert sc.ticks_per_beat == 480
+    assert [(c.numerator, c.denominator, c.time) for c in sc.time_signature_changes] == [(3, 4, 0)]
+    assert [(round(c.tempo, 6), c.time) for c in sc.tempo_changes] == [(120.0, 0), (60.0, 960)]
+    assert [(i.program, i.is_drum, i.name) for i in sc.instruments] == [(5, False, 'Right'), (9, False, 'Right'), (0, True, '')]
+    notes = lambda inst: [(n.start, n.end, n.pitch, n.velocity) for n in inst.notes]
+    assert notes(sc.instruments[0]) == [(0, 120, 60, 100), (120, 240, 60, 80), (180, 240, 60, 70), (0, 240, 64, 90)]
+    assert notes(sc.instruments[1]) == [(240, 270, 67, 50)]
+    assert notes(sc.instruments[2]) == [(0, 30, 36, 110)]
+    # format 0: everything in one track
+    open(path, 'wb').write(_smf(0, 96, [conductor[:-4] + piano[9:]]))
+    sc0 = K.read_midi(path)
+    assert sc0.ticks_per_beat == 96 and len(sc0.tempo_changes) == 2 and sum(len(i.notes) for i in sc0.instruments) == 5
+    # the reader feeds the encoder: one Octuple row per note, programs kept (drums: max_inst + 1 = 129, convert.py:214)
+    rows = K.score_to_octuple(sc)
+    assert len(rows) == 6 and sorted({r[2] for r in rows}) == [5, 9, 129]
+    with pytest.raises(ValueError):
+        open(path, 'wb').write(b'RIFF' + bytes(20))
+        K.read_midi(path)
